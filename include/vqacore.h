@@ -1,0 +1,349 @@
+/*
+ * vqacore.h — C ABI of libvqacore_sm100a.so: the B200 (sm_100a) reasoning core shared by the
+ * reference's two models, ODA (object-difference attention) and CoR2 (chain of reasoning).
+ *
+ * The reference (bupt-cist/vqa-playground-pytorch) is pure Python over ATen and has no FFI
+ * layer; the boundary a maintainer binds is therefore this header, one entry point per
+ * reference building block on the hot path.  Each declaration cites the
+ * reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions (all entry points):
+ *   - plain C: POD structs, device pointers, sizes; no torch / C++ types cross the boundary;
+ *   - the CALLER owns every buffer (inputs, outputs, workspace, gradient buffers); the library
+ *     never allocates, frees or retains device memory past return;
+ *   - all work is enqueued on the stream passed in (a cudaStream_t cast to void*); no hidden
+ *     synchronisation, no default-stream use, safe to capture in a CUDA graph;
+ *   - return 0 on success, a negative VQA_E* code otherwise; vqa_last_error() gives a
+ *     thread-local message; no C++ exception crosses the boundary;
+ *   - tensors are row-major fp32 unless a struct says otherwise; "ld*" are row strides in
+ *     elements;
+ *   - there is NO CPU fallback: without an sm_100 device every compute call fails with
+ *     VQA_ENODEVICE / a CUDA launch error.
+ *
+ * Dropout (train mode).  The reference calls F.dropout(p) on the INPUT of every MyLinear /
+ * MyConv1d (config/CoR2.py:77-78,115-116; config/ODA.py:94-95,128-129).  Here the mask is
+ * never stored: it is regenerated from a counter-based Philox4x32-10 stream,
+ *     keep(seed, layer, idx) = Philox(key=seed, ctr=(idx>>2, layer, 0))[idx&3] >= floor(p*2^32),
+ * idx = row-major linear index of the element in the logical tensor the reference drops,
+ * scale 1/(1-p).  oracle/philox.py is the CPU twin used by the parity tests.
+ */
+#ifndef VQACORE_H_
+#define VQACORE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQA_ABI_VERSION 1
+
+enum {
+  VQA_OK = 0,
+  VQA_EINVAL = -1,      /* bad argument (shape, null pointer, unsupported combination) */
+  VQA_ECUDA = -2,       /* CUDA runtime / launch error, see vqa_last_error() */
+  VQA_ENODEVICE = -3,   /* no sm_100 device */
+  VQA_EWORKSPACE = -4   /* workspace too small */
+};
+
+enum { VQA_ACT_NONE = 0, VQA_ACT_RELU = 1, VQA_ACT_SIGMOID = 2 };
+
+/* GEMM arithmetic. FP32_SIMT: fp32 FMA on CUDA cores (exact-fp32 parity path).
+ * TF32X3 / TF32 / BF16: tcgen05 tensor cores, fp32 accumulate in TMEM. */
+enum { VQA_MATH_FP32_SIMT = 0, VQA_MATH_TF32X3 = 1, VQA_MATH_TF32 = 2, VQA_MATH_BF16 = 3 };
+
+#define VQA_MAX_GROUPS 8
+#define VQA_GLIMPSES 4
+
+int vqa_abi_version(void);
+const char* vqa_last_error(void);
+/* 0 when an sm_100 device is current, VQA_ENODEVICE otherwise. */
+int vqa_device_check(void);
+/* sizeof() of a parameter struct by name ("vqa_linear_fwd_params", ...); 0 if unknown. Lets a
+ * binding written in another language verify its mirror of the layouts below. */
+size_t vqa_sizeof(const char* struct_name);
+
+typedef struct {
+  float p;            /* drop probability; 0 disables */
+  uint32_t layer;     /* Philox counter word 2 */
+  uint64_t seed;      /* Philox key; change it every step */
+} vqa_dropout;
+
+/* ------------------------------------------------------------------------------------------
+ * Grouped linear:  Y_g = act( dropout_g(X_g) . W_g^T + b_g ),  g < groups.
+ * Replaces MyLinear.forward (config/CoR2.py:106-119 == config/ODA.py:123-136) and
+ * MyConv1d.forward with kernel_size 1 (config/CoR2.py:72-88 == config/ODA.py:89-105; the two
+ * transposes vanish: a k=1 conv over [B,N,Cin] is this GEMM with M = B*N), and putils.Linear
+ * (putils/__init__.py:25-30).  Groups share M,K,N,act,p and differ in pointers and dropout
+ * layer; they run in one launch (e.g. the four 2400->310 question projections of CoR2,
+ * the four glimpse linears of MyATT, config/CoR2.py:147-152).
+ * dropout index of X_g[m,k] is  drop_index_base[g] + m*K + k.
+ */
+typedef struct {
+  int groups;
+  int64_t M, K, N;
+  int act;
+  int math;
+  float p;
+  uint64_t seed;
+  const float* X[VQA_MAX_GROUPS];  int64_t ldx[VQA_MAX_GROUPS];
+  const float* W[VQA_MAX_GROUPS];            /* [N,K] row-major (nn.Linear / Conv1d k=1 layout) */
+  const float* b[VQA_MAX_GROUPS];            /* [N] or NULL */
+  float* Y[VQA_MAX_GROUPS];        int64_t ldy[VQA_MAX_GROUPS];
+  uint32_t layer[VQA_MAX_GROUPS];
+  uint64_t drop_index_base[VQA_MAX_GROUPS];
+} vqa_linear_fwd_params;
+int vqa_linear_fwd(const vqa_linear_fwd_params* p, void* stream);
+
+/* Backward of the grouped linear.  dZ = dY (.) act'(Y);  dW_g (+)= dZ^T . dropout(X);
+ * db_g (+)= colsum(dZ);  dX_g (+)= (dZ . W_g) (.) mask/(1-p)   (dX_g NULL: skipped, as for the
+ * graph inputs v and q).  accumulate_w / accumulate_x choose "+=" over "=" so that weight
+ * gradients can land directly in a flat data-parallel gradient buffer.
+ * Autograd of F.linear / F.conv1d / F.dropout / relu / sigmoid in the reference.
+ */
+typedef struct {
+  int groups;
+  int64_t M, K, N;
+  int act;
+  int math;
+  float p;
+  uint64_t seed;
+  int accumulate_w;
+  int accumulate_x;
+  const float* X[VQA_MAX_GROUPS];  int64_t ldx[VQA_MAX_GROUPS];
+  const float* W[VQA_MAX_GROUPS];
+  const float* Y[VQA_MAX_GROUPS];  int64_t ldy[VQA_MAX_GROUPS];   /* forward output (for act') */
+  const float* dY[VQA_MAX_GROUPS]; int64_t lddy[VQA_MAX_GROUPS];
+  float* dW[VQA_MAX_GROUPS];
+  float* db[VQA_MAX_GROUPS];
+  float* dX[VQA_MAX_GROUPS];       int64_t lddx[VQA_MAX_GROUPS];
+  uint32_t layer[VQA_MAX_GROUPS];
+  uint64_t drop_index_base[VQA_MAX_GROUPS];
+} vqa_linear_bwd_params;
+int vqa_linear_bwd(const vqa_linear_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mutan (bilinear) fusion:  Y[m,:] = sum_{r<R} (X1[m,:].W1_r^T + b1_r) (.) H2_r[m / rows_per_h2, :]
+ * with H2_r = X2.W2_r^T + b2_r  ([Mh,F], Mh = M / rows_per_h2).
+ * Replaces MutanFusion.forward (putils/__init__.py:232-238) and its per-sample bmul loop
+ * (putils/__init__.py:98-104): rows_per_h2 = N regions when x1 is [B,N,.] and x2 is [B,.]
+ * (fusion_vq1/2, config/CoR2.py:214,219), 1 for fusion_final (config/CoR2.py:233,
+ * config/ODA.py:236).
+ * H1 (optional, [R,M,F]) and H2 ([R,Mh,F]) are caller-owned stashes used by the backward.
+ */
+typedef struct {
+  int R;
+  int64_t M, K1, K2, F;
+  int64_t rows_per_h2;
+  int math;
+  const float* X1; int64_t ldx1;
+  const float* X2; int64_t ldx2;
+  const float* W1[VQA_MAX_GROUPS]; const float* b1[VQA_MAX_GROUPS];
+  const float* W2[VQA_MAX_GROUPS]; const float* b2[VQA_MAX_GROUPS];
+  float* H1;      /* [R,M,F] or NULL */
+  float* H2;      /* [R,Mh,F] */
+  float* Y; int64_t ldy;
+} vqa_mutan_fwd_params;
+int vqa_mutan_fwd(const vqa_mutan_fwd_params* p, void* stream);
+
+typedef struct {
+  int R;
+  int64_t M, K1, K2, F;
+  int64_t rows_per_h2;
+  int math;
+  int accumulate_w;
+  int accumulate_x1;
+  int accumulate_x2;
+  const float* X1; int64_t ldx1;
+  const float* X2; int64_t ldx2;
+  const float* W1[VQA_MAX_GROUPS];
+  const float* W2[VQA_MAX_GROUPS];
+  const float* H1;   /* [R,M,F] from forward */
+  const float* H2;   /* [R,Mh,F] from forward */
+  const float* dY; int64_t lddy;
+  float* dH2;        /* workspace [R,Mh,F] */
+  float* dW1[VQA_MAX_GROUPS]; float* db1[VQA_MAX_GROUPS];
+  float* dW2[VQA_MAX_GROUPS]; float* db2[VQA_MAX_GROUPS];
+  float* dX1; int64_t lddx1;     /* NULL: skipped */
+  float* dX2; int64_t lddx2;     /* NULL: skipped */
+} vqa_mutan_bwd_params;
+int vqa_mutan_bwd(const vqa_mutan_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Region softmax attention + pooling — the core of MyATT.forward
+ * (config/CoR2.py:137-154 == config/ODA.py:154-171):
+ *   z[b,i,g]   = sum_c Wc[g,c] * dropout(fuse)[b,i,c] + bc[g]        conv_att (Conv1d Ff->G, k=1)
+ *   alpha[b,:,g] = softmax over regions i                            (af='softmax', dim=1)
+ *   pooled[b,g,:] = sum_i alpha[b,i,g] * x[b,i,:]                    bmatmul, putils/__init__.py:89-95
+ * The G glimpse linears that follow are a grouped vqa_linear_fwd on pooled.
+ * dropout index of fuse[b,i,c] is (b*N+i)*Ff + c.
+ */
+typedef struct {
+  int64_t B, N, Ff, D;
+  vqa_dropout drop;
+  const float* fuse;     /* [B,N,Ff] */
+  const float* Wc;       /* [G,Ff] (Conv1d weight [G,Ff,1]) */
+  const float* bc;       /* [G] */
+  const float* x;        /* [B,N,D] */
+  float* alpha;          /* [B,N,G] */
+  float* pooled;         /* [B,G,D] */
+} vqa_region_softmax_pool_fwd_params;
+int vqa_region_softmax_pool_fwd(const vqa_region_softmax_pool_fwd_params* p, void* stream);
+
+/* Backward (SURVEY.md §8a "K-pool"):
+ *   dalpha[b,i,g] = <dpooled[b,g,:], x[b,i,:]> + (g==0 ? dalpha0_ext[b] : 0)
+ *   dz = alpha (.) (dalpha - sum_i alpha*dalpha)
+ *   dWc (+)= sum_{b,i} dz[b,i,g]*dropout(fuse)[b,i,c];  dbc (+)= sum dz
+ *   dfuse[b,i,c] = (sum_g dz[b,i,g] Wc[g,c]) * mask/(1-p)
+ *   dx[b,i,:] (+)= sum_g alpha[b,i,g] dpooled[b,g,:]      (dx NULL: x is a graph input)
+ * dalpha0_ext ([B] or NULL) carries CoR2's d(s)/d(alpha) term from vqa_cor_compound_bwd.
+ */
+typedef struct {
+  int64_t B, N, Ff, D;
+  vqa_dropout drop;
+  int accumulate_w;
+  int accumulate_x;
+  const float* fuse; const float* Wc;
+  const float* x; const float* alpha;
+  const float* dpooled;        /* [B,G,D] */
+  const float* dalpha0_ext;    /* [B] or NULL */
+  float* dalpha;               /* workspace [B,N,G] */
+  float* dz;                   /* workspace [B,N,G]; holds dz on return */
+  float* dWc; float* dbc;
+  float* dfuse;                /* [B,N,Ff] or NULL */
+  float* dx;                   /* [B,N,D] or NULL */
+} vqa_region_softmax_pool_bwd_params;
+int vqa_region_softmax_pool_bwd(const vqa_region_softmax_pool_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CoR2 compound objects.  Replaces decare_cat + the alpha-weighted sum
+ * (config/CoR2.py:191-199, :215-216), which materialise [B,N,N,D]:
+ *   v2_cat[b,i,j,:] = v[b,i,:]*g1[b,:] + v[b,j,:]*g2[b,:];  v2[b,j,:] = sum_i alpha1_0[b,i] v2_cat[b,i,j,:]
+ * collapsed exactly to   v2[b,j,:] = vt[b,:]*g1[b,:] + s[b]*v[b,j,:]*g2[b,:],
+ *   vt = sum_i alpha_i v_i  (= pooled[:,0,:] of att1),  s = sum_i alpha_i  (kept, not assumed 1).
+ */
+typedef struct {
+  int64_t B, N, D;
+  const float* x;          /* [B,N,D] block2 */
+  const float* pooled;     /* [B,G,D]; glimpse 0 is vt */
+  const float* alpha;      /* [B,N,G]; glimpse 0 gives s */
+  const float* g1;         /* [B,D] */
+  const float* g2;         /* [B,D] */
+  float* v2;               /* [B,N,D] */
+} vqa_cor_compound_fwd_params;
+int vqa_cor_compound_fwd(const vqa_cor_compound_fwd_params* p, void* stream);
+
+/* Backward: Dbar = sum_j dv2[j,:];  dg1 = vt*Dbar;  dpooled[b,0,:] += g1*Dbar;
+ *   dg2 = s * sum_j v[j,:]*dv2[j,:];  dalpha0_ext[b] = sum_j <v[j,:]*g2, dv2[j,:]>. */
+typedef struct {
+  int64_t B, N, D;
+  const float* x; const float* pooled; const float* alpha;
+  const float* g1; const float* g2;
+  const float* dv2;        /* [B,N,D] */
+  float* dg1; float* dg2;  /* [B,D] */
+  float* dpooled;          /* [B,G,D]; glimpse-0 slice is ACCUMULATED into */
+  float* dalpha0_ext;      /* [B] */
+} vqa_cor_compound_bwd_params;
+int vqa_cor_compound_bwd(const vqa_cor_compound_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ODA object-difference attention logits + region softmax + pooling.  Replaces the 36x36
+ * Python pair loop, the stack/transpose copy and conv_att over N*H channels
+ * (config/ODA.py:216-226 with fuse_dim = N*310, :192):
+ *   z[b,i,g] = bc[g] + sum_{j,k} W[g,j*H+k] * dropout(vq)[b,i,j*H+k],  vq = (vl[b,i,k]-vl[b,j,k])*ql[b,k]
+ * The [B,N,N*H] tensor is never formed.  train = 0: factorised form
+ * (z = sum_k ql*vl[i]*Wsum[k] + const_i, Wsum = sum_j W[g,j,:]); train = 1: every (i,j,k) term is
+ * produced in registers with its Philox mask (index ((b*N+i)*N+j)*H+k).
+ */
+typedef struct {
+  int64_t B, N, H, D;
+  int train;
+  vqa_dropout drop;
+  const float* vl;       /* [B,N,H] */
+  const float* ql;       /* [B,H] */
+  const float* W;        /* [G,N*H] */
+  const float* bc;       /* [G] */
+  const float* x;        /* [B,N,D] */
+  float* wsum;           /* workspace [G,H] (eval) */
+  float* alpha;          /* [B,N,G] */
+  float* pooled;         /* [B,G,D] */
+} vqa_oda_pair_attn_fwd_params;
+int vqa_oda_pair_attn_fwd(const vqa_oda_pair_attn_fwd_params* p, void* stream);
+
+typedef struct {
+  int64_t B, N, H, D;
+  int train;
+  vqa_dropout drop;
+  int accumulate_w;
+  const float* vl; const float* ql; const float* W;
+  const float* x; const float* alpha;
+  const float* wsum;          /* from forward (eval) */
+  const float* dpooled;       /* [B,G,D] */
+  float* dalpha;              /* workspace [B,N,G] */
+  float* dz;                  /* workspace [B,N,G]; holds dz on return */
+  float* dwsum;               /* workspace [G,H] (eval) */
+  float* dW; float* dbc;
+  float* dvl;                 /* [B,N,H] */
+  float* dql;                 /* [B,H] */
+} vqa_oda_pair_attn_bwd_params;
+int vqa_oda_pair_attn_bwd(const vqa_oda_pair_attn_bwd_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss: KLDivLoss(size_average=False)(log_softmax(logits,1), target)  (train.py:536-544), fused
+ * with its gradient:  loss_rows[b] = sum_c a*(log a - log_softmax(x)_c);
+ * dlogits = grad_scale * (softmax(x) * sum_c a - a).  The scalar loss is sum(loss_rows).
+ */
+typedef struct {
+  int64_t B, C;
+  float grad_scale;
+  const float* logits;   /* [B,C] */
+  const float* target;   /* [B,C] */
+  float* loss_rows;      /* [B] */
+  float* dlogits;        /* [B,C] or NULL */
+} vqa_kld_logsoftmax_params;
+int vqa_kld_logsoftmax_fwd_bwd(const vqa_kld_logsoftmax_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-model plans: one call enqueues every kernel of Model.forward / its backward
+ * (config/CoR2.py:201-237, config/ODA.py:200-240), nothing from ATen in between.
+ * Parameters are passed as a table of pointers in the reference's state_dict order
+ * (seq2vec.* excluded): CoR2 62 tensors, ODA 38.  `grads` uses the same order.
+ */
+#define VQA_COR2_NPARAMS 62
+#define VQA_ODA_NPARAMS 38
+
+typedef struct {
+  int64_t B, N, C;           /* batch, regions, answers */
+  int train;                 /* 1: dropout on (Philox, `seed`) */
+  int math;
+  uint64_t seed;
+  const float* v;            /* [B,N,2048] */
+  const float* q;            /* [B,2400] */
+  const float* const* params;
+  float* logits;             /* [B,C] */
+  float* alpha1;             /* [B,N,G] */
+  float* alpha2;             /* [B,N,G]  (ODA: unused) */
+  float* v2;                 /* [B,N,2048] (ODA: unused) */
+  void* workspace; size_t workspace_bytes;
+} vqa_model_fwd_params;
+
+typedef struct {
+  vqa_model_fwd_params fwd;  /* same values as the forward call (workspace holds its stash) */
+  const float* dlogits;      /* [B,C] */
+  float* const* grads;       /* table of gradient pointers, state_dict order */
+  int accumulate;            /* 1: grads += , 0: grads = */
+} vqa_model_bwd_params;
+
+size_t vqa_cor2_workspace_bytes(int64_t B, int64_t N, int64_t C);
+int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream);
+int vqa_cor2_bwd(const vqa_model_bwd_params* p, void* stream);
+
+size_t vqa_oda_workspace_bytes(int64_t B, int64_t N, int64_t C);
+int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream);
+int vqa_oda_bwd(const vqa_model_bwd_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQACORE_H_ */

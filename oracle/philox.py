@@ -1,0 +1,88 @@
+"""Counter-based random bits shared bit-for-bit by the oracle and the CUDA kernels.
+
+TEST INFRASTRUCTURE ONLY (see oracle/README.md): nothing in the product path imports this
+file.  The CUDA twin is `csrc/philox.cuh`; both implement Philox4x32-10 (Salmon et al.,
+SC'11) with the standard constants, so that a dropout mask generated here on the CPU is
+the mask the kernels regenerate in registers.
+
+Why it exists: the reference draws its dropout masks from torch's global generator
+(`F.dropout`, /root/reference/config/CoR2.py:78, :116; config/ODA.py:95, :129), which cannot
+be reproduced inside a fused kernel.  Train-mode parity is therefore checked by
+monkey-patching the reference's `F.dropout` with `dropout_mask` below.
+
+Mask definition (the contract, restated in include/vqacore.h):
+    word(seed, layer, idx) = Philox4x32-10(key = (seed_lo, seed_hi),
+                                           ctr = (q_lo, q_hi, layer, 0))[idx & 3],  q = idx >> 2
+    keep(seed, layer, idx) = word >= floor(p * 2**32)
+`idx` is the row-major linear index of the element in the LOGICAL tensor the reference
+applies dropout to (e.g. (b*N + i)*D + c for compress_v's input, ((b*N+i)*N+j)*H+k for
+ODA's pairwise tensor, config/ODA.py:222).
+"""
+import numpy as np
+
+_M0 = np.uint64(0xD2511F53)
+_M1 = np.uint64(0xCD9E8D57)
+_W0 = 0x9E3779B9
+_W1 = 0xBB67AE85
+_MASK32 = np.uint64(0xFFFFFFFF)
+_SH32 = np.uint64(32)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10. Counter words are uint64 arrays holding 32-bit values,
+    keys are python ints. Returns four uint32 arrays."""
+    c0 = np.asarray(c0, dtype=np.uint64)
+    c1 = np.broadcast_to(np.asarray(c1, dtype=np.uint64), c0.shape)
+    c2 = np.broadcast_to(np.asarray(c2, dtype=np.uint64), c0.shape)
+    c3 = np.broadcast_to(np.asarray(c3, dtype=np.uint64), c0.shape)
+    k0 &= 0xFFFFFFFF
+    k1 &= 0xFFFFFFFF
+    for _ in range(10):
+        p0 = _M0 * c0
+        p1 = _M1 * c2
+        hi0, lo0 = p0 >> _SH32, p0 & _MASK32
+        hi1, lo1 = p1 >> _SH32, p1 & _MASK32
+        n0 = hi1 ^ c1 ^ np.uint64(k0)
+        n2 = hi0 ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, lo1, n2, lo0
+        k0 = (k0 + _W0) & 0xFFFFFFFF
+        k1 = (k1 + _W1) & 0xFFFFFFFF
+    return (c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32))
+
+
+def words(seed, layer, n, start=0, stream=0):
+    """uint32 word for each linear index in [start, start+n)."""
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    q = idx >> np.uint64(2)
+    r = philox4x32_10(q & _MASK32, q >> _SH32, np.uint64(layer & 0xFFFFFFFF), np.uint64(stream),
+                      int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
+    sel = (idx & np.uint64(3)).astype(np.int64)
+    out = np.where(sel == 0, r[0], np.where(sel == 1, r[1], np.where(sel == 2, r[2], r[3])))
+    return out.astype(np.uint32)
+
+
+def threshold(p):
+    return min(int(np.floor(float(p) * 4294967296.0)), 0xFFFFFFFF)
+
+
+def dropout_mask(seed, layer, shape, p):
+    """float32 {0,1} keep-mask of `shape` (row-major linear index = element index)."""
+    n = int(np.prod(shape))
+    keep = words(seed, layer, n) >= np.uint32(threshold(p))
+    return keep.astype(np.float32).reshape(shape)
+
+
+def uniform(seed, layer, shape, stream=1):
+    """float32 uniform in [0,1): top 24 bits of the word (stream 1 keeps it disjoint from masks)."""
+    n = int(np.prod(shape))
+    w = words(seed, layer, n, stream=stream)
+    return ((w >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)).reshape(shape)
+
+
+def pseudo_normal(seed, layer, shape):
+    """Irwin-Hall(4) shifted/scaled to zero mean, unit variance. Version-independent synthetic data."""
+    n = int(np.prod(shape))
+    acc = np.zeros(n, dtype=np.float32)
+    for s in range(4):
+        acc += uniform(seed, layer, (n,), stream=2 + s)
+    return ((acc - np.float32(2.0)) * np.float32(np.sqrt(3.0))).reshape(shape)

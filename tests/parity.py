@@ -1,0 +1,96 @@
+"""Shared helpers for the parity tests (test infrastructure; may import oracle/)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import reasoning_core as rc
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = ["oda_eval_b4", "oda_train_b4", "cor2_eval_b4", "cor2_train_b4", "cor2_eval_b2_small_ans"]
+
+# Parity metric of SURVEY.md §8d: max|new-ref| / max(max|ref|, floor), floor = 1e-6 * largest gradient max-abs,
+# so structurally-zero gradients (conv_att biases, fusion_vq biases) compare as ~0 instead of noise/noise.
+FP32_TOL = 1e-4
+
+
+def rel_err(new, ref, floor=0.0):
+    new = torch.as_tensor(new).detach().double().cpu()
+    ref = torch.as_tensor(ref).detach().double().cpu()
+    assert new.shape == ref.shape, (new.shape, ref.shape)
+    denom = max(ref.abs().max().item(), floor, 1e-30)
+    return (new - ref).abs().max().item() / denom
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = {k[5:]: z[k].item() for k in z.files if k.startswith("meta.")}
+    return z, meta
+
+
+def golden_grad_names(z):
+    return sorted({k[5:].rsplit(".", 1)[0] for k in z.files if k.startswith("grad.")})
+
+
+def golden_grad_floor(z):
+    return 1e-6 * max(float(z[f"grad.{n}.absmax"]) for n in golden_grad_names(z) if not n.startswith("__"))
+
+
+def compare_grad_to_golden(z, name, g, floor):
+    """g: full gradient tensor from the implementation under test. Returns the §8d error."""
+    g = g.detach().float().cpu()
+    absmax = float(z[f"grad.{name}.absmax"])
+    denom = max(absmax, floor, 1e-30)
+    if f"grad.{name}.full" in z.files:
+        ref = torch.from_numpy(z[f"grad.{name}.full"])
+        return (g.reshape(ref.shape) - ref).abs().max().item() / denom
+    stride = int(z[f"grad.{name}.stride"])
+    ref = torch.from_numpy(z[f"grad.{name}.sample"])
+    got = g.reshape(-1)[::stride][:ref.numel()]
+    e_samp = (got - ref).abs().max().item() / denom
+    e_norm = abs(g.double().norm().item() - float(z[f"grad.{name}.l2"])) / max(float(z[f"grad.{name}.l2"]),
+                                                                                  floor * np.sqrt(g.numel()), 1e-30)
+    return max(e_samp, e_norm)
+
+
+def flatten_alpha(alpha_dict):
+    out = {}
+    for k, val in alpha_dict.items():
+        if isinstance(val, (tuple, list)):
+            out[k] = torch.cat([t.detach() for t in val], dim=2)
+        else:
+            out[k] = val.detach()
+    return out
+
+
+def oracle_case(model, B, num_ans, N=36, train_seed=None, weight_seed=10, input_seed=1234, want_input_grads=False,
+                gain=1.0):
+    sd = rc.synth_state_dict(model, num_ans, seed=weight_seed, num_regions=N, gain=gain)
+    v, q, a = rc.synth_inputs(B, N, num_ans, seed=input_seed)
+    drop = rc.no_drop if train_seed is None else rc.PhiloxDrop(train_seed)
+    ref = rc.step(model, sd, v, q, a, drop=drop, num_regions=N, want_input_grads=want_input_grads)
+    return sd, (v, q, a), ref
+
+
+def run_cuda_model(model, sd, v, q, a, N=36, train_seed=None, precision="fp32", device="cuda:0"):
+    """fwd + KLD loss + bwd through the product's public API (config.<model>.Model)."""
+    import importlib
+    cf = importlib.import_module("vqa_playground_pytorch_b200.config." + model)
+    from vqa_playground_pytorch_b200 import ops
+    num_ans = a.shape[1]
+    m = cf.Model(None, num_ans, num_regions=N, precision=precision)
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    m = m.to(device)
+    m.train(train_seed is not None)
+    m.fixed_seed = train_seed
+    sample = {"v": v.to(device), "q_idxes": q.to(device)}
+    logits = m(sample)
+    rows = ops.kld_loss_rows(logits, a.to(device))
+    loss = rows.sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {n: p.grad.detach().cpu() for n, p in m.named_parameters()}
+    return {"logits": logits.detach().cpu(), "loss": loss.detach().cpu(), "alpha_dict":
+            {k: (tuple(t.cpu() for t in val) if isinstance(val, tuple) else val.cpu()) for k, val in m.alpha_dict.items()},
+            "grads": grads, "model": m}

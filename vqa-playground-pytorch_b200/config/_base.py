@@ -1,0 +1,51 @@
+"""Shared Model plumbing for config/CoR2.py and config/ODA.py (reference Model.forward contracts)."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class CoreModel(nn.Module):
+    """Holds the parameter containers (same names/order as the reference so state_dict matches) and
+    runs Model.forward as ONE call into libvqacore (ops.ModelCoreFn).
+
+    Extra constructor arguments, all defaulting to the reference's behaviour:
+      num_regions  N (reference hard-codes 36: config/CoR2.py:203, config/ODA.py:202,222)
+      precision    GEMM arithmetic: 'fp32' (CUDA-core FMA), 'tf32x3', 'tf32', 'bf16' (tcgen05)
+      seq2vec      question encoder module; default passes sample['q_idxes'] through as the
+                   2400-d embedding (blocks.QuestionPassThrough)
+    """
+    MODEL = None
+
+    def _finish_init(self, layer_names, precision):
+        self.precision = precision
+        # dropout call-site ids in forward-call order == oracle/reasoning_core.py *_LAYERS
+        for i, name in enumerate(layer_names):
+            mod = self.get_submodule(name)
+            mod.layer_id = i
+        for m in self.modules():
+            if hasattr(m, "math"):
+                m.math = precision
+        self.alpha_dict = {}
+        self.grad_sink = None          # set by parallel.DataParallelEngine
+        self.fixed_seed = None         # tests: pin the Philox key of the next train-mode forward
+
+    def core_parameters(self):
+        """Parameters in the reference's state_dict order, seq2vec.* excluded."""
+        return [p for n, p in self.named_parameters() if not n.startswith("seq2vec.")]
+
+    def _run_core(self, sample):
+        v = sample['v']
+        q = self.seq2vec(sample['q_idxes'])
+        if v.numel() % (self.num_regions * 2048) != 0:
+            raise ValueError("sample['v'] with %d elements cannot be viewed as [-1, %d, 2048]" %
+                             (v.numel(), self.num_regions))
+        train = bool(self.training)
+        seed = 0
+        if train:
+            seed = self.fixed_seed if self.fixed_seed is not None else ops.next_seed()
+        return ops.ModelCoreFn.apply(self.MODEL, v, q, train, self.precision, seed, self.num_regions,
+                                     self.num_classes, self.grad_sink, *self.core_parameters())
+
+    def __call__(self, *input, **kwargs):
+        return super().__call__(*input, **kwargs)

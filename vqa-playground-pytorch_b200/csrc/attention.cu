@@ -1,0 +1,170 @@
+// vqa_region_softmax_pool_{fwd,bwd}: the MyATT core (config/CoR2.py:137-154 == config/ODA.py:154-171).
+#include "attention.cuh"
+
+namespace vqa {
+
+__global__ void softmax_regions_kernel(int64_t N, float* __restrict__ alpha) {
+  extern __shared__ float z_s[];
+  const int64_t b = blockIdx.x;
+  for (int64_t t = threadIdx.x; t < N * G; t += blockDim.x) z_s[t] = alpha[b * N * G + t];
+  __syncthreads();
+  softmax_regions_smem(z_s, (int)N);
+  __syncthreads();
+  for (int64_t t = threadIdx.x; t < N * G; t += blockDim.x) alpha[b * N * G + t] = z_s[t];
+}
+
+// pooled[b,g,c] = sum_i alpha[b,i,g]*x[b,i,c].  HBM-bound: x is read exactly once, 128-bit loads,
+// every thread keeps UNROLL independent loads in flight.  grid = (cdiv(D/4,128), B).
+constexpr int POOL_THREADS = 128;
+__global__ void __launch_bounds__(POOL_THREADS)
+pool_fwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* __restrict__ alpha,
+                float* __restrict__ pooled) {
+  extern __shared__ float al_s[];   // [N*G]
+  const int64_t b = blockIdx.y;
+  for (int64_t t = threadIdx.x; t < N * G; t += POOL_THREADS) al_s[t] = alpha[b * N * G + t];
+  __syncthreads();
+  const int64_t c = ((int64_t)blockIdx.x * POOL_THREADS + threadIdx.x) * 4;
+  if (c >= D) return;
+  float4 acc[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* xb = x + b * N * D + c;
+  constexpr int UNROLL = 6;
+  int64_t i = 0;
+  for (; i + UNROLL <= N; i += UNROLL) {
+    float4 xv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) xv[u] = ld_stream4(xb + (i + u) * D);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const float4 a = *reinterpret_cast<const float4*>(&al_s[(i + u) * G]);
+      const float av[G] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        acc[g].x = fmaf(av[g], xv[u].x, acc[g].x);
+        acc[g].y = fmaf(av[g], xv[u].y, acc[g].y);
+        acc[g].z = fmaf(av[g], xv[u].z, acc[g].z);
+        acc[g].w = fmaf(av[g], xv[u].w, acc[g].w);
+      }
+    }
+  }
+  for (; i < N; ++i) {
+    const float4 xv = ld_stream4(xb + i * D);
+    const float4 a = *reinterpret_cast<const float4*>(&al_s[i * G]);
+    const float av[G] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      acc[g].x = fmaf(av[g], xv.x, acc[g].x);
+      acc[g].y = fmaf(av[g], xv.y, acc[g].y);
+      acc[g].z = fmaf(av[g], xv.z, acc[g].z);
+      acc[g].w = fmaf(av[g], xv.w, acc[g].w);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) *reinterpret_cast<float4*>(&pooled[(b * G + g) * D + c]) = acc[g];
+}
+
+int launch_pool_fwd(int64_t B, int64_t N, int64_t D, const float* x, const float* alpha, float* pooled,
+                    cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(D / 4, POOL_THREADS), (unsigned)B);
+  pool_fwd_kernel<<<grid, POOL_THREADS, (size_t)N * G * sizeof(float), st>>>(N, D, x, alpha, pooled);
+  return check_launch("pool_fwd");
+}
+
+// dalpha[b,i,g] = <dpooled[b,g,:], x[b,i,:]> (+ ext for g=0);  dx[b,i,:] (+)= sum_g alpha[b,i,g] dpooled[b,g,:].
+// One warp per region: the second (and last) pass over x in the backward.  grid = (cdiv(N,8), B).
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* __restrict__ alpha,
+                const float* __restrict__ dpooled, const float* __restrict__ dalpha0_ext, float* __restrict__ dalpha,
+                float* __restrict__ dx, int accumulate_x) {
+  const int64_t b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= N) return;
+  float a[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) a[g] = alpha[(b * N + i) * G + g];
+  float dot[G] = {0.f, 0.f, 0.f, 0.f};
+  const float* xr = x + (b * N + i) * D;
+  const float* dp = dpooled + b * G * D;
+  float* dxr = dx ? dx + (b * N + i) * D : nullptr;
+  for (int64_t c = lane * 4; c < D; c += 128) {
+    const float4 xv = ld_stream4(xr + c);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dp + g * D + c));
+      dot[g] = fmaf(xv.x, d.x, fmaf(xv.y, d.y, fmaf(xv.z, d.z, fmaf(xv.w, d.w, dot[g]))));
+      o.x = fmaf(a[g], d.x, o.x); o.y = fmaf(a[g], d.y, o.y);
+      o.z = fmaf(a[g], d.z, o.z); o.w = fmaf(a[g], d.w, o.w);
+    }
+    if (dxr) {
+      float4* dst = reinterpret_cast<float4*>(dxr + c);
+      if (accumulate_x) {
+        const float4 old = *dst;
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *dst = o;
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) dot[g] = warp_sum(dot[g]);
+  if (lane == 0) {
+    if (dalpha0_ext) dot[0] += dalpha0_ext[b];
+#pragma unroll
+    for (int g = 0; g < G; ++g) dalpha[(b * N + i) * G + g] = dot[g];
+  }
+}
+
+int launch_pool_bwd(int64_t B, int64_t N, int64_t D, const float* x, const float* alpha, const float* dpooled,
+                    const float* dalpha0_ext, float* dalpha, float* dx, int accumulate_x, cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(N, 8), (unsigned)B);
+  pool_bwd_kernel<<<grid, 256, 0, st>>>(N, D, x, alpha, dpooled, dalpha0_ext, dalpha, dx, accumulate_x);
+  return check_launch("pool_bwd");
+}
+
+}  // namespace vqa
+
+using namespace vqa;
+
+extern "C" int vqa_region_softmax_pool_fwd(const vqa_region_softmax_pool_fwd_params* p, void* stream) {
+  VQA_REQUIRE(p != nullptr, "vqa_region_softmax_pool_fwd: null params");
+  VQA_REQUIRE(p->B >= 0 && p->N >= 1 && p->Ff >= 1 && p->D >= 4 && p->D % 4 == 0,
+              "vqa_region_softmax_pool_fwd: bad shape B=%lld N=%lld Ff=%lld D=%lld (D must be a multiple of 4)",
+              (long long)p->B, (long long)p->N, (long long)p->Ff, (long long)p->D);
+  VQA_REQUIRE(p->fuse && p->Wc && p->bc && p->x && p->alpha && p->pooled, "vqa_region_softmax_pool_fwd: null pointer");
+  VQA_REQUIRE(p->drop.p >= 0.0f && p->drop.p < 1.0f, "vqa_region_softmax_pool_fwd: dropout p");
+  const size_t smem = (size_t)(G * p->Ff + p->N * G) * sizeof(float);
+  VQA_REQUIRE(smem <= 200 * 1024, "vqa_region_softmax_pool_fwd: Ff=%lld too large for shared memory", (long long)p->Ff);
+  if (p->B == 0) return VQA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0)};
+  auto kern = att_logits_softmax_kernel<FuseGeneric>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<(unsigned)p->B, ATT_THREADS, smem, st>>>(fs, p->N, p->Ff, p->Wc, p->bc, p->alpha);
+  VQA_TRY(check_launch("att_logits_softmax"));
+  return launch_pool_fwd(p->B, p->N, p->D, p->x, p->alpha, p->pooled, st);
+}
+
+extern "C" int vqa_region_softmax_pool_bwd(const vqa_region_softmax_pool_bwd_params* p, void* stream) {
+  VQA_REQUIRE(p != nullptr, "vqa_region_softmax_pool_bwd: null params");
+  VQA_REQUIRE(p->B >= 0 && p->N >= 1 && p->Ff >= 1 && p->D >= 4 && p->D % 4 == 0,
+              "vqa_region_softmax_pool_bwd: bad shape");
+  VQA_REQUIRE(p->fuse && p->Wc && p->x && p->alpha && p->dpooled && p->dalpha && p->dz && p->dWc,
+              "vqa_region_softmax_pool_bwd: null pointer");
+  if (p->B == 0) return VQA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VQA_TRY(launch_pool_bwd(p->B, p->N, p->D, p->x, p->alpha, p->dpooled, p->dalpha0_ext, p->dalpha, p->dx,
+                          p->accumulate_x, st));
+  if (!p->accumulate_w) {
+    cudaMemsetAsync(p->dWc, 0, (size_t)G * p->Ff * sizeof(float), st);
+    if (p->dbc) cudaMemsetAsync(p->dbc, 0, G * sizeof(float), st);
+  }
+  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0)};
+  const int64_t groups = p->B < 2 * (int64_t)sm_count() ? p->B : 2 * (int64_t)sm_count();
+  dim3 grid((unsigned)groups, (unsigned)cdiv(p->Ff, ATT_THREADS));
+  const size_t smem = (size_t)2 * p->N * G * sizeof(float);
+  att_logits_softmax_bwd_kernel<FuseGeneric, false><<<grid, ATT_THREADS, smem, st>>>(
+      fs, p->B, p->N, p->Ff, p->Wc, p->alpha, p->dalpha, p->dz, p->dWc, p->dbc, p->dfuse, nullptr);
+  return check_launch("att_logits_softmax_bwd");
+}

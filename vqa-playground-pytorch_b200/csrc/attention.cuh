@@ -1,0 +1,170 @@
+// Region-softmax attention + pooling kernels shared by MyATT (both models) and ODA's
+// object-difference attention.  See include/vqacore.h for the maths and the reference lines.
+#pragma once
+#include "common.cuh"
+
+namespace vqa {
+
+constexpr int ATT_THREADS = 256;
+
+// ---- sources of the "fuse" row the attention logits are taken from ---------------------------
+// Generic: a materialised [B,N,Ff] tensor with input dropout (MyATT.conv_att, config/CoR2.py:140).
+struct FuseGeneric {
+  const float* fuse; int64_t N, Ff; Drop d;
+  __device__ __forceinline__ float mul(int64_t b, int64_t i, int64_t c) const {
+    return d.mul((uint64_t)((b * N + i) * Ff + c));
+  }
+  __device__ __forceinline__ float raw(int64_t b, int64_t i, int64_t c) const { return fuse[(b * N + i) * Ff + c]; }
+};
+// ODA, eval mode: fuse_eff[b,i,k] = vl[b,i,k]*ql[b,k] against Wsum[g,k] = sum_j W[g,j*H+k]
+// (the -vl[b,j,k] part is constant over i and cancels in the region softmax).
+struct FuseOdaEval {
+  const float* vl; const float* ql; int64_t N, Ff;   // Ff == H
+  __device__ __forceinline__ float mul(int64_t, int64_t, int64_t) const { return 1.0f; }
+  __device__ __forceinline__ float raw(int64_t b, int64_t i, int64_t c) const {
+    return vl[(b * N + i) * Ff + c] * ql[b * Ff + c];
+  }
+};
+
+// softmax over regions of z[N][G] held in shared memory, one warp per glimpse, in place
+__device__ __forceinline__ void softmax_regions_smem(float* z, int N) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < G) {
+    float mx = -INFINITY;
+    for (int i = lane; i < N; i += 32) mx = fmaxf(mx, z[i * G + warp]);
+    mx = warp_max(mx);
+    float s = 0.0f;
+    for (int i = lane; i < N; i += 32) {
+      const float e = expf(z[i * G + warp] - mx);
+      z[i * G + warp] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int i = lane; i < N; i += 32) z[i * G + warp] *= inv;
+  }
+}
+
+// z[b,i,g] = sum_c Wc[g,c]*fuse~[b,i,c] + bc[g]; alpha = softmax_i z.   grid = B.
+// dynamic smem: G*Ff (weights) + N*G (logits)
+template <class FS>
+__global__ void __launch_bounds__(ATT_THREADS)
+att_logits_softmax_kernel(FS fs, int64_t N, int64_t Ff, const float* __restrict__ Wc, const float* __restrict__ bc,
+                          float* __restrict__ alpha) {
+  extern __shared__ float smem[];
+  float* w_s = smem;
+  float* z_s = smem + G * Ff;
+  const int64_t b = blockIdx.x;
+  for (int64_t t = threadIdx.x; t < G * Ff; t += ATT_THREADS) w_s[t] = Wc[t];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t i = warp; i < N; i += ATT_THREADS / 32) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int64_t c = lane; c < Ff; c += 32) {
+      const float f = fs.raw(b, i, c) * fs.mul(b, i, c);
+      a0 = fmaf(w_s[c], f, a0);
+      a1 = fmaf(w_s[Ff + c], f, a1);
+      a2 = fmaf(w_s[2 * Ff + c], f, a2);
+      a3 = fmaf(w_s[3 * Ff + c], f, a3);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    if (lane == 0) {
+      z_s[i * G + 0] = a0 + bc[0];
+      z_s[i * G + 1] = a1 + bc[1];
+      z_s[i * G + 2] = a2 + bc[2];
+      z_s[i * G + 3] = a3 + bc[3];
+    }
+  }
+  __syncthreads();
+  softmax_regions_smem(z_s, (int)N);
+  __syncthreads();
+  for (int64_t t = threadIdx.x; t < N * G; t += ATT_THREADS) alpha[b * N * G + t] = z_s[t];
+}
+
+// in-place z -> alpha for logits already in global memory (ODA train path). grid = B, smem N*G
+__global__ void softmax_regions_kernel(int64_t N, float* __restrict__ alpha);
+
+int launch_pool_fwd(int64_t B, int64_t N, int64_t D, const float* x, const float* alpha, float* pooled,
+                    cudaStream_t st);
+// dalpha (into dz buffer) and optional dx
+int launch_pool_bwd(int64_t B, int64_t N, int64_t D, const float* x, const float* alpha, const float* dpooled,
+                    const float* dalpha0_ext, float* dalpha, float* dx, int accumulate_x, cudaStream_t st);
+
+// ---- backward of logits+softmax --------------------------------------------------------------
+// grid = (sample groups, cdiv(Ff, ATT_THREADS)); each thread owns one column c for its samples.
+// dalpha is read by every CTA; dz_out is written by the blockIdx.y == 0 CTAs only (separate buffers).
+// ODA_EVAL: dfuse is redirected into dvl/dql.
+template <class FS, bool ODA_EVAL>
+__global__ void __launch_bounds__(ATT_THREADS)
+att_logits_softmax_bwd_kernel(FS fs, int64_t B, int64_t N, int64_t Ff, const float* __restrict__ Wc,
+                              const float* __restrict__ alpha, const float* __restrict__ dalpha,
+                              float* __restrict__ dz_out, float* __restrict__ dWc,
+                              float* __restrict__ dbc, float* __restrict__ dfuse, float* __restrict__ dql) {
+  extern __shared__ float smem[];
+  float* dz_s = smem;            // [N*G]
+  float* al_s = smem + N * G;    // [N*G]
+  __shared__ float dot_s[G];
+  const int64_t c = (int64_t)blockIdx.y * ATT_THREADS + threadIdx.x;
+  const bool active = c < Ff;
+  float w[G] = {0.f, 0.f, 0.f, 0.f}, accw[G] = {0.f, 0.f, 0.f, 0.f};
+  float accb = 0.0f;
+  if (active)
+#pragma unroll
+    for (int g = 0; g < G; ++g) w[g] = Wc[g * Ff + c];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int64_t t = threadIdx.x; t < N * G; t += ATT_THREADS) {
+      dz_s[t] = dalpha[b * N * G + t];
+      al_s[t] = alpha[b * N * G + t];
+    }
+    __syncthreads();
+    if (warp < G) {
+      float s = 0.0f;
+      for (int i = lane; i < N; i += 32) s = fmaf(al_s[i * G + warp], dz_s[i * G + warp], s);
+      s = warp_sum(s);
+      if (lane == 0) dot_s[warp] = s;
+    }
+    __syncthreads();
+    for (int64_t t = threadIdx.x; t < N * G; t += ATT_THREADS) dz_s[t] = al_s[t] * (dz_s[t] - dot_s[t % G]);
+    __syncthreads();
+    if (blockIdx.y == 0) {
+      for (int64_t t = threadIdx.x; t < N * G; t += ATT_THREADS) {
+        dz_out[b * N * G + t] = dz_s[t];
+        if (t < G) {
+          float s = 0.0f;
+          for (int64_t i = 0; i < N; ++i) s += dz_s[i * G + t];
+          accb += s;      // thread t < G accumulates dbc[t]
+        }
+      }
+    }
+    if (active) {
+      float dq = 0.0f;
+      for (int64_t i = 0; i < N; ++i) {
+        const float4 z4 = *reinterpret_cast<const float4*>(&dz_s[i * G]);
+        const float mul = fs.mul(b, i, c);
+        const float f = fs.raw(b, i, c) * mul;
+        accw[0] = fmaf(z4.x, f, accw[0]);
+        accw[1] = fmaf(z4.y, f, accw[1]);
+        accw[2] = fmaf(z4.z, f, accw[2]);
+        accw[3] = fmaf(z4.w, f, accw[3]);
+        const float df = (z4.x * w[0] + z4.y * w[1] + z4.z * w[2] + z4.w * w[3]) * mul;
+        if constexpr (ODA_EVAL) {
+          // fuse_eff = vl*ql: dvl = df*ql, dql += df*vl
+          const float qv = fs.ql[b * Ff + c], vv = fs.vl[(b * N + i) * Ff + c];
+          dfuse[(b * N + i) * Ff + c] = df * qv;
+          dq = fmaf(df, vv, dq);
+        } else {
+          if (dfuse) dfuse[(b * N + i) * Ff + c] = df;
+        }
+      }
+      if constexpr (ODA_EVAL) dql[b * Ff + c] = dq;
+    }
+  }
+  if (active)
+#pragma unroll
+    for (int g = 0; g < G; ++g) atomicAdd(&dWc[g * Ff + c], accw[g]);
+  if (blockIdx.y == 0 && threadIdx.x < G && dbc) atomicAdd(&dbc[threadIdx.x], accb);
+}
+
+}  // namespace vqa

@@ -1,0 +1,127 @@
+// Shared device/host helpers for libvqacore_sm100a.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/vqacore.h"
+
+namespace vqa {
+
+// ------------------------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);          // cudaGetLastError -> VQA_ECUDA
+int sm_count();
+
+#define VQA_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      vqa::set_error(__VA_ARGS__);        \
+      return VQA_EINVAL;                  \
+    }                                     \
+  } while (0)
+
+#define VQA_TRY(expr)                     \
+  do {                                    \
+    int _rc = (expr);                     \
+    if (_rc != VQA_OK) return _rc;        \
+  } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr int G = VQA_GLIMPSES;
+
+// ------------------------------------------------------------------------------- Philox4x32-10
+// Twin of oracle/philox.py (test infrastructure); the contract is in include/vqacore.h.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// The four words covering linear indices 4q .. 4q+3.
+__device__ __forceinline__ uint4 philox_quad(uint64_t seed, uint32_t layer, uint64_t q) {
+  return philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), layer, 0u),
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint32_t layer, uint64_t idx) {
+  const uint4 r = philox_quad(seed, layer, idx >> 2);
+  const uint32_t s = (uint32_t)idx & 3u;
+  return s == 0 ? r.x : (s == 1 ? r.y : (s == 2 ? r.z : r.w));
+}
+
+// Device-side view of one dropout call site.
+struct Drop {
+  uint64_t seed;
+  uint64_t base;      // added to the element index
+  uint32_t layer;
+  uint32_t thr;       // keep iff word >= thr
+  float scale;        // 1/(1-p)
+  int on;
+  // multiplier (0 or scale) for logical element idx
+  __device__ __forceinline__ float mul(uint64_t idx) const {
+    if (!on) return 1.0f;
+    return philox_word(seed, layer, base + idx) >= thr ? scale : 0.0f;
+  }
+};
+
+static inline uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;   // floor
+}
+
+static inline Drop make_drop(float p, uint64_t seed, uint32_t layer, uint64_t base, int train_on = 1) {
+  Drop d;
+  d.seed = seed;
+  d.base = base;
+  d.layer = layer;
+  d.on = (train_on && p > 0.0f) ? 1 : 0;
+  d.thr = drop_threshold(p);
+  d.scale = d.on ? 1.0f / (1.0f - p) : 1.0f;
+  return d;
+}
+
+// ------------------------------------------------------------------------------- small device utils
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float act_apply(int act, float z) {
+  if (act == VQA_ACT_RELU) return fmaxf(z, 0.0f);
+  if (act == VQA_ACT_SIGMOID) return 1.0f / (1.0f + __expf(-z));
+  return z;
+}
+// derivative expressed through the OUTPUT y = act(z)
+__device__ __forceinline__ float act_grad(int act, float y) {
+  if (act == VQA_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+  if (act == VQA_ACT_SIGMOID) return y * (1.0f - y);
+  return 1.0f;
+}
+
+// streaming 128-bit load that does not allocate in L1 (data read once)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+}  // namespace vqa

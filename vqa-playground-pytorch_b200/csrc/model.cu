@@ -1,0 +1,429 @@
+// Whole-model plans: every kernel of Model.forward / backward enqueued from one C call
+// (include/vqacore.h: vqa_cor2_{fwd,bwd}, vqa_oda_{fwd,bwd}).
+// Reference: config/CoR2.py:201-237 (+ decare_cat :191-199), config/ODA.py:200-240.
+// Parameter tables follow the reference's state_dict order (seq2vec.* excluded).
+#include "common.cuh"
+
+namespace vqa {
+
+constexpr int64_t H = 310, F = 510, A = 620, AG = 155, Q = 2400, D = 2048;
+constexpr float P_DROP = 0.5f;
+
+// ---- state_dict indices -------------------------------------------------------------------------
+namespace cor2 {
+enum {
+  COMPRESS_V = 0, COMPRESS_V2 = 2, COMPRESS_Q = 4,
+  VQ1_L1 = 6, VQ1_L2 = 10, ATT1_CONV = 14, ATT1_G = 16,
+  VQ2_L1 = 24, VQ2_L2 = 28, ATT2_CONV = 32, ATT2_G = 34,
+  LINEAR_Q = 42, FF_L1 = 44, FF_L2 = 48, CLASSIF = 52,
+  CQ1 = 54, EQ1 = 56, CQ2 = 58, EQ2 = 60
+};
+// dropout call sites in forward order (oracle/reasoning_core.py COR2_LAYERS)
+enum {
+  L_COMPRESS_Q = 0, L_COMPRESS_V = 1, L_ATT1_CONV = 2, L_ATT1_G = 3, L_CQ1 = 7, L_EQ1 = 8, L_CQ2 = 9, L_EQ2 = 10,
+  L_COMPRESS_V2 = 11, L_ATT2_CONV = 12, L_ATT2_G = 13, L_LINEAR_Q = 17, L_CLASSIF = 18
+};
+}  // namespace cor2
+namespace oda {
+enum { COMPRESS_V = 0, COMPRESS_Q = 2, ATT_CONV = 4, ATT_G = 6, LINEAR_Q = 14, FF_L1 = 16, FF_L2 = 26, CLASSIF = 36 };
+enum { L_COMPRESS_V = 0, L_COMPRESS_Q = 1, L_ATT_CONV = 2, L_ATT_G = 3, L_LINEAR_Q = 7, L_CLASSIF = 8 };
+}  // namespace oda
+
+// ---- workspace carving ----------------------------------------------------------------------------
+struct Carver {
+  char* base; size_t off;
+  float* take(int64_t n) {
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += ((size_t)n * sizeof(float) + 255) & ~(size_t)255;
+    return p;
+  }
+};
+
+struct Cor2Ws {
+  float *ql, *hq1, *hq2, *qf, *g1, *g2, *vl, *f1_H1, *f1_H2, *fuse1, *pooled1, *vf, *v2l, *f2_H1, *f2_H2, *fuse2,
+      *pooled2, *ff_H1, *ff_H2, *xf;
+  float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled2, *dalpha2, *dz2, *dfuse2, *dv2, *dv2l, *d_f2_H2, *dql, *dg1, *dg2, *dhq1,
+      *dhq2, *dalpha_ext, *dpooled1, *dalpha1, *dz1, *dfuse1, *dvl, *d_f1_H2;
+  size_t bytes;
+};
+
+static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N) {
+  Carver c{reinterpret_cast<char*>(base), 0};
+  const int64_t M = B * N;
+  Cor2Ws w;
+  w.ql = c.take(B * H); w.hq1 = c.take(B * H); w.hq2 = c.take(B * H); w.qf = c.take(B * H);
+  w.g1 = c.take(B * D); w.g2 = c.take(B * D);
+  w.vl = c.take(M * H);
+  w.f1_H1 = c.take(2 * M * F); w.f1_H2 = c.take(2 * B * F); w.fuse1 = c.take(M * F);
+  w.pooled1 = c.take(B * G * D);
+  w.vf = c.take(B * 2 * A);
+  w.v2l = c.take(M * H);
+  w.f2_H1 = c.take(2 * M * F); w.f2_H2 = c.take(2 * B * F); w.fuse2 = c.take(M * F);
+  w.pooled2 = c.take(B * G * D);
+  w.ff_H1 = c.take(2 * B * F); w.ff_H2 = c.take(2 * B * F); w.xf = c.take(B * F);
+  // backward temporaries
+  w.dxf = c.take(B * F); w.dvf = c.take(B * 2 * A); w.dqf = c.take(B * H); w.d_ff_H2 = c.take(2 * B * F);
+  w.dpooled2 = c.take(B * G * D); w.dalpha2 = c.take(M * G); w.dz2 = c.take(M * G);
+  w.dfuse2 = c.take(M * F); w.dv2 = c.take(M * D); w.dv2l = c.take(M * H); w.d_f2_H2 = c.take(2 * B * F);
+  w.dql = c.take(B * H); w.dg1 = c.take(B * D); w.dg2 = c.take(B * D); w.dhq1 = c.take(B * H); w.dhq2 = c.take(B * H);
+  w.dalpha_ext = c.take(B);
+  w.dpooled1 = c.take(B * G * D); w.dalpha1 = c.take(M * G); w.dz1 = c.take(M * G);
+  w.dfuse1 = c.take(M * F); w.dvl = c.take(M * H); w.d_f1_H2 = c.take(2 * B * F);
+  w.bytes = c.off;
+  return w;
+}
+
+struct OdaWs {
+  float *vl, *ql, *qf, *wsum, *pooled, *vf, *ff_H1, *ff_H2, *xf;
+  float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled, *dalpha, *dz, *dwsum, *dvl, *dql;
+  size_t bytes;
+};
+
+static OdaWs carve_oda(void* base, int64_t B, int64_t N) {
+  Carver c{reinterpret_cast<char*>(base), 0};
+  const int64_t M = B * N;
+  OdaWs w;
+  w.vl = c.take(M * H); w.ql = c.take(B * H); w.qf = c.take(B * H); w.wsum = c.take(G * H);
+  w.pooled = c.take(B * G * D); w.vf = c.take(B * A);
+  w.ff_H1 = c.take(5 * B * F); w.ff_H2 = c.take(5 * B * F); w.xf = c.take(B * F);
+  w.dxf = c.take(B * F); w.dvf = c.take(B * A); w.dqf = c.take(B * H); w.d_ff_H2 = c.take(5 * B * F);
+  w.dpooled = c.take(B * G * D); w.dalpha = c.take(M * G); w.dz = c.take(M * G); w.dwsum = c.take(G * H);
+  w.dvl = c.take(M * H); w.dql = c.take(B * H);
+  w.bytes = c.off;
+  return w;
+}
+
+// ---- small builders ---------------------------------------------------------------------------------
+struct Ctx {
+  const vqa_model_fwd_params* p;
+  void* stream;
+  const float* const* W;      // parameter table
+  float* const* dW;           // gradient table (backward) or nullptr
+  int accumulate;
+  float pdrop() const { return p->train ? P_DROP : 0.0f; }
+  float* grad(int idx) const { return dW ? dW[idx] : nullptr; }
+};
+
+// single or grouped linear forward; weight index widx[g] (bias = widx[g]+1)
+static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
+                   const int64_t* ldx, const int* widx, float* const* Y, const int64_t* ldy, const uint32_t* layer) {
+  vqa_linear_fwd_params lp = {};
+  lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
+  lp.p = c.pdrop(); lp.seed = c.p->seed;
+  for (int g = 0; g < groups; ++g) {
+    lp.X[g] = X[g]; lp.ldx[g] = ldx[g]; lp.W[g] = c.W[widx[g]]; lp.b[g] = c.W[widx[g] + 1];
+    lp.Y[g] = Y[g]; lp.ldy[g] = ldy[g]; lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
+  }
+  return vqa_linear_fwd(&lp, c.stream);
+}
+
+static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
+                   const int64_t* ldx, const int* widx, const float* const* Y, const int64_t* ldy,
+                   const float* const* dY, const int64_t* lddy, float* const* dX, const int64_t* lddx, int accumulate_x,
+                   const uint32_t* layer) {
+  vqa_linear_bwd_params lp = {};
+  lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
+  lp.p = c.pdrop(); lp.seed = c.p->seed; lp.accumulate_w = c.accumulate; lp.accumulate_x = accumulate_x;
+  for (int g = 0; g < groups; ++g) {
+    lp.X[g] = X[g]; lp.ldx[g] = ldx[g]; lp.W[g] = c.W[widx[g]];
+    lp.Y[g] = Y[g]; lp.ldy[g] = ldy[g]; lp.dY[g] = dY[g]; lp.lddy[g] = lddy[g];
+    lp.dW[g] = c.grad(widx[g]); lp.db[g] = c.grad(widx[g] + 1);
+    lp.dX[g] = dX ? dX[g] : nullptr; lp.lddx[g] = lddx ? lddx[g] : 0;
+    lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
+  }
+  return vqa_linear_bwd(&lp, c.stream);
+}
+
+static int mutan_fwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int64_t rows_per, const float* X1,
+                     const float* X2, int l1, int l2, float* H1, float* H2, float* Y) {
+  vqa_mutan_fwd_params mp = {};
+  mp.R = R; mp.M = M; mp.K1 = K1; mp.K2 = K2; mp.F = F; mp.rows_per_h2 = rows_per; mp.math = c.p->math;
+  mp.X1 = X1; mp.ldx1 = K1; mp.X2 = X2; mp.ldx2 = K2;
+  for (int r = 0; r < R; ++r) {
+    mp.W1[r] = c.W[l1 + 2 * r]; mp.b1[r] = c.W[l1 + 2 * r + 1];
+    mp.W2[r] = c.W[l2 + 2 * r]; mp.b2[r] = c.W[l2 + 2 * r + 1];
+  }
+  mp.H1 = H1; mp.H2 = H2; mp.Y = Y; mp.ldy = F;
+  return vqa_mutan_fwd(&mp, c.stream);
+}
+
+static int mutan_bwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int64_t rows_per, const float* X1,
+                     const float* X2, int l1, int l2, const float* H1, const float* H2, const float* dY, float* dH2,
+                     float* dX1, float* dX2, int accumulate_x2) {
+  vqa_mutan_bwd_params mp = {};
+  mp.R = R; mp.M = M; mp.K1 = K1; mp.K2 = K2; mp.F = F; mp.rows_per_h2 = rows_per; mp.math = c.p->math;
+  mp.accumulate_w = c.accumulate; mp.accumulate_x1 = 0; mp.accumulate_x2 = accumulate_x2;
+  mp.X1 = X1; mp.ldx1 = K1; mp.X2 = X2; mp.ldx2 = K2;
+  for (int r = 0; r < R; ++r) {
+    mp.W1[r] = c.W[l1 + 2 * r]; mp.W2[r] = c.W[l2 + 2 * r];
+    mp.dW1[r] = c.grad(l1 + 2 * r); mp.db1[r] = c.grad(l1 + 2 * r + 1);
+    mp.dW2[r] = c.grad(l2 + 2 * r); mp.db2[r] = c.grad(l2 + 2 * r + 1);
+  }
+  mp.H1 = H1; mp.H2 = H2; mp.dY = dY; mp.lddy = F; mp.dH2 = dH2;
+  mp.dX1 = dX1; mp.lddx1 = K1; mp.dX2 = dX2; mp.lddx2 = K2;
+  return vqa_mutan_bwd(&mp, c.stream);
+}
+
+// MyATT glimpse linears: pooled[B,G,D] -> vf[:, col0 + g*155 ...]
+static int glimpse_fwd(const Ctx& c, int64_t B, const float* pooled, int w0, float* vf, int64_t ldvf, int64_t col0,
+                       uint32_t layer0) {
+  const float* X[G]; int64_t ldx[G]; int widx[G]; float* Y[G]; int64_t ldy[G]; uint32_t layer[G];
+  for (int g = 0; g < G; ++g) {
+    X[g] = pooled + g * D; ldx[g] = G * D; widx[g] = w0 + 2 * g; Y[g] = vf + col0 + g * AG; ldy[g] = ldvf;
+    layer[g] = layer0 + g;
+  }
+  return lin_fwd(c, G, B, D, AG, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer);
+}
+static int glimpse_bwd(const Ctx& c, int64_t B, const float* pooled, int w0, const float* vf, const float* dvf,
+                       int64_t ldvf, int64_t col0, float* dpooled, uint32_t layer0) {
+  const float* X[G]; int64_t ldx[G]; int widx[G]; const float* Y[G]; int64_t ldy[G]; const float* dY[G];
+  int64_t lddy[G]; float* dX[G]; int64_t lddx[G]; uint32_t layer[G];
+  for (int g = 0; g < G; ++g) {
+    X[g] = pooled + g * D; ldx[g] = G * D; widx[g] = w0 + 2 * g;
+    Y[g] = vf + col0 + g * AG; ldy[g] = ldvf; dY[g] = dvf + col0 + g * AG; lddy[g] = ldvf;
+    dX[g] = dpooled + g * D; lddx[g] = G * D; layer[g] = layer0 + g;
+  }
+  return lin_bwd(c, G, B, D, AG, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer);
+}
+
+static int check_model(const vqa_model_fwd_params* p, size_t need, const char* who, bool cor2) {
+  VQA_REQUIRE(p != nullptr, "%s: null params", who);
+  VQA_REQUIRE(p->B >= 1 && p->N >= 1 && p->C >= 1, "%s: bad shape B=%lld N=%lld C=%lld", who, (long long)p->B,
+              (long long)p->N, (long long)p->C);
+  VQA_REQUIRE(p->v && p->q && p->params && p->logits && p->alpha1 && p->workspace, "%s: null pointer", who);
+  if (cor2) VQA_REQUIRE(p->alpha2 && p->v2, "%s: alpha2 / v2 output buffers required", who);
+  if (p->workspace_bytes < need) {
+    set_error("%s: workspace has %zu bytes, %zu needed", who, p->workspace_bytes, need);
+    return VQA_EWORKSPACE;
+  }
+  return vqa_device_check();
+}
+
+}  // namespace vqa
+
+using namespace vqa;
+
+// ====================================================================================== CoR2
+extern "C" size_t vqa_cor2_workspace_bytes(int64_t B, int64_t N, int64_t C) {
+  (void)C;
+  return carve_cor2(nullptr, B, N).bytes;
+}
+
+extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
+  VQA_TRY(check_model(p, p ? carve_cor2(nullptr, p->B, p->N).bytes : 0, "vqa_cor2_fwd", true));
+  using namespace cor2;
+  const int64_t B = p->B, N = p->N, M = B * N;
+  Cor2Ws w = carve_cor2(p->workspace, B, N);
+  Ctx c{p, stream, p->params, nullptr, 0};
+  {  // four 2400->310 question projections in one launch (config/CoR2.py:211,195,196,228)
+    const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
+    int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
+    int64_t ldy[4] = {H, H, H, H}; uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
+    VQA_TRY(lin_fwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+  }
+  {  // gates g1, g2 = sigmoid(310->2048) (config/CoR2.py:195-196)
+    const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {H, H}; int widx[2] = {EQ1, EQ2};
+    float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; uint32_t layer[2] = {L_EQ1, L_EQ2};
+    VQA_TRY(lin_fwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer));
+  }
+  {  // compress_v (config/CoR2.py:213)
+    const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
+    int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
+    VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+  }
+  VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, w.ql, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1));   // fusion_vq1 :214
+  {  // att1 on raw v (:214)
+    vqa_region_softmax_pool_fwd_params ap = {};
+    ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed;
+    ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.bc = c.W[ATT1_CONV + 1]; ap.x = p->v;
+    ap.alpha = p->alpha1; ap.pooled = w.pooled1;
+    VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream));
+  }
+  VQA_TRY(glimpse_fwd(c, B, w.pooled1, ATT1_G, w.vf, 2 * A, 0, L_ATT1_G));
+  {  // compound objects (:215-216)
+    vqa_cor_compound_fwd_params cp = {};
+    cp.B = B; cp.N = N; cp.D = D; cp.x = p->v; cp.pooled = w.pooled1; cp.alpha = p->alpha1; cp.g1 = w.g1; cp.g2 = w.g2;
+    cp.v2 = p->v2;
+    VQA_TRY(vqa_cor_compound_fwd(&cp, stream));
+  }
+  {  // compress_v2 (:218)
+    const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; float* Y[1] = {w.v2l};
+    int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V2};
+    VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+  }
+  VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, w.ql, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2));  // fusion_vq2 :219
+  {  // att2 on v2 (:219)
+    vqa_region_softmax_pool_fwd_params ap = {};
+    ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed;
+    ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.bc = c.W[ATT2_CONV + 1]; ap.x = p->v2;
+    ap.alpha = p->alpha2; ap.pooled = w.pooled2;
+    VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream));
+  }
+  VQA_TRY(glimpse_fwd(c, B, w.pooled2, ATT2_G, w.vf, 2 * A, A, L_ATT2_G));
+  VQA_TRY(mutan_fwd(c, 2, B, 2 * A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf));    // fusion_final :233
+  {  // linear_classif (:236)
+    const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
+    int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
+    VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer));
+  }
+  return VQA_OK;
+}
+
+extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
+  VQA_REQUIRE(bp != nullptr, "vqa_cor2_bwd: null params");
+  const vqa_model_fwd_params* p = &bp->fwd;
+  VQA_TRY(check_model(p, carve_cor2(nullptr, p->B, p->N).bytes, "vqa_cor2_bwd", true));
+  VQA_REQUIRE(bp->dlogits && bp->grads, "vqa_cor2_bwd: null dlogits / grads");
+  using namespace cor2;
+  const int64_t B = p->B, N = p->N, M = B * N;
+  Cor2Ws w = carve_cor2(p->workspace, B, N);
+  Ctx c{p, stream, p->params, bp->grads, bp->accumulate};
+  {  // linear_classif
+    const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
+    int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
+    float* dX[1] = {w.dxf}; int64_t lddx[1] = {F}; uint32_t layer[1] = {L_CLASSIF};
+    VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer));
+  }
+  VQA_TRY(mutan_bwd(c, 2, B, 2 * A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, w.d_ff_H2, w.dvf, w.dqf, 0));
+  // ---- att2 branch
+  VQA_TRY(glimpse_bwd(c, B, w.pooled2, ATT2_G, w.vf, w.dvf, 2 * A, A, w.dpooled2, L_ATT2_G));
+  {
+    vqa_region_softmax_pool_bwd_params ap = {};
+    ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed;
+    ap.accumulate_w = bp->accumulate; ap.accumulate_x = 0;
+    ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.x = p->v2; ap.alpha = p->alpha2; ap.dpooled = w.dpooled2;
+    ap.dalpha0_ext = nullptr; ap.dalpha = w.dalpha2; ap.dz = w.dz2;
+    ap.dWc = c.grad(ATT2_CONV); ap.dbc = c.grad(ATT2_CONV + 1); ap.dfuse = w.dfuse2; ap.dx = w.dv2;
+    VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream));
+  }
+  VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, w.ql, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, w.d_f2_H2, w.dv2l, w.dql, 0));
+  {  // compress_v2: dgrad accumulates into dv2 (v2 feeds both compress_v2 and att2's pooling)
+    const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; const float* Y[1] = {w.v2l};
+    int64_t ldy[1] = {H}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {H};
+    float* dX[1] = {w.dv2}; int64_t lddx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V2};
+    VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 1, layer));
+  }
+  // ---- att1 branch: glimpse linears first (they initialise dpooled1), then the compound objects add to it
+  VQA_TRY(glimpse_bwd(c, B, w.pooled1, ATT1_G, w.vf, w.dvf, 2 * A, 0, w.dpooled1, L_ATT1_G));
+  {
+    vqa_cor_compound_bwd_params cp = {};
+    cp.B = B; cp.N = N; cp.D = D; cp.x = p->v; cp.pooled = w.pooled1; cp.alpha = p->alpha1; cp.g1 = w.g1; cp.g2 = w.g2;
+    cp.dv2 = w.dv2; cp.dg1 = w.dg1; cp.dg2 = w.dg2; cp.dpooled = w.dpooled1; cp.dalpha0_ext = w.dalpha_ext;
+    VQA_TRY(vqa_cor_compound_bwd(&cp, stream));
+  }
+  {  // gates
+    const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {H, H}; int widx[2] = {EQ1, EQ2};
+    const float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; const float* dY[2] = {w.dg1, w.dg2};
+    int64_t lddy[2] = {D, D}; float* dX[2] = {w.dhq1, w.dhq2}; int64_t lddx[2] = {H, H};
+    uint32_t layer[2] = {L_EQ1, L_EQ2};
+    VQA_TRY(lin_bwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer));
+  }
+  {
+    vqa_region_softmax_pool_bwd_params ap = {};
+    ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed;
+    ap.accumulate_w = bp->accumulate; ap.accumulate_x = 0;
+    ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.dpooled = w.dpooled1;
+    ap.dalpha0_ext = w.dalpha_ext; ap.dalpha = w.dalpha1; ap.dz = w.dz1;
+    ap.dWc = c.grad(ATT1_CONV); ap.dbc = c.grad(ATT1_CONV + 1); ap.dfuse = w.dfuse1; ap.dx = nullptr;
+    VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream));
+  }
+  VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, w.ql, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, w.d_f1_H2, w.dvl, w.dql, 1));
+  {  // compress_v: v is a graph input, no dgrad
+    const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
+    int64_t ldy[1] = {H}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
+    VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer));
+  }
+  {  // the four question projections
+    const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
+    int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; const float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
+    int64_t ldy[4] = {H, H, H, H}; const float* dY[4] = {w.dql, w.dhq1, w.dhq2, w.dqf}; int64_t lddy[4] = {H, H, H, H};
+    uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
+    VQA_TRY(lin_bwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer));
+  }
+  return VQA_OK;
+}
+
+// ====================================================================================== ODA
+extern "C" size_t vqa_oda_workspace_bytes(int64_t B, int64_t N, int64_t C) {
+  (void)C;
+  return carve_oda(nullptr, B, N).bytes;
+}
+
+extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
+  VQA_TRY(check_model(p, p ? carve_oda(nullptr, p->B, p->N).bytes : 0, "vqa_oda_fwd", false));
+  using namespace oda;
+  const int64_t B = p->B, N = p->N, M = B * N;
+  OdaWs w = carve_oda(p->workspace, B, N);
+  Ctx c{p, stream, p->params, nullptr, 0};
+  {  // compress_v (config/ODA.py:211)
+    const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
+    int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
+    VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+  }
+  {  // compress_q + linear_q (:214, :233)
+    const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
+    float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, H}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
+    VQA_TRY(lin_fwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+  }
+  {  // pairwise differences + conv_att + softmax + pooling (:216-226)
+    vqa_oda_pair_attn_fwd_params ap = {};
+    ap.B = B; ap.N = N; ap.H = H; ap.D = D; ap.train = p->train;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT_CONV; ap.drop.seed = p->seed;
+    ap.vl = w.vl; ap.ql = w.ql; ap.W = c.W[ATT_CONV]; ap.bc = c.W[ATT_CONV + 1]; ap.x = p->v; ap.wsum = w.wsum;
+    ap.alpha = p->alpha1; ap.pooled = w.pooled;
+    VQA_TRY(vqa_oda_pair_attn_fwd(&ap, stream));
+  }
+  VQA_TRY(glimpse_fwd(c, B, w.pooled, ATT_G, w.vf, A, 0, L_ATT_G));
+  VQA_TRY(mutan_fwd(c, 5, B, A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf));       // fusion_final :236
+  {  // linear_classif (:239)
+    const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
+    int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
+    VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer));
+  }
+  return VQA_OK;
+}
+
+extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
+  VQA_REQUIRE(bp != nullptr, "vqa_oda_bwd: null params");
+  const vqa_model_fwd_params* p = &bp->fwd;
+  VQA_TRY(check_model(p, carve_oda(nullptr, p->B, p->N).bytes, "vqa_oda_bwd", false));
+  VQA_REQUIRE(bp->dlogits && bp->grads, "vqa_oda_bwd: null dlogits / grads");
+  using namespace oda;
+  const int64_t B = p->B, N = p->N, M = B * N;
+  OdaWs w = carve_oda(p->workspace, B, N);
+  Ctx c{p, stream, p->params, bp->grads, bp->accumulate};
+  {
+    const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
+    int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
+    float* dX[1] = {w.dxf}; int64_t lddx[1] = {F}; uint32_t layer[1] = {L_CLASSIF};
+    VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer));
+  }
+  VQA_TRY(mutan_bwd(c, 5, B, A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, w.d_ff_H2, w.dvf, w.dqf, 0));
+  VQA_TRY(glimpse_bwd(c, B, w.pooled, ATT_G, w.vf, w.dvf, A, 0, w.dpooled, L_ATT_G));
+  {
+    vqa_oda_pair_attn_bwd_params ap = {};
+    ap.B = B; ap.N = N; ap.H = H; ap.D = D; ap.train = p->train;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT_CONV; ap.drop.seed = p->seed;
+    ap.accumulate_w = bp->accumulate;
+    ap.vl = w.vl; ap.ql = w.ql; ap.W = c.W[ATT_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.wsum = w.wsum;
+    ap.dpooled = w.dpooled; ap.dalpha = w.dalpha; ap.dz = w.dz; ap.dwsum = w.dwsum;
+    ap.dW = c.grad(ATT_CONV); ap.dbc = c.grad(ATT_CONV + 1); ap.dvl = w.dvl; ap.dql = w.dql;
+    VQA_TRY(vqa_oda_pair_attn_bwd(&ap, stream));
+  }
+  {
+    const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
+    int64_t ldy[1] = {H}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
+    VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer));
+  }
+  {
+    const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
+    const float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, H}; const float* dY[2] = {w.dql, w.dqf};
+    int64_t lddy[2] = {H, H}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
+    VQA_TRY(lin_bwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer));
+  }
+  return VQA_OK;
+}

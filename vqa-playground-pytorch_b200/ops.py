@@ -1,0 +1,352 @@
+"""Thin torch.autograd.Function wrappers over the C ABI (include/vqacore.h).
+
+PyTorch is used only for device memory, the current stream and the autograd graph; every
+forward and backward below is one C call that enqueues hand-written sm_100a kernels on
+torch's current stream.  Nothing here computes with ATen, and there is no CPU fallback:
+CPU tensors raise ValueError.
+"""
+import ctypes as C
+import itertools
+
+import torch
+
+from . import _lib
+from ._lib import GLIMPSES, MAXG, fp
+
+H_DIM, F_DIM, A_DIM, Q_DIM, D_DIM = 310, 510, 620, 2400, 2048
+
+_seed_counter = itertools.count(1)
+_base_seed = 0x5EED
+
+
+def manual_seed(seed):
+    """Base key of the Philox dropout stream (each train-mode forward takes the next counter)."""
+    global _base_seed, _seed_counter
+    _base_seed = int(seed) & 0xFFFFFFFF
+    _seed_counter = itertools.count(1)
+
+
+def next_seed():
+    return (_base_seed << 32) | (next(_seed_counter) & 0xFFFFFFFF)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name, dims=None):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError("%s: expected a tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s: must be a CUDA tensor (libvqacore has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise ValueError("%s: must be float32, got %s" % (name, t.dtype))
+    if dims is not None and t.dim() != dims:
+        raise ValueError("%s: expected %d dims, got %d" % (name, dims, t.dim()))
+    return t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _math(math):
+    return _lib.MATH_BY_NAME[math] if isinstance(math, str) else int(math)
+
+
+# =========================================================================== grouped linear
+def linear_forward(xs, ws, bs, act, p, seed, layers, math=0, outs=None):
+    """Y_g = act(dropout(X_g) W_g^T + b_g). xs/ws/bs: lists (one entry per group), X_g [M,K] (row stride
+    may exceed K). Returns list of Y_g [M,N] (or writes into `outs`, which may be strided views)."""
+    g = len(xs)
+    M, K = xs[0].shape
+    N = ws[0].shape[0]
+    pr = _lib.LinearFwd()
+    pr.groups, pr.M, pr.K, pr.N, pr.act, pr.math, pr.p, pr.seed = g, M, K, N, act, _math(math), float(p), int(seed)
+    if outs is None:
+        outs = [torch.empty((M, N), device=xs[0].device, dtype=torch.float32) for _ in range(g)]
+    for i in range(g):
+        assert xs[i].stride(1) == 1 and outs[i].stride(1) == 1
+        pr.X[i], pr.ldx[i] = xs[i].data_ptr(), xs[i].stride(0)
+        pr.W[i], pr.b[i] = ws[i].data_ptr(), _p(bs[i])
+        pr.Y[i], pr.ldy[i] = outs[i].data_ptr(), outs[i].stride(0)
+        pr.layer[i], pr.drop_index_base[i] = int(layers[i]), 0
+    _lib.check(_lib.lib().vqa_linear_fwd(C.byref(pr), _stream()), "vqa_linear_fwd")
+    return outs
+
+
+def linear_backward(xs, ws, ys, dys, act, p, seed, layers, need_dx, math=0, dws=None, dbs=None, dxs=None,
+                    accumulate_w=False, accumulate_x=False):
+    g = len(xs)
+    M, K = xs[0].shape
+    N = ws[0].shape[0]
+    dev = xs[0].device
+    pr = _lib.LinearBwd()
+    pr.groups, pr.M, pr.K, pr.N, pr.act, pr.math, pr.p, pr.seed = g, M, K, N, act, _math(math), float(p), int(seed)
+    pr.accumulate_w, pr.accumulate_x = int(accumulate_w), int(accumulate_x)
+    if dws is None:
+        dws = [torch.empty_like(w) for w in ws]
+    if dbs is None:
+        dbs = [torch.empty((N,), device=dev, dtype=torch.float32) for _ in range(g)]
+    if dxs is None:
+        dxs = [torch.empty((M, K), device=dev, dtype=torch.float32) if need_dx else None for _ in range(g)]
+    for i in range(g):
+        pr.X[i], pr.ldx[i] = xs[i].data_ptr(), xs[i].stride(0)
+        pr.W[i] = ws[i].data_ptr()
+        pr.Y[i], pr.ldy[i] = _p(ys[i]), (ys[i].stride(0) if ys[i] is not None else N)
+        pr.dY[i], pr.lddy[i] = dys[i].data_ptr(), dys[i].stride(0)
+        pr.dW[i], pr.db[i] = _p(dws[i]), _p(dbs[i])
+        pr.dX[i], pr.lddx[i] = _p(dxs[i]), (dxs[i].stride(0) if dxs[i] is not None else K)
+        pr.layer[i], pr.drop_index_base[i] = int(layers[i]), 0
+    _lib.check(_lib.lib().vqa_linear_bwd(C.byref(pr), _stream()), "vqa_linear_bwd")
+    return dws, dbs, dxs
+
+
+class LinearFn(torch.autograd.Function):
+    """Single-group linear with fused input dropout / bias / activation (MyLinear, MyConv1d k=1)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, p, seed, layer, math):
+        x2 = _chk(x, "x").reshape(-1, x.shape[-1])
+        w2 = _chk(w, "weight").reshape(w.shape[0], -1)
+        y = linear_forward([x2], [w2], [b], act, p, seed, [layer], math)[0]
+        ctx.save_for_backward(x2, w2, y)
+        ctx.meta = (act, p, seed, layer, math, x.shape, w.shape, b is not None)
+        return y.reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w2, y = ctx.saved_tensors
+        act, p, seed, layer, math, xshape, wshape, has_b = ctx.meta
+        dy2 = dy.contiguous().reshape(-1, dy.shape[-1])
+        dws, dbs, dxs = linear_backward([x2], [w2], [y], [dy2], act, p, seed, [layer], ctx.needs_input_grad[0], math)
+        dx = dxs[0].reshape(xshape) if dxs[0] is not None else None
+        return dx, dws[0].reshape(wshape), (dbs[0] if has_b else None), None, None, None, None, None
+
+
+# =========================================================================== Mutan fusion
+def _ptr_table(tensors, n=MAXG):
+    arr = (fp * n)()
+    for i, t in enumerate(tensors):
+        arr[i] = _p(t)
+    return arr
+
+
+class MutanFn(torch.autograd.Function):
+    """sum_r (x1 W1_r^T + b1_r) (.) (x2 W2_r^T + b2_r), x2 broadcast over the region axis of x1."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, math, R, *wb):
+        # wb = W1_0, b1_0, ..., W1_{R-1}, b1_{R-1}, W2_0, b2_0, ...
+        x1c, x2c = _chk(x1, "inputs1"), _chk(x2, "inputs2")
+        a = x1c.reshape(-1, x1c.shape[-1])
+        c = x2c.reshape(-1, x2c.shape[-1])
+        M, K1 = a.shape
+        Mh, K2 = c.shape
+        if M % Mh != 0:
+            raise ValueError("MutanFusion: inputs1 rows (%d) not a multiple of inputs2 rows (%d)" % (M, Mh))
+        W1, b1 = wb[0:2 * R:2], wb[1:2 * R:2]
+        W2, b2 = wb[2 * R::2], wb[2 * R + 1::2]
+        Fd = W1[0].shape[0]
+        dev = a.device
+        H1 = torch.empty((R, M, Fd), device=dev, dtype=torch.float32)
+        H2 = torch.empty((R, Mh, Fd), device=dev, dtype=torch.float32)
+        y = torch.empty((M, Fd), device=dev, dtype=torch.float32)
+        pr = _lib.MutanFwd()
+        pr.R, pr.M, pr.K1, pr.K2, pr.F, pr.rows_per_h2, pr.math = R, M, K1, K2, Fd, M // Mh, _math(math)
+        pr.X1, pr.ldx1, pr.X2, pr.ldx2 = a.data_ptr(), K1, c.data_ptr(), K2
+        for r in range(R):
+            pr.W1[r], pr.b1[r], pr.W2[r], pr.b2[r] = W1[r].data_ptr(), _p(b1[r]), W2[r].data_ptr(), _p(b2[r])
+        pr.H1, pr.H2, pr.Y, pr.ldy = H1.data_ptr(), H2.data_ptr(), y.data_ptr(), Fd
+        _lib.check(_lib.lib().vqa_mutan_fwd(C.byref(pr), _stream()), "vqa_mutan_fwd")
+        ctx.save_for_backward(a, c, H1, H2, *wb)
+        ctx.meta = (math, R, x1.shape, x2.shape)
+        return y.reshape(*x1.shape[:-1], Fd)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, c, H1, H2, *wb = ctx.saved_tensors
+        math, R, x1shape, x2shape = ctx.meta
+        W1, W2 = wb[0:2 * R:2], wb[2 * R::2]
+        M, K1 = a.shape
+        Mh, K2 = c.shape
+        Fd = W1[0].shape[0]
+        dev = a.device
+        dy2 = dy.contiguous().reshape(M, Fd)
+        grads = [torch.empty_like(t) for t in wb]
+        dH2 = torch.empty_like(H2)
+        dx1 = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        dx2 = torch.empty_like(c) if ctx.needs_input_grad[1] else None
+        pr = _lib.MutanBwd()
+        pr.R, pr.M, pr.K1, pr.K2, pr.F, pr.rows_per_h2, pr.math = R, M, K1, K2, Fd, M // Mh, _math(math)
+        pr.X1, pr.ldx1, pr.X2, pr.ldx2 = a.data_ptr(), K1, c.data_ptr(), K2
+        for r in range(R):
+            pr.W1[r], pr.W2[r] = W1[r].data_ptr(), W2[r].data_ptr()
+            pr.dW1[r], pr.db1[r] = grads[2 * r].data_ptr(), grads[2 * r + 1].data_ptr()
+            pr.dW2[r], pr.db2[r] = grads[2 * R + 2 * r].data_ptr(), grads[2 * R + 2 * r + 1].data_ptr()
+        pr.H1, pr.H2, pr.dY, pr.lddy, pr.dH2 = H1.data_ptr(), H2.data_ptr(), dy2.data_ptr(), Fd, dH2.data_ptr()
+        pr.dX1, pr.lddx1, pr.dX2, pr.lddx2 = _p(dx1), K1, _p(dx2), K2
+        _lib.check(_lib.lib().vqa_mutan_bwd(C.byref(pr), _stream()), "vqa_mutan_bwd")
+        return (dx1.reshape(x1shape) if dx1 is not None else None,
+                dx2.reshape(x2shape) if dx2 is not None else None, None, None, *grads)
+
+
+# =========================================================================== region softmax + pooling
+class RegionSoftmaxPoolFn(torch.autograd.Function):
+    """alpha = softmax_regions(conv_att(dropout(fuse))); pooled = alpha^T x.  Returns (pooled, alpha).
+    alpha is a side output (its incoming gradient is only honoured for glimpse 0 through
+    `CorCompoundFn`, which is how the reference uses it; config/CoR2.py:216)."""
+
+    @staticmethod
+    def forward(ctx, x, fuse, wc, bc, p, seed, layer):
+        xc, fc = _chk(x, "inputs", 3), _chk(fuse, "fuse", 3)
+        B, N, Dd = xc.shape
+        Ff = fc.shape[2]
+        wc2 = _chk(wc, "conv_att.weight").reshape(GLIMPSES, Ff)
+        alpha = torch.empty((B, N, GLIMPSES), device=xc.device, dtype=torch.float32)
+        pooled = torch.empty((B, GLIMPSES, Dd), device=xc.device, dtype=torch.float32)
+        pr = _lib.PoolFwd()
+        pr.B, pr.N, pr.Ff, pr.D = B, N, Ff, Dd
+        pr.drop.p, pr.drop.layer, pr.drop.seed = float(p), int(layer), int(seed)
+        pr.fuse, pr.Wc, pr.bc, pr.x = fc.data_ptr(), wc2.data_ptr(), bc.data_ptr(), xc.data_ptr()
+        pr.alpha, pr.pooled = alpha.data_ptr(), pooled.data_ptr()
+        _lib.check(_lib.lib().vqa_region_softmax_pool_fwd(C.byref(pr), _stream()), "vqa_region_softmax_pool_fwd")
+        ctx.save_for_backward(xc, fc, wc2, alpha)
+        ctx.meta = (p, seed, layer, wc.shape)
+        return pooled, alpha
+
+    @staticmethod
+    def backward(ctx, dpooled, dalpha_in):
+        xc, fc, wc2, alpha = ctx.saved_tensors
+        p, seed, layer, wshape = ctx.meta
+        B, N, Dd = xc.shape
+        Ff = fc.shape[2]
+        dev = xc.device
+        dpooled = dpooled.contiguous()
+        ext = None
+        if dalpha_in is not None:
+            # only a per-sample scalar added to glimpse 0 is representable (CoR2's d s / d alpha term)
+            ext = dalpha_in[:, 0, 0].contiguous()
+        dalpha = torch.empty_like(alpha)
+        dz = torch.empty_like(alpha)
+        dwc = torch.empty_like(wc2)
+        dbc = torch.empty((GLIMPSES,), device=dev, dtype=torch.float32)
+        dfuse = torch.empty_like(fc) if ctx.needs_input_grad[1] else None
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        pr = _lib.PoolBwd()
+        pr.B, pr.N, pr.Ff, pr.D = B, N, Ff, Dd
+        pr.drop.p, pr.drop.layer, pr.drop.seed = float(p), int(layer), int(seed)
+        pr.accumulate_w, pr.accumulate_x = 0, 0
+        pr.fuse, pr.Wc, pr.x, pr.alpha = fc.data_ptr(), wc2.data_ptr(), xc.data_ptr(), alpha.data_ptr()
+        pr.dpooled, pr.dalpha0_ext = dpooled.data_ptr(), _p(ext)
+        pr.dalpha, pr.dz, pr.dWc, pr.dbc = dalpha.data_ptr(), dz.data_ptr(), dwc.data_ptr(), dbc.data_ptr()
+        pr.dfuse, pr.dx = _p(dfuse), _p(dx)
+        _lib.check(_lib.lib().vqa_region_softmax_pool_bwd(C.byref(pr), _stream()), "vqa_region_softmax_pool_bwd")
+        return dx, dfuse, dwc.reshape(wshape), dbc, None, None, None
+
+
+# =========================================================================== loss
+class KldLogSoftmaxFn(torch.autograd.Function):
+    """KLDivLoss(size_average=False)(log_softmax(x,1), a) — train.py:536-544."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        x, a = _chk(logits, "logits", 2), _chk(target, "target", 2)
+        B, Cc = x.shape
+        rows = torch.empty((B,), device=x.device, dtype=torch.float32)
+        dlogits = torch.empty_like(x)
+        pr = _lib.KldParams()
+        pr.B, pr.C, pr.grad_scale = B, Cc, 1.0
+        pr.logits, pr.target, pr.loss_rows, pr.dlogits = x.data_ptr(), a.data_ptr(), rows.data_ptr(), dlogits.data_ptr()
+        _lib.check(_lib.lib().vqa_kld_logsoftmax_fwd_bwd(C.byref(pr), _stream()), "vqa_kld_logsoftmax_fwd_bwd")
+        ctx.save_for_backward(dlogits)
+        return rows
+
+    @staticmethod
+    def backward(ctx, drows):
+        (dlogits,) = ctx.saved_tensors
+        # drows is all-ones for loss = rows.sum(); general case scales per row
+        return dlogits * drows.unsqueeze(1), None
+
+
+def kld_loss_rows(logits, target):
+    return KldLogSoftmaxFn.apply(logits, target)
+
+
+# =========================================================================== whole-model plans
+_MODEL = {
+    "CoR2": ("vqa_cor2_workspace_bytes", "vqa_cor2_fwd", "vqa_cor2_bwd"),
+    "ODA": ("vqa_oda_workspace_bytes", "vqa_oda_fwd", "vqa_oda_bwd"),
+}
+
+
+def _fill_model_params(pr, B, N, Cc, train, math, seed, v, q, ptab, logits, alpha1, alpha2, v2, ws):
+    pr.B, pr.N, pr.C, pr.train, pr.math, pr.seed = B, N, Cc, int(train), _math(math), int(seed)
+    pr.v, pr.q, pr.params = v.data_ptr(), q.data_ptr(), ptab
+    pr.logits, pr.alpha1, pr.alpha2, pr.v2 = logits.data_ptr(), alpha1.data_ptr(), _p(alpha2), _p(v2)
+    pr.workspace, pr.workspace_bytes = ws.data_ptr(), ws.numel()
+
+
+class ModelCoreFn(torch.autograd.Function):
+    """Model.forward of config/CoR2.py:201-237 or config/ODA.py:200-240 as ONE C call (and one more
+    for the whole backward).  Returns (logits, alpha1, alpha2, v2); the last three are
+    non-differentiable side outputs feeding `alpha_dict`."""
+
+    @staticmethod
+    def forward(ctx, model, v, q, train, math, seed, num_regions, num_ans, grad_sink, *params):
+        wsb, fwd, _ = _MODEL[model]
+        L = _lib.lib()
+        vc = _chk(v, "sample['v']").reshape(-1, num_regions, D_DIM)
+        qc = _chk(q, "question embedding", 2)
+        B, N = vc.shape[0], num_regions
+        if qc.shape[0] != B or qc.shape[1] != Q_DIM:
+            raise ValueError("question embedding must be [%d,%d], got %s" % (B, Q_DIM, tuple(qc.shape)))
+        Cc = int(num_ans)
+        dev = vc.device
+        params = [_chk(t, "parameter") for t in params]
+        ws = torch.empty((int(getattr(L, wsb)(B, N, Cc)),), device=dev, dtype=torch.uint8)
+        logits = torch.empty((B, Cc), device=dev, dtype=torch.float32)
+        alpha1 = torch.empty((B, N, GLIMPSES), device=dev, dtype=torch.float32)
+        cor2 = model == "CoR2"
+        alpha2 = torch.empty((B, N, GLIMPSES), device=dev, dtype=torch.float32) if cor2 else None
+        v2 = torch.empty((B, N, D_DIM), device=dev, dtype=torch.float32) if cor2 else None
+        ptab = _ptr_table(params, len(params))
+        pr = _lib.ModelFwd()
+        _fill_model_params(pr, B, N, Cc, train, math, seed, vc, qc, ptab, logits, alpha1, alpha2, v2, ws)
+        _lib.check(getattr(L, fwd)(C.byref(pr), _stream()), fwd)
+        ctx.model, ctx.meta, ctx.grad_sink = model, (B, N, Cc, train, math, seed), grad_sink
+        ctx.keep = (vc, qc, params, ws, logits, alpha1, alpha2, v2)
+        if cor2:
+            ctx.mark_non_differentiable(alpha1, alpha2, v2)
+            return logits, alpha1, alpha2, v2
+        ctx.mark_non_differentiable(alpha1)
+        return logits, alpha1, None, None
+
+    @staticmethod
+    def backward(ctx, dlogits, *_unused):
+        _, _, bwd = _MODEL[ctx.model]
+        L = _lib.lib()
+        B, N, Cc, train, math, seed = ctx.meta
+        vc, qc, params, ws, logits, alpha1, alpha2, v2 = ctx.keep
+        dlogits = dlogits.contiguous()
+        sink = ctx.grad_sink
+        if sink is not None:
+            # data-parallel engine: gradients land directly in its flat buffer (no autograd copies)
+            grads, accumulate, ret = sink.slices, int(sink.accumulate), [None] * len(params)
+        else:
+            flat = torch.empty((sum(t.numel() for t in params),), device=dlogits.device, dtype=torch.float32)
+            grads, off = [], 0
+            for t in params:
+                grads.append(flat[off:off + t.numel()].view(t.shape))
+                off += t.numel()
+            accumulate, ret = 0, grads
+        ptab = _ptr_table(params, len(params))
+        gtab = _ptr_table(grads, len(grads))
+        pr = _lib.ModelBwd()
+        _fill_model_params(pr.fwd, B, N, Cc, train, math, seed, vc, qc, ptab, logits, alpha1, alpha2, v2, ws)
+        pr.dlogits, pr.grads, pr.accumulate = dlogits.data_ptr(), gtab, accumulate
+        _lib.check(getattr(L, bwd)(C.byref(pr), _stream()), bwd)
+        if sink is not None:
+            sink.after_backward()
+        ctx.keep = None
+        return (None, None, None, None, None, None, None, None, None, *ret)

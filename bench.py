@@ -1,0 +1,344 @@
+"""Benchmark of the hot path: CoR2 (or ODA) fwd + KLD loss + bwd, samples/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--model CoR2|ODA] [--batch 256] [--regions 36] [--precision fp32|tf32x3|tf32|bf16]
+
+One JSON line on stdout (rank 0).  Workload at N=1: BASELINE.json configs[1], "CoR2 forward+backward
+on 1 B200, batch 256 x 36 regions x 2048-d, fp32 parity mode" (the stock config/CoR2.py chain:
+att1 -> compound objects -> att2), train mode (dropout on), batch 256 PER GPU (weak scaling).
+  value     device-resident inputs, timed region = K steps bracketed by CUDA events
+  e2e       same step through model(sample) with PINNED HOST inputs: H2D of v/q/a and a D2H read of the
+            loss inside the timed region, every step
+  roofline  the op with the largest share of the step (per-op CUDA events, vqa_profile_*), against
+            MEASURED_PEAKS.json
+  cpu_baseline  the oracle (restated reference, torch CPU) on this box's host cores, bounded sample
+`--impl reference` times that CPU oracle alone (the reference is pure Python/ATen; /root/reference does
+not exist on the GPU box, so the arm runs the committed restatement, kind "port").
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H, F, A, Q, D, G = 310, 510, 620, 2400, 2048, 4
+NUM_ANS = {"CoR2": 2000, "ODA": 3000}
+
+
+# ----------------------------------------------------------------------------------------- helpers
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="CoR2", choices=["CoR2", "ODA"])
+    ap.add_argument("--batch", type=int, default=256, help="per GPU")
+    ap.add_argument("--regions", type=int, default=36)
+    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the CPU oracle sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-mode", action="store_true", help="dropout off (default: train mode)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d.get("bf16_tflops_sustained",
+                d["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def op_work(model, B, N, C):
+    """Algorithmic work per launch of each plan op: ('tensor', flops) or ('hbm', bytes)."""
+    M = B * N
+    gemm = lambda m, k, n: 2.0 * m * k * n
+    w = {
+        "compress_v.fwd": ("tensor", gemm(M, D, H)), "compress_v2.fwd": ("tensor", gemm(M, D, H)),
+        "compress_v.bwd": ("tensor", gemm(M, D, H)), "compress_v2.bwd": ("tensor", 2 * gemm(M, D, H)),
+        "fusion_vq1.fwd": ("tensor", 2 * gemm(M, H, F)), "fusion_vq2.fwd": ("tensor", 2 * gemm(M, H, F)),
+        "fusion_vq1.bwd": ("tensor", 4 * gemm(M, H, F)), "fusion_vq2.bwd": ("tensor", 4 * gemm(M, H, F)),
+        "att1.pool.fwd": ("hbm", 4.0 * (M * D + M * F + B * G * D + M * G)),
+        "att2.pool.fwd": ("hbm", 4.0 * (M * D + M * F + B * G * D + M * G)),
+        "att1.pool.bwd": ("hbm", 4.0 * (M * D + 2 * M * F)), "att2.pool.bwd": ("hbm", 4.0 * (2 * M * D + 2 * M * F)),
+        "compound.fwd": ("hbm", 4.0 * 2 * M * D), "compound.bwd": ("hbm", 4.0 * 2 * M * D),
+        "oda_pair_attn.fwd": ("hbm", 4.0 * (M * D + M * H)), "oda_pair_attn.bwd": ("hbm", 4.0 * (M * D + 2 * M * H)),
+        "q_proj4.fwd": ("tensor", 4 * gemm(B, Q, H)), "q_proj4.bwd": ("tensor", 4 * gemm(B, Q, H)),
+        "q_proj2.fwd": ("tensor", 2 * gemm(B, Q, H)), "q_proj2.bwd": ("tensor", 2 * gemm(B, Q, H)),
+        "gates.fwd": ("tensor", 2 * gemm(B, H, D)), "gates.bwd": ("tensor", 4 * gemm(B, H, D)),
+        "classif.fwd": ("tensor", gemm(B, F, C)), "classif.bwd": ("tensor", 2 * gemm(B, F, C)),
+    }
+    R, K1 = (2, 2 * A) if model == "CoR2" else (5, A)
+    w["fusion_final.fwd"] = ("tensor", R * (gemm(B, K1, F) + gemm(B, H, F)))
+    w["fusion_final.bwd"] = ("tensor", 2 * R * (gemm(B, K1, F) + gemm(B, H, F)))
+    for a in ("att1", "att2", "att"):
+        w[a + ".glimpse.fwd"] = ("tensor", 4 * gemm(B, D, A // G))
+        w[a + ".glimpse.bwd"] = ("tensor", 8 * gemm(B, D, A // G))
+    return w
+
+
+def make_batch(B, N, C, device, gen):
+    v = torch.relu(torch.randn(B, N, D, generator=gen))
+    q = 0.1 * torch.relu(torch.randn(B, Q, generator=gen))
+    a = torch.zeros(B, C)
+    cls = torch.randint(0, C, (B, 3), generator=gen)
+    for k, mass in enumerate((0.6, 0.3, 0.1)):
+        a.scatter_add_(1, cls[:, k:k + 1], torch.full((B, 1), mass))
+    return v, q, a
+
+
+# ----------------------------------------------------------------------------------------- CPU oracle
+def cpu_oracle_rate(model, Bc, N, C, steps, warmup, train):
+    """samples/s of the restated reference on the host cores (torch CPU, all threads)."""
+    from oracle import reasoning_core as rc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = rc.synth_state_dict(model, C, seed=10, num_regions=N)
+    gen = torch.Generator().manual_seed(1234)
+    v, q, a = make_batch(Bc, N, C, "cpu", gen)
+    drop = rc.torch_drop if train else rc.no_drop
+    for _ in range(warmup):
+        rc.step(model, sd, v, q, a, drop=drop, num_regions=N)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rc.step(model, sd, v, q, a, drop=drop, num_regions=N)
+    dt = time.perf_counter() - t0
+    return Bc * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    C = NUM_ANS[args.model]
+    rate, per_step, cores = cpu_oracle_rate(args.model, args.cpu_batch, args.regions, C, args.steps,
+                                            min(args.warmup, 2), not args.eval_mode)
+    sample = "%s fwd+KLD+bwd, reference-form oracle (materialised pairwise/compound tensors), batch %d x %d regions, " \
+             "%s mode, torch CPU %d threads, %d steps" % (args.model, args.cpu_batch, args.regions,
+                                                          "eval" if args.eval_mode else "train", cores, args.steps)
+    line = {
+        "impl": "reference", "metric": "%s train samples/sec (fwd+bwd)" % args.model, "value": rate,
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2),
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, C),
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, C):
+    return {"workload": "%s fwd+KLD-loss+bwd, batch %d/GPU x %d regions x 2048-d + 2400-d question, %d answers, "
+                        "%s mode, %s" % (args.model, args.batch, args.regions, C,
+                                         "eval" if args.eval_mode else "train (Philox dropout p=0.5)",
+                                         "stock config/CoR2.py chain (att1 -> compound -> att2)" if args.model == "CoR2"
+                                         else "stock config/ODA.py"),
+            "precision": args.precision, "parallelism": "dp%d" % args.gpus,
+            "l2": "inputs rotate over 4 distinct batches and each step touches >0.6 GB of activations (> 126 MB L2)"}
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import importlib
+    import ctypes
+    from vqa_playground_pytorch_b200 import _lib, ops
+    from vqa_playground_pytorch_b200.parallel import DataParallelEngine
+    cf = importlib.import_module("vqa_playground_pytorch_b200.config." + args.model)
+    L = _lib.lib()
+    C, B, N = NUM_ANS[args.model], args.batch, args.regions
+
+    torch.manual_seed(10)                      # reference default init under manual_seed(10) (config/CoR2.py:244)
+    model = cf.Model(None, C, num_regions=N, precision=args.precision).to(dev)
+    model.train(not args.eval_mode)
+    ops.manual_seed(1234 + rank)
+    engine = DataParallelEngine(model)
+    engine.broadcast_parameters()
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host = [make_batch(B, N, C, "cpu", gen) for _ in range(4)]
+    pinned = [tuple(t.pin_memory() for t in b) for b in host]
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+
+    def step(v, q, a):
+        logits = model({"v": v, "q_idxes": q})
+        loss = ops.kld_loss_rows(logits, a).sum()
+        loss.backward()
+        engine.wait()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs
+    for i in range(args.warmup):
+        step(*resident[i % 4])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = L.vqa_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(*resident[i % 4])
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    launches = L.vqa_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the loss, every step
+    def e2e_step(i):
+        v, q, a = (t.to(dev, non_blocking=True) for t in pinned[i % 4])
+        return step(v, q, a).item()
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in pinned[0])
+
+    # ---- per-op timing (same step, CUDA events around every plan op) -> roofline of the dominant op
+    roof, breakdown = None, None
+    if rank == 0:
+        L.vqa_profile_begin()
+        nprof = min(args.steps, 10)
+        for i in range(nprof):
+            step(*resident[i % 4])
+        torch.cuda.synchronize()
+        buf = ctypes.create_string_buffer(1 << 16)
+        L.vqa_profile_end(buf, len(buf))
+        per_op = {}
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, rest = item.split("=")
+                tot, cnt = rest.split("/")
+                per_op[name] = float(tot) / int(cnt)
+        total = sum(per_op.values())
+        work = op_work(args.model, B, N, C)
+        pk = peaks()
+        breakdown = {k: round(v, 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])}
+        top = max(per_op, key=per_op.get)
+        kind, amount = work.get(top, ("hbm", 0.0))
+        dur = per_op[top] * 1e-3
+        if kind == "tensor":
+            ach = amount / dur / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tensor"], "traffic": None,
+                    "note": "%s math; peak = measured dense bf16 (sustained), %s" % (args.precision, pk["src"])}
+        else:
+            ach = amount / dur / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": None, "note": pk["src"]}
+        roof["share_of_step"] = per_op[top] / total if total else None
+        roof["ms"] = per_op[top]
+    if world > 1:
+        dist.barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, per_step, cores = cpu_oracle_rate(args.model, args.cpu_batch, N, C, 3, 1, not args.eval_mode)
+        cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "oracle (restated reference, torch CPU, %d threads), %s fwd+KLD+bwd at batch %d x %d regions, "
+                         "3 steps after 1 warm-up (%.2f s/step)" % (cores, args.model, args.cpu_batch, N, per_step)}
+
+    if rank == 0:
+        line = {
+            "metric": "%s train samples/sec (fwd+bwd)" % args.model, "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, C),
+            "clocks": sampler.result(),
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "per_op_ms": breakdown,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

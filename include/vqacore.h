@@ -63,6 +63,13 @@ int vqa_device_check(void);
 /* sizeof() of a parameter struct by name ("vqa_linear_fwd_params", ...); 0 if unknown. Lets a
  * binding written in another language verify its mirror of the layouts below. */
 size_t vqa_sizeof(const char* struct_name);
+/* Number of kernels this library has launched in this process (all threads). */
+unsigned long long vqa_launch_count(void);
+/* Optional per-op timing of the whole-model plans: between begin and end every op of vqa_*_fwd/bwd is
+ * bracketed by CUDA events on the caller's stream; end() synchronises them and writes
+ * "op=total_ms/count;..." into buf. Used by bench.py for the roofline of the dominant kernel. */
+int vqa_profile_begin(void);
+int vqa_profile_end(char* buf, size_t cap);
 
 typedef struct {
   float p;            /* drop probability; 0 disables */

@@ -56,6 +56,11 @@ def no_drop(x, p, layer_id):
     return x
 
 
+def torch_drop(x, p, layer_id):
+    """Stock F.dropout (torch's generator), as the reference runs it; used for CPU timing only."""
+    return F.dropout(x, p=p, training=True)
+
+
 class PhiloxDrop:
     """Deterministic train-mode dropout: x * keep / (1-p), keep from oracle/philox.py."""
 

@@ -1,0 +1,104 @@
+"""Parity proper: the CUDA path, called through the product's public API (config.<M>.Model -> C ABI),
+against (i) the golden vectors made by the unmodified reference and (ii) the oracle on seeded inputs."""
+import pytest
+import torch
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_against_oracle(out, ref, tol=parity.FP32_TOL):
+    assert parity.rel_err(out["logits"], ref["logits"]) <= tol
+    assert abs(out["loss"].item() - ref["loss"].item()) <= tol * abs(ref["loss"].item())
+    fa, fb = parity.flatten_alpha(out["alpha_dict"]), parity.flatten_alpha(ref["alpha_dict"])
+    assert set(fa) == set(fb)
+    for k in fb:
+        assert parity.rel_err(fa[k], fb[k]) <= tol, k
+    gmax = max(g.abs().max().item() for g in ref["grads"].values())
+    for k, g in ref["grads"].items():
+        if k.endswith("conv_att.conv.bias"):      # analytically zero on both sides
+            assert out["grads"][k].abs().max().item() <= 1e-6 * gmax, k
+            continue
+        assert parity.rel_err(out["grads"][k], g, 1e-6 * gmax) <= tol, k
+
+
+@pytest.mark.parametrize("name", parity.GOLDEN_CASES)
+def test_cuda_matches_reference_golden(cuda, name):
+    from oracle import reasoning_core as rc
+    z, meta = parity.load_golden(name)
+    seed = None if meta["train_seed"] < 0 else int(meta["train_seed"])
+    model, B, C = meta["model"], int(meta["B"]), int(meta["num_ans"])
+    sd = rc.synth_state_dict(model, C, seed=int(meta["weight_seed"]))
+    v, q, a = rc.synth_inputs(B, 36, C, seed=int(meta["input_seed"]))
+    out = parity.run_cuda_model(model, sd, v, q, a, train_seed=seed)
+    assert parity.rel_err(out["logits"], z["logits"]) <= parity.FP32_TOL
+    assert abs(out["loss"].item() - float(z["loss"])) <= parity.FP32_TOL * abs(float(z["loss"]))
+    for k, t in parity.flatten_alpha(out["alpha_dict"]).items():
+        assert parity.rel_err(t, z["alpha." + k]) <= parity.FP32_TOL, k
+    floor = parity.golden_grad_floor(z)
+    for n in parity.golden_grad_names(z):
+        if n.startswith("__") or n.endswith("conv_att.conv.bias"):
+            continue
+        assert parity.compare_grad_to_golden(z, n, out["grads"][n], floor) <= parity.FP32_TOL, n
+
+
+@pytest.mark.parametrize("model,C", [("CoR2", 2000), ("ODA", 3000)])
+@pytest.mark.parametrize("B,N,seed", [(2, 36, None), (7, 36, 11), (3, 10, None), (3, 10, 5), (2, 100, None),
+                                      (2, 100, 9), (33, 36, 3)])
+def test_cuda_matches_oracle(cuda, model, C, B, N, seed):
+    sd, (v, q, a), ref = parity.oracle_case(model, B, C, N=N, train_seed=seed, weight_seed=21, input_seed=B * 1000 + N)
+    out = parity.run_cuda_model(model, sd, v, q, a, N=N, train_seed=seed)
+    _check_against_oracle(out, ref)
+
+
+@pytest.mark.parametrize("model,C", [("CoR2", 2000), ("ODA", 3000)])
+def test_batch_of_one(cuda, model, C):
+    """The reference crashes at B=1 (e.squeeze() drops the batch dim); parity is taken from
+    the B=2 oracle run with the row duplicated."""
+    sd, (v, q, a), ref = parity.oracle_case(model, 2, C, weight_seed=4, input_seed=8)
+    v2, q2, a2 = v[:1].repeat(2, 1, 1), q[:1].repeat(2, 1), a[:1].repeat(2, 1)
+    from oracle import reasoning_core as rc
+    ref2 = rc.step(model, sd, v2, q2, a2)
+    out = parity.run_cuda_model(model, sd, v[:1], q[:1], a[:1])
+    assert parity.rel_err(out["logits"], ref2["logits"][:1]) <= parity.FP32_TOL
+    gmax = max(g.abs().max().item() for g in ref2["grads"].values())
+    for k, g in ref2["grads"].items():
+        if k.endswith("conv_att.conv.bias"):
+            continue
+        assert parity.rel_err(out["grads"][k] * 2.0, g, 1e-6 * gmax) <= parity.FP32_TOL, k
+
+
+def test_full_size_properties(cuda):
+    """BASELINE config (CoR2, B=256, N=36): size-independent properties instead of an oracle run:
+    every alpha column sums to 1, batch rows are independent (a row's logits do not depend on its
+    neighbours), eval is deterministic, the train mask depends only on (seed, index)."""
+    from oracle import reasoning_core as rc
+    from vqa_playground_pytorch_b200.config import CoR2
+    B, N, C = 256, 36, 2000
+    sd = rc.synth_state_dict("CoR2", C, seed=10)
+    m = CoR2.Model(None, C)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    v = torch.relu(torch.randn(B, N, 2048, device="cuda", generator=g))
+    q = 0.1 * torch.relu(torch.randn(B, 2400, device="cuda", generator=g))
+    y1 = m({"v": v, "q_idxes": q})
+    a1 = torch.cat(m.alpha_dict["alpha1"], 2)
+    assert torch.allclose(a1.sum(1), torch.ones(B, 4, device="cuda"), atol=1e-5)
+    y2 = m({"v": v, "q_idxes": q})
+    assert torch.equal(y1, y2)
+    ys = m({"v": v[100:132], "q_idxes": q[100:132]})
+    assert parity.rel_err(ys, y1[100:132]) <= 1e-5
+    m.train()
+    m.fixed_seed = 99
+    t1 = m({"v": v, "q_idxes": q})
+    t2 = m({"v": v, "q_idxes": q})
+    assert torch.equal(t1, t2)
+    m.fixed_seed = 100
+    t3 = m({"v": v, "q_idxes": q})
+    assert not torch.equal(t1, t3)
+    ts = m({"v": v[:32], "q_idxes": q[:32]})          # rows 0..31 keep their mask indices
+    m.fixed_seed = 99
+    ts = m({"v": v[:32], "q_idxes": q[:32]})
+    assert parity.rel_err(ts, t1[:32]) <= 1e-5

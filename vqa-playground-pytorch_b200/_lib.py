@@ -124,6 +124,9 @@ SYMBOLS = {
     "vqa_last_error": (C.c_char_p, []),
     "vqa_device_check": (C.c_int, []),
     "vqa_sizeof": (C.c_size_t, [C.c_char_p]),
+    "vqa_launch_count": (C.c_ulonglong, []),
+    "vqa_profile_begin": (C.c_int, []),
+    "vqa_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
     "vqa_linear_fwd": _OP(LinearFwd), "vqa_linear_bwd": _OP(LinearBwd),
     "vqa_mutan_fwd": _OP(MutanFwd), "vqa_mutan_bwd": _OP(MutanBwd),
     "vqa_region_softmax_pool_fwd": _OP(PoolFwd), "vqa_region_softmax_pool_bwd": _OP(PoolBwd),

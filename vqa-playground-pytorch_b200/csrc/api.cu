@@ -1,6 +1,10 @@
 // Library-level entry points: ABI version, thread-local error string, device check.
 #include "common.cuh"
 #include <string.h>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
 
 namespace vqa {
 
@@ -13,7 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+
 int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
@@ -35,7 +42,70 @@ int sm_count() {
   return cached;
 }
 
+// ---- optional per-op timing of the whole-model plans (CUDA events on the caller's stream) -----
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+ProfScope::ProfScope(void* stream, const char* name) : idx(-1), st(stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r;
+  r.name = name;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, (cudaStream_t)stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  idx = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[idx].b, (cudaStream_t)st);
+}
+
 }  // namespace vqa
+
+extern "C" unsigned long long vqa_launch_count(void) { return vqa::g_launches.load(); }
+
+extern "C" int vqa_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(vqa::g_prof_mu);
+  for (auto& r : vqa::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  vqa::g_prof.clear();
+  vqa::g_prof_on.store(1);
+  return VQA_OK;
+}
+
+// Writes "name=total_ms/count;..." (aggregated by name, first-seen order) into buf. Synchronises the events.
+extern "C" int vqa_profile_end(char* buf, size_t cap) {
+  using namespace vqa;
+  g_prof_on.store(0);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::vector<std::string> names;
+  std::vector<double> tot;
+  std::vector<int> cnt;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) {
+      cudaGetLastError();
+      ms = 0.f;
+    }
+    size_t i = 0;
+    for (; i < names.size(); ++i) if (names[i] == r.name) break;
+    if (i == names.size()) { names.push_back(r.name); tot.push_back(0); cnt.push_back(0); }
+    tot[i] += ms; cnt[i] += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  std::string out;
+  char tmp[256];
+  for (size_t i = 0; i < names.size(); ++i) {
+    snprintf(tmp, sizeof(tmp), "%s=%.6f/%d;", names[i].c_str(), tot[i], cnt[i]);
+    out += tmp;
+  }
+  if (buf && cap) { strncpy(buf, out.c_str(), cap - 1); buf[cap - 1] = 0; }
+  return out.size() < cap ? VQA_OK : VQA_EINVAL;
+}
 
 extern "C" int vqa_abi_version(void) { return VQA_ABI_VERSION; }
 extern "C" const char* vqa_last_error(void) { return vqa::g_err; }

@@ -14,6 +14,13 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);          // cudaGetLastError -> VQA_ECUDA
 int sm_count();
 
+// Times one op of a whole-model plan when vqa_profile_begin() is active (no-op otherwise).
+struct ProfScope {
+  int idx; void* st;
+  ProfScope(void* stream, const char* name);
+  ~ProfScope();
+};
+
 #define VQA_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

@@ -219,54 +219,54 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
     int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
     int64_t ldy[4] = {H, H, H, H}; uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
-    VQA_TRY(lin_fwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+    { ProfScope ps_(stream, "q_proj4.fwd"); VQA_TRY(lin_fwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
   {  // gates g1, g2 = sigmoid(310->2048) (config/CoR2.py:195-196)
     const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {H, H}; int widx[2] = {EQ1, EQ2};
     float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; uint32_t layer[2] = {L_EQ1, L_EQ2};
-    VQA_TRY(lin_fwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer));
+    { ProfScope ps_(stream, "gates.fwd"); VQA_TRY(lin_fwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer)); }
   }
   {  // compress_v (config/CoR2.py:213)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
-  VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, w.ql, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1));   // fusion_vq1 :214
+  { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, w.ql, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1)); }   // fusion_vq1 :214
   {  // att1 on raw v (:214)
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed;
     ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.bc = c.W[ATT1_CONV + 1]; ap.x = p->v;
     ap.alpha = p->alpha1; ap.pooled = w.pooled1;
-    VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream));
+    { ProfScope ps_(stream, "att1.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
   }
-  VQA_TRY(glimpse_fwd(c, B, w.pooled1, ATT1_G, w.vf, 2 * A, 0, L_ATT1_G));
+  { ProfScope ps_(stream, "att1.glimpse.fwd"); VQA_TRY(glimpse_fwd(c, B, w.pooled1, ATT1_G, w.vf, 2 * A, 0, L_ATT1_G)); }
   {  // compound objects (:215-216)
     vqa_cor_compound_fwd_params cp = {};
     cp.B = B; cp.N = N; cp.D = D; cp.x = p->v; cp.pooled = w.pooled1; cp.alpha = p->alpha1; cp.g1 = w.g1; cp.g2 = w.g2;
     cp.v2 = p->v2;
-    VQA_TRY(vqa_cor_compound_fwd(&cp, stream));
+    { ProfScope ps_(stream, "compound.fwd"); VQA_TRY(vqa_cor_compound_fwd(&cp, stream)); }
   }
   {  // compress_v2 (:218)
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; float* Y[1] = {w.v2l};
     int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V2};
-    VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+    { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
-  VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, w.ql, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2));  // fusion_vq2 :219
+  { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, w.ql, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2)); }  // fusion_vq2 :219
   {  // att2 on v2 (:219)
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed;
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.bc = c.W[ATT2_CONV + 1]; ap.x = p->v2;
     ap.alpha = p->alpha2; ap.pooled = w.pooled2;
-    VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream));
+    { ProfScope ps_(stream, "att2.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
   }
-  VQA_TRY(glimpse_fwd(c, B, w.pooled2, ATT2_G, w.vf, 2 * A, A, L_ATT2_G));
-  VQA_TRY(mutan_fwd(c, 2, B, 2 * A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf));    // fusion_final :233
+  { ProfScope ps_(stream, "att2.glimpse.fwd"); VQA_TRY(glimpse_fwd(c, B, w.pooled2, ATT2_G, w.vf, 2 * A, A, L_ATT2_G)); }
+  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 2, B, 2 * A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf)); }    // fusion_final :233
   {  // linear_classif (:236)
     const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
-    VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer));
+    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer)); }
   }
   return VQA_OK;
 }
@@ -284,11 +284,11 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
     float* dX[1] = {w.dxf}; int64_t lddx[1] = {F}; uint32_t layer[1] = {L_CLASSIF};
-    VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer));
+    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer)); }
   }
-  VQA_TRY(mutan_bwd(c, 2, B, 2 * A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, w.d_ff_H2, w.dvf, w.dqf, 0));
+  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 2, B, 2 * A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, w.d_ff_H2, w.dvf, w.dqf, 0)); }
   // ---- att2 branch
-  VQA_TRY(glimpse_bwd(c, B, w.pooled2, ATT2_G, w.vf, w.dvf, 2 * A, A, w.dpooled2, L_ATT2_G));
+  { ProfScope ps_(stream, "att2.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled2, ATT2_G, w.vf, w.dvf, 2 * A, A, w.dpooled2, L_ATT2_G)); }
   {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
@@ -297,29 +297,29 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.x = p->v2; ap.alpha = p->alpha2; ap.dpooled = w.dpooled2;
     ap.dalpha0_ext = nullptr; ap.dalpha = w.dalpha2; ap.dz = w.dz2;
     ap.dWc = c.grad(ATT2_CONV); ap.dbc = c.grad(ATT2_CONV + 1); ap.dfuse = w.dfuse2; ap.dx = w.dv2;
-    VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream));
+    { ProfScope ps_(stream, "att2.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
-  VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, w.ql, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, w.d_f2_H2, w.dv2l, w.dql, 0));
+  { ProfScope ps_(stream, "fusion_vq2.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, w.ql, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, w.d_f2_H2, w.dv2l, w.dql, 0)); }
   {  // compress_v2: dgrad accumulates into dv2 (v2 feeds both compress_v2 and att2's pooling)
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; const float* Y[1] = {w.v2l};
     int64_t ldy[1] = {H}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {H};
     float* dX[1] = {w.dv2}; int64_t lddx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V2};
-    VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 1, layer));
+    { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 1, layer)); }
   }
   // ---- att1 branch: glimpse linears first (they initialise dpooled1), then the compound objects add to it
-  VQA_TRY(glimpse_bwd(c, B, w.pooled1, ATT1_G, w.vf, w.dvf, 2 * A, 0, w.dpooled1, L_ATT1_G));
+  { ProfScope ps_(stream, "att1.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled1, ATT1_G, w.vf, w.dvf, 2 * A, 0, w.dpooled1, L_ATT1_G)); }
   {
     vqa_cor_compound_bwd_params cp = {};
     cp.B = B; cp.N = N; cp.D = D; cp.x = p->v; cp.pooled = w.pooled1; cp.alpha = p->alpha1; cp.g1 = w.g1; cp.g2 = w.g2;
     cp.dv2 = w.dv2; cp.dg1 = w.dg1; cp.dg2 = w.dg2; cp.dpooled = w.dpooled1; cp.dalpha0_ext = w.dalpha_ext;
-    VQA_TRY(vqa_cor_compound_bwd(&cp, stream));
+    { ProfScope ps_(stream, "compound.bwd"); VQA_TRY(vqa_cor_compound_bwd(&cp, stream)); }
   }
   {  // gates
     const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {H, H}; int widx[2] = {EQ1, EQ2};
     const float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; const float* dY[2] = {w.dg1, w.dg2};
     int64_t lddy[2] = {D, D}; float* dX[2] = {w.dhq1, w.dhq2}; int64_t lddx[2] = {H, H};
     uint32_t layer[2] = {L_EQ1, L_EQ2};
-    VQA_TRY(lin_bwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer));
+    { ProfScope ps_(stream, "gates.bwd"); VQA_TRY(lin_bwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer)); }
   }
   {
     vqa_region_softmax_pool_bwd_params ap = {};
@@ -329,20 +329,20 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.dpooled = w.dpooled1;
     ap.dalpha0_ext = w.dalpha_ext; ap.dalpha = w.dalpha1; ap.dz = w.dz1;
     ap.dWc = c.grad(ATT1_CONV); ap.dbc = c.grad(ATT1_CONV + 1); ap.dfuse = w.dfuse1; ap.dx = nullptr;
-    VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream));
+    { ProfScope ps_(stream, "att1.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
-  VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, w.ql, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, w.d_f1_H2, w.dvl, w.dql, 1));
+  { ProfScope ps_(stream, "fusion_vq1.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, w.ql, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, w.d_f1_H2, w.dvl, w.dql, 1)); }
   {  // compress_v: v is a graph input, no dgrad
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer));
+    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
   {  // the four question projections
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
     int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; const float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
     int64_t ldy[4] = {H, H, H, H}; const float* dY[4] = {w.dql, w.dhq1, w.dhq2, w.dqf}; int64_t lddy[4] = {H, H, H, H};
     uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
-    VQA_TRY(lin_bwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer));
+    { ProfScope ps_(stream, "q_proj4.bwd"); VQA_TRY(lin_bwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
   return VQA_OK;
 }
@@ -362,12 +362,12 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // compress_v (config/ODA.py:211)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
   {  // compress_q + linear_q (:214, :233)
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
     float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, H}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
-    VQA_TRY(lin_fwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer));
+    { ProfScope ps_(stream, "q_proj2.fwd"); VQA_TRY(lin_fwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
   {  // pairwise differences + conv_att + softmax + pooling (:216-226)
     vqa_oda_pair_attn_fwd_params ap = {};
@@ -375,14 +375,14 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT_CONV; ap.drop.seed = p->seed;
     ap.vl = w.vl; ap.ql = w.ql; ap.W = c.W[ATT_CONV]; ap.bc = c.W[ATT_CONV + 1]; ap.x = p->v; ap.wsum = w.wsum;
     ap.alpha = p->alpha1; ap.pooled = w.pooled;
-    VQA_TRY(vqa_oda_pair_attn_fwd(&ap, stream));
+    { ProfScope ps_(stream, "oda_pair_attn.fwd"); VQA_TRY(vqa_oda_pair_attn_fwd(&ap, stream)); }
   }
-  VQA_TRY(glimpse_fwd(c, B, w.pooled, ATT_G, w.vf, A, 0, L_ATT_G));
-  VQA_TRY(mutan_fwd(c, 5, B, A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf));       // fusion_final :236
+  { ProfScope ps_(stream, "att.glimpse.fwd"); VQA_TRY(glimpse_fwd(c, B, w.pooled, ATT_G, w.vf, A, 0, L_ATT_G)); }
+  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 5, B, A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf)); }       // fusion_final :236
   {  // linear_classif (:239)
     const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
-    VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer));
+    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer)); }
   }
   return VQA_OK;
 }
@@ -400,10 +400,10 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
     const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
     float* dX[1] = {w.dxf}; int64_t lddx[1] = {F}; uint32_t layer[1] = {L_CLASSIF};
-    VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer));
+    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer)); }
   }
-  VQA_TRY(mutan_bwd(c, 5, B, A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, w.d_ff_H2, w.dvf, w.dqf, 0));
-  VQA_TRY(glimpse_bwd(c, B, w.pooled, ATT_G, w.vf, w.dvf, A, 0, w.dpooled, L_ATT_G));
+  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 5, B, A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, w.d_ff_H2, w.dvf, w.dqf, 0)); }
+  { ProfScope ps_(stream, "att.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled, ATT_G, w.vf, w.dvf, A, 0, w.dpooled, L_ATT_G)); }
   {
     vqa_oda_pair_attn_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.H = H; ap.D = D; ap.train = p->train;
@@ -412,18 +412,18 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
     ap.vl = w.vl; ap.ql = w.ql; ap.W = c.W[ATT_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.wsum = w.wsum;
     ap.dpooled = w.dpooled; ap.dalpha = w.dalpha; ap.dz = w.dz; ap.dwsum = w.dwsum;
     ap.dW = c.grad(ATT_CONV); ap.dbc = c.grad(ATT_CONV + 1); ap.dvl = w.dvl; ap.dql = w.dql;
-    VQA_TRY(vqa_oda_pair_attn_bwd(&ap, stream));
+    { ProfScope ps_(stream, "oda_pair_attn.bwd"); VQA_TRY(vqa_oda_pair_attn_bwd(&ap, stream)); }
   }
   {
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer));
+    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
   {
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
     const float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, H}; const float* dY[2] = {w.dql, w.dqf};
     int64_t lddy[2] = {H, H}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
-    VQA_TRY(lin_bwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer));
+    { ProfScope ps_(stream, "q_proj2.bwd"); VQA_TRY(lin_bwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
   return VQA_OK;
 }

@@ -1,0 +1,126 @@
+"""Data-parallel training support: one process per GPU, gradients all-reduced over NCCL.
+
+Replaces the reference's only multi-GPU mechanism, single-process `nn.DataParallel`
+(train.py:517): every sample is independent through the whole forward, so the batch is
+sharded across ranks and the ONE collective is a SUM all-reduce of the parameter gradients
+(the loss is sum-reduced, train.py:541, so gradients are summed — not averaged — to match a
+single-GPU run at the global batch).
+
+Gradients live in one flat fp32 buffer laid out in BACKWARD-COMPLETION order; `p.grad` of every
+core parameter is a view into it and the backward kernels write there directly
+(ops.ModelCoreFn with a grad sink: no autograd copies).  The buffer is cut into a few
+contiguous buckets; a bucket is all-reduced on a side stream as soon as the backward plan has
+enqueued its last producer, so communication overlaps the remaining backward kernels.
+The host logic (layout, bucketing, reduction semantics) also runs on CPU tensors with the
+gloo backend, which is how tests/test_parallel.py covers world_size 2 without GPUs.
+"""
+import torch
+import torch.distributed as dist
+
+# state_dict index groups in the order the backward plans (csrc/model.cu) finish them
+_COR2_ORDER = [[52, 53], list(range(44, 52)), list(range(34, 42)), [32, 33], list(range(24, 32)), [2, 3],
+               list(range(16, 24)), [56, 57, 60, 61], [14, 15], list(range(6, 14)), [0, 1],
+               [4, 5, 54, 55, 58, 59, 42, 43]]
+_ODA_ORDER = [[36, 37], list(range(16, 36)), list(range(6, 14)), [4, 5], [0, 1], [2, 3, 14, 15]]
+COMPLETION_ORDER = {"CoR2": _COR2_ORDER, "ODA": _ODA_ORDER}
+
+
+def plan_buckets(sizes_in_order, num_buckets):
+    """Cut a sequence of tensor sizes into <= num_buckets contiguous buckets of roughly equal bytes.
+    Returns a list of (first_index, last_index_exclusive)."""
+    total = sum(sizes_in_order)
+    if not sizes_in_order:
+        return []
+    target = total / max(1, num_buckets)
+    buckets, start, acc = [], 0, 0
+    for i, s in enumerate(sizes_in_order):
+        acc += s
+        remaining_buckets = num_buckets - len(buckets) - 1
+        if acc >= target and remaining_buckets > 0 and i + 1 < len(sizes_in_order):
+            buckets.append((start, i + 1))
+            start, acc = i + 1, 0
+    buckets.append((start, len(sizes_in_order)))
+    return buckets
+
+
+class GradSink:
+    """Flat gradient buffer + its per-parameter views (see module docstring)."""
+
+    def __init__(self, params, model_name, num_buckets=4):
+        order = [i for grp in COMPLETION_ORDER[model_name] for i in grp]
+        assert sorted(order) == list(range(len(params))), "completion order must cover every parameter once"
+        self.order = order
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.slices = [None] * len(params)
+        offsets, off = {}, 0
+        for i in order:
+            n = params[i].numel()
+            self.slices[i] = self.flat[off:off + n].view(params[i].shape)
+            offsets[i] = (off, off + n)
+            off += n
+        # buckets are cut at completion-group boundaries
+        group_sizes = [sum(params[i].numel() for i in grp) for grp in COMPLETION_ORDER[model_name]]
+        self.bucket_groups = plan_buckets(group_sizes, num_buckets)
+        self.bucket_ranges = []
+        groups = COMPLETION_ORDER[model_name]
+        for g0, g1 in self.bucket_groups:
+            first, last = groups[g0][0], groups[g1 - 1][-1]
+            self.bucket_ranges.append((offsets[first][0], offsets[last][1]))
+        self.accumulate = False
+        for p, s in zip(params, self.slices):
+            p.grad = s
+
+    def after_backward(self):
+        pass
+
+
+class DataParallelEngine(GradSink):
+    """Wraps a config.<M>.Model for one-process-per-GPU data parallelism.
+
+        engine = DataParallelEngine(model)            # after dist.init_process_group
+        loss = ...; loss.backward(); engine.wait()    # grads now hold the global SUM
+    """
+
+    def __init__(self, model, num_buckets=4, process_group=None):
+        self.model = model
+        self.group = process_group
+        params = model.core_parameters()
+        super().__init__(params, model.MODEL, num_buckets)
+        self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.is_cuda = self.flat.is_cuda
+        self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.is_cuda else None
+        self._pending = []
+        model.grad_sink = self
+
+    def broadcast_parameters(self, src=0):
+        """Every rank starts from rank 0's weights (the reference's DataParallel replicates each step)."""
+        if self.world_size > 1:
+            for p in self.model.parameters():
+                dist.broadcast(p.data, src, group=self.group)
+
+    def reduce_bucket(self, k):
+        """All-reduce (SUM) bucket k on the communication stream once the work enqueued so far is done."""
+        if self.world_size == 1:
+            return
+        lo, hi = self.bucket_ranges[k]
+        chunk = self.flat[lo:hi]
+        if self.is_cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def after_backward(self):
+        # called by ops.ModelCoreFn.backward right after the backward plan has been enqueued
+        for k in range(len(self.bucket_ranges)):
+            self.reduce_bucket(k)
+
+    def wait(self):
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        if self.is_cuda and self.world_size > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)

@@ -100,7 +100,13 @@ typedef struct {
   float* Y[VQA_MAX_GROUPS];        int64_t ldy[VQA_MAX_GROUPS];
   uint32_t layer[VQA_MAX_GROUPS];
   uint64_t drop_index_base[VQA_MAX_GROUPS];
+  void* workspace;          /* >= vqa_linear_fwd_workspace_bytes(); may be NULL when that is 0 */
+  size_t workspace_bytes;
 } vqa_linear_fwd_params;
+/* Scratch the tensor-core paths need (padded copies of weights whose row stride is not a multiple of 16
+ * bytes, which TMA cannot address; the activation-gradient dZ in the backward). 0 for VQA_MATH_FP32_SIMT. */
+size_t vqa_linear_fwd_workspace_bytes(int math, int groups, int64_t M, int64_t K, int64_t N);
+size_t vqa_linear_bwd_workspace_bytes(int math, int groups, int64_t M, int64_t K, int64_t N);
 int vqa_linear_fwd(const vqa_linear_fwd_params* p, void* stream);
 
 /* Backward of the grouped linear.  dZ = dY (.) act'(Y);  dW_g (+)= dZ^T . dropout(X);
@@ -127,6 +133,8 @@ typedef struct {
   float* dX[VQA_MAX_GROUPS];       int64_t lddx[VQA_MAX_GROUPS];
   uint32_t layer[VQA_MAX_GROUPS];
   uint64_t drop_index_base[VQA_MAX_GROUPS];
+  void* workspace;          /* >= vqa_linear_bwd_workspace_bytes() */
+  size_t workspace_bytes;
 } vqa_linear_bwd_params;
 int vqa_linear_bwd(const vqa_linear_bwd_params* p, void* stream);
 
@@ -151,7 +159,12 @@ typedef struct {
   float* H1;      /* [R,M,F] or NULL */
   float* H2;      /* [R,Mh,F] */
   float* Y; int64_t ldy;
+  void* workspace;          /* >= vqa_mutan_workspace_bytes(.., bwd=0); 256-byte aligned */
+  size_t workspace_bytes;
 } vqa_mutan_fwd_params;
+/* Scratch of the tensor-core Mutan paths (padded stacked weights; dH1/dH2 in the backward); 0 for FP32_SIMT. */
+size_t vqa_mutan_workspace_bytes(int math, int R, int64_t M, int64_t rows_per_h2, int64_t K1, int64_t K2, int64_t F,
+                                 int bwd);
 int vqa_mutan_fwd(const vqa_mutan_fwd_params* p, void* stream);
 
 typedef struct {
@@ -174,6 +187,8 @@ typedef struct {
   float* dW2[VQA_MAX_GROUPS]; float* db2[VQA_MAX_GROUPS];
   float* dX1; int64_t lddx1;     /* NULL: skipped */
   float* dX2; int64_t lddx2;     /* NULL: skipped */
+  void* workspace;          /* >= vqa_mutan_workspace_bytes(.., bwd=1); 256-byte aligned */
+  size_t workspace_bytes;
 } vqa_mutan_bwd_params;
 int vqa_mutan_bwd(const vqa_mutan_bwd_params* p, void* stream);
 

@@ -34,20 +34,22 @@ class LinearFwd(C.Structure):
     _fields_ = [("groups", C.c_int), ("M", i64), ("K", i64), ("N", i64), ("act", C.c_int), ("math", C.c_int),
                 ("p", C.c_float), ("seed", C.c_uint64),
                 ("X", PA), ("ldx", IA), ("W", PA), ("b", PA), ("Y", PA), ("ldy", IA),
-                ("layer", U32A), ("drop_index_base", U64A)]
+                ("layer", U32A), ("drop_index_base", U64A), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
 class LinearBwd(C.Structure):
     _fields_ = [("groups", C.c_int), ("M", i64), ("K", i64), ("N", i64), ("act", C.c_int), ("math", C.c_int),
                 ("p", C.c_float), ("seed", C.c_uint64), ("accumulate_w", C.c_int), ("accumulate_x", C.c_int),
                 ("X", PA), ("ldx", IA), ("W", PA), ("Y", PA), ("ldy", IA), ("dY", PA), ("lddy", IA),
-                ("dW", PA), ("db", PA), ("dX", PA), ("lddx", IA), ("layer", U32A), ("drop_index_base", U64A)]
+                ("dW", PA), ("db", PA), ("dX", PA), ("lddx", IA), ("layer", U32A), ("drop_index_base", U64A),
+                ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
 class MutanFwd(C.Structure):
     _fields_ = [("R", C.c_int), ("M", i64), ("K1", i64), ("K2", i64), ("F", i64), ("rows_per_h2", i64),
                 ("math", C.c_int), ("X1", fp), ("ldx1", i64), ("X2", fp), ("ldx2", i64),
-                ("W1", PA), ("b1", PA), ("W2", PA), ("b2", PA), ("H1", fp), ("H2", fp), ("Y", fp), ("ldy", i64)]
+                ("W1", PA), ("b1", PA), ("W2", PA), ("b2", PA), ("H1", fp), ("H2", fp), ("Y", fp), ("ldy", i64),
+                ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
 class MutanBwd(C.Structure):
@@ -56,7 +58,8 @@ class MutanBwd(C.Structure):
                 ("X1", fp), ("ldx1", i64), ("X2", fp), ("ldx2", i64), ("W1", PA), ("W2", PA),
                 ("H1", fp), ("H2", fp), ("dY", fp), ("lddy", i64), ("dH2", fp),
                 ("dW1", PA), ("db1", PA), ("dW2", PA), ("db2", PA),
-                ("dX1", fp), ("lddx1", i64), ("dX2", fp), ("lddx2", i64)]
+                ("dX1", fp), ("lddx1", i64), ("dX2", fp), ("lddx2", i64),
+                ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
 class PoolFwd(C.Structure):
@@ -128,7 +131,10 @@ SYMBOLS = {
     "vqa_profile_begin": (C.c_int, []),
     "vqa_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
     "vqa_linear_fwd": _OP(LinearFwd), "vqa_linear_bwd": _OP(LinearBwd),
+    "vqa_linear_fwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),
+    "vqa_linear_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),
     "vqa_mutan_fwd": _OP(MutanFwd), "vqa_mutan_bwd": _OP(MutanBwd),
+    "vqa_mutan_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64, i64, i64, C.c_int]),
     "vqa_region_softmax_pool_fwd": _OP(PoolFwd), "vqa_region_softmax_pool_bwd": _OP(PoolBwd),
     "vqa_cor_compound_fwd": _OP(CompoundFwd), "vqa_cor_compound_bwd": _OP(CompoundBwd),
     "vqa_oda_pair_attn_fwd": _OP(OdaFwd), "vqa_oda_pair_attn_bwd": _OP(OdaBwd),

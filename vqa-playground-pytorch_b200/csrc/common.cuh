@@ -65,6 +65,20 @@ __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint32_t layer, u
   return s == 0 ? r.x : (s == 1 ? r.y : (s == 2 ? r.z : r.w));
 }
 
+// Words for four consecutive linear indices idx..idx+3 (idx need not be a multiple of 4).
+__device__ __forceinline__ void philox_words4(uint64_t seed, uint32_t layer, uint64_t idx, uint32_t (&w)[4]) {
+  const uint4 a = philox_quad(seed, layer, idx >> 2);
+  const uint32_t sh = (uint32_t)idx & 3u;
+  if (sh == 0) {
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    return;
+  }
+  const uint4 b = philox_quad(seed, layer, (idx >> 2) + 1);
+  const uint32_t t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) w[e] = t[sh + e];
+}
+
 // Device-side view of one dropout call site.
 struct Drop {
   uint64_t seed;

@@ -1,7 +1,614 @@
-// tcgen05 tensor-core GEMM family (placeholder until the TMA/TMEM kernels land in this file).
+// Host side of the tcgen05 GEMM family: TMA tensor-map construction, epilogue functors, launch plumbing
+// for the grouped linear forward / wgrad / dgrad (include/vqacore.h: vqa_linear_fwd / vqa_linear_bwd with
+// math = VQA_MATH_TF32X3 or VQA_MATH_TF32).  Kernel: tc_gemm.cuh.
 #include "gemm_tc.h"
 
+#include <mutex>
+
+#include "tc_gemm.cuh"
+
 namespace vqa {
-int tc_linear_fwd(const vqa_linear_fwd_params*, cudaStream_t) { return VQA_TC_UNSUPPORTED; }
-int tc_linear_bwd(const vqa_linear_bwd_params*, cudaStream_t) { return VQA_TC_UNSUPPORTED; }
+namespace tc {
+
+// ------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] row-major with row stride ld (elements); box = box_cols x box_rows, 128B swizzle.
+// Out-of-bounds parts of a box are zero-filled, which is what pads ragged M / N / K edges.
+static int make_tmap(CUtensorMap* out, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                     int box_rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return VQA_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for ptr=%p rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r,
+              (const void*)ptr, (long long)rows, (long long)cols, (long long)ld, box_cols, box_rows);
+    return VQA_ECUDA;
+  }
+  return VQA_OK;
+}
+
+static inline bool tma_ok(const void* ptr, int64_t ld) {
+  return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (ld % 4 == 0);
+}
+
+// K-major operand: source is [rows(M or N), K]; MN-major operand: source is [K, rows(M or N)].
+static int operand_tmap(CUtensorMap* out, const float* ptr, bool mn_major, int64_t mn_extent, int64_t k_extent,
+                        int64_t ld, int tile_mn) {
+  if (!mn_major) return make_tmap(out, ptr, mn_extent, k_extent, ld, BK, tile_mn, CU_TENSOR_MAP_SWIZZLE_128B);
+  return make_tmap(out, ptr, k_extent, mn_extent, ld, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+// ------------------------------------------------------------------------------------------ epilogues
+// Each receives 32 consecutive accumulator columns [n0, n0+32) of row m.
+
+// y = act(acc + bias), row-major store; columns in [N, Nstore) are written as zeros (padding that later
+// GEMMs read through TMA).
+struct EpiBiasAct {
+  float* Y[MAXG];
+  const float* bias[MAXG];
+  int64_t ld[MAXG];
+  int act;
+  int Nstore;
+  __device__ __forceinline__ void operator()(int g, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
+    if (m >= M) return;
+    float* y = Y[g] + m * ld[g];
+    const float* b = bias[g];
+    const bool vec = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const int n = n0 + c;
+      if (n >= Nstore) break;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (n + e < N) ? act_apply(act, v[c + e] + (b ? __ldg(b + n + e) : 0.0f)) : 0.0f;
+      if (vec && n + 3 < Nstore) {
+        *reinterpret_cast<float4*>(y + n) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < Nstore) y[n + e] = o[e];
+      }
+    }
+  }
+};
+
+// wgrad: D'(m' = input feature k, n' = output feature n) accumulated into dW[n, k] (row stride ldw) with
+// red.global.add (split-K partials and the "+=" of a flat gradient buffer are the same operation).
+struct EpiWgradT {
+  float* dW[MAXG];
+  int64_t ldw;
+  __device__ __forceinline__ void operator()(int g, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
+    if (m >= M) return;
+    float* w = dW[g];
+    if (!w) return;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int n = n0 + c;
+      if (n < N) atomicAdd(w + (int64_t)n * ldw + m, v[c]);      // consecutive lanes -> consecutive m: coalesced
+    }
+  }
+};
+
+// dgrad: dX[m, n] (=|+=) acc * mask(m*drop_ld + n) / (1-p)
+struct EpiDgrad {
+  float* dX[MAXG];
+  int64_t ld[MAXG];
+  int accumulate;
+  int drop_on;
+  Drop drop;
+  GroupDrop gd;
+  int64_t drop_ld;
+  __device__ __forceinline__ void operator()(int g, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
+    if (m >= M) return;
+    float* x = dX[g];
+    if (!x) return;
+    x += m * ld[g];
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const int n = n0 + c;
+      if (n >= N) break;
+      float o[4] = {v[c], v[c + 1], v[c + 2], v[c + 3]};
+      if (drop_on) {
+        const uint64_t idx = gd.base[g] + (uint64_t)(m * drop_ld + n);
+        uint32_t wd[4];
+        philox_words4(drop.seed, gd.layer[g], idx, wd);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = wd[e] >= drop.thr ? o[e] * drop.scale : 0.0f;
+      }
+      if (vec && n + 3 < N) {
+        float4* dst = reinterpret_cast<float4*>(x + n);
+        if (accumulate) {
+          const float4 old = *dst;
+          o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+        }
+        *dst = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < N) x[n + e] = accumulate ? x[n + e] + o[e] : o[e];
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------ launch
+template <int BN, bool X3, class Epi>
+static int launch_cfg(const Params<Epi>& p, int groups, cudaStream_t st, const char* what) {
+  using C = Cfg<BN, X3>;
+  auto kern = tc_gemm_kernel<BN, X3, Epi>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+    return check_launch(what);
+  dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(groups * p.k_splits));
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  return check_launch(what);
+}
+
+static inline int pick_bn(int64_t N) {
+  const int64_t w160 = cdiv(N, 160) * 160 - N, w128 = cdiv(N, 128) * 128 - N;
+  return w160 < w128 ? 160 : 128;
+}
+
+template <class Epi>
+static int launch(const Params<Epi>& p, int groups, bool x3, cudaStream_t st, const char* what) {
+  const int bn = pick_bn(p.N);
+  if (bn == 160) return x3 ? launch_cfg<160, true>(p, groups, st, what) : launch_cfg<160, false>(p, groups, st, what);
+  return x3 ? launch_cfg<128, true>(p, groups, st, what) : launch_cfg<128, false>(p, groups, st, what);
+}
+
+static void fill_drop(Drop& d, GroupDrop& gd, float pdrop, uint64_t seed, const uint32_t* layer, const uint64_t* base,
+                      int groups) {
+  d = make_drop(pdrop, seed, 0, 0);
+  for (int g = 0; g < MAXG; ++g) {
+    const int s = g < groups ? g : 0;
+    gd.layer[g] = layer[s];
+    gd.base[g] = base[s];
+  }
+}
+
+// dZ = dY (.) act'(Y) into a padded [M, ldz] buffer (pad columns zero) and db (+)= colsum(dZ).
+// grid = (cdiv(N,32), row chunks, groups); 256 threads = 8 rows x 32 columns.
+struct DzArgs {
+  const float* dY[MAXG]; const float* Y[MAXG]; float* dZ[MAXG]; float* db[MAXG];
+  int64_t lddy[MAXG], ldy[MAXG];
+};
+__global__ void __launch_bounds__(256)
+dz_colsum_kernel(DzArgs a, int64_t M, int64_t N, int64_t ldz, int act, int rows_per_cta) {
+  __shared__ float red[8][33];
+  const int g = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+  const float* dy = a.dY[g];
+  const float* y = a.Y[g];
+  float* dz = a.dZ[g];
+  float s = 0.0f;
+  for (int64_t m = r0 + ty; m < r1; m += 8) {
+    float v = 0.0f;
+    if (n < N) {
+      v = dy[m * a.lddy[g] + n];
+      if (act != VQA_ACT_NONE) v *= act_grad(act, y[m * a.ldy[g] + n]);
+    }
+    if (dz && n < ldz) dz[m * ldz + n] = v;
+    s += v;
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N && a.db[g]) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(a.db[g] + n, t);
+  }
+}
+
+// Padded copy of weights whose row stride (K*4 bytes) is not a multiple of 16 and therefore cannot be
+// addressed by TMA: dst[g][r, 0..Kp) = src[g][r, 0..K) | 0 for r < rows, zero rows up to rows_pad.
+// grid = (blocks, groups)
+struct PackArgs { const float* src[MAXG]; };
+__global__ void pack_rows_kernel(PackArgs a, float* __restrict__ dst, int64_t rows, int64_t rows_pad, int64_t K,
+                                 int64_t Kp) {
+  const int g = blockIdx.y;
+  const float* src = a.src[g];
+  float* d = dst + (size_t)g * rows_pad * Kp;
+  const int64_t total = rows_pad * Kp;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / Kp, k = t - r * Kp;
+    d[t] = (k < K && r < rows) ? src[r * K + k] : 0.0f;
+  }
+}
+
+static inline int64_t roundup(int64_t x, int64_t m) { return cdiv(x, m) * m; }
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int pack_weights(const float* const* W, int groups, int64_t rows, int64_t rows_pad, int64_t K, float* dst,
+                        cudaStream_t st) {
+  PackArgs a = {};
+  for (int g = 0; g < MAXG; ++g) a.src[g] = W[g < groups ? g : 0];
+  const int64_t Kp = roundup(K, 4);
+  int64_t blocks = cdiv(rows_pad * Kp, 256);
+  if (blocks > 4096) blocks = 4096;
+  pack_rows_kernel<<<dim3((unsigned)blocks, (unsigned)groups), 256, 0, st>>>(a, dst, rows, rows_pad, K, Kp);
+  return check_launch("pack_rows");
+}
+
+// ------------------------------------------------------------------------------------------ Mutan pieces
+// forward epilogue for rank r: h1 = acc + b1_r;  H1_r[m,n] = h1;  Y[m,n] (r ? += : =) h1 * H2_r[m / rows_per, n]
+struct EpiMutan {
+  const float* bias; const float* H2; float* H1; float* Y;
+  int64_t ldh, ldy, rows_per; int accumulate;
+  __device__ __forceinline__ void operator()(int, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
+    if (m >= M) return;
+    const float* h2 = H2 + (m / rows_per) * ldh;
+    float* h1 = H1 ? H1 + m * ldh : nullptr;
+    float* y = Y + m * ldy;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int n = n0 + c;
+      if (n < N) {
+        const float h = v[c] + (bias ? __ldg(bias + n) : 0.0f);
+        if (h1) h1[n] = h;
+        const float o = h * __ldg(h2 + n);
+        y[n] = accumulate ? y[n] + o : o;
+      }
+    }
+  }
+};
+
+// dH1cat[m, r*Fp + f] = dY[m,f] * H2[r, m/rows_per, f] (zero for f >= F), db1_r[f] += column sums.
+// grid = (cdiv(Fp,32), row chunks, R), 256 threads = 8 rows x 32 columns
+struct DbTable { float* p[MAXG]; };
+__global__ void __launch_bounds__(256)
+mutan_dh1_kernel(int64_t M, int64_t F, int64_t Fp, int64_t rows_per, int R, const float* __restrict__ dY, int64_t lddy,
+                 const float* __restrict__ H2, float* __restrict__ dH1cat, DbTable db, int rows_per_cta) {
+  __shared__ float red[8][33];
+  const int r = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t f = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t Mh = M / rows_per;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+  float s = 0.0f;
+  for (int64_t m = r0 + ty; m < r1; m += 8) {
+    float v = 0.0f;
+    if (f < F) v = dY[m * lddy + f] * H2[((int64_t)r * Mh + m / rows_per) * F + f];
+    if (f < Fp) dH1cat[m * (R * Fp) + r * Fp + f] = v;
+    s += v;
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && f < F && db.p[r]) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(db.p[r] + f, t);
+  }
+}
+
+// dH2cat[mh, r*Fp + f] = sum_{j<rows_per} dY[mh*rp+j, f] * H1[r, mh*rp+j, f];  db2_r[f] += over mh.
+// grid = (Mh, R)
+__global__ void mutan_dh2cat_kernel(int64_t M, int64_t F, int64_t Fp, int64_t rows_per, int R,
+                                    const float* __restrict__ dY, int64_t lddy, const float* __restrict__ H1,
+                                    float* __restrict__ dH2cat, DbTable db) {
+  const int64_t mh = blockIdx.x;
+  const int r = blockIdx.y;
+  for (int64_t f = threadIdx.x; f < Fp; f += blockDim.x) {
+    float s = 0.0f;
+    if (f < F) {
+      for (int64_t j = 0; j < rows_per; ++j) {
+        const int64_t m = mh * rows_per + j;
+        s = fmaf(dY[m * lddy + f], H1[((int64_t)r * M + m) * F + f], s);
+      }
+      if (db.p[r]) atomicAdd(db.p[r] + f, s);
+    }
+    dH2cat[mh * (R * Fp) + r * Fp + f] = s;
+  }
+}
+
+}  // namespace tc
+
+// ============================================================================================ linear fwd
+int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
+  using namespace tc;
+  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return VQA_TC_UNSUPPORTED;
+  if (p->M > INT32_MAX || p->K > INT32_MAX || p->N > INT32_MAX) return VQA_TC_UNSUPPORTED;
+  bool pack = false;
+  for (int g = 0; g < p->groups; ++g) {
+    if (!tma_ok(p->X[g], p->ldx[g])) return VQA_TC_UNSUPPORTED;
+    pack |= !tma_ok(p->W[g], p->K);
+  }
+  const int64_t Kp = roundup(p->K, 4);
+  float* wpk = reinterpret_cast<float*>(p->workspace);
+  if (pack) {
+    if (!wpk || p->workspace_bytes < (size_t)p->groups * p->N * Kp * sizeof(float) ||
+        reinterpret_cast<uintptr_t>(wpk) % 16 != 0)
+      return VQA_TC_UNSUPPORTED;
+    VQA_TRY(pack_weights(p->W, p->groups, p->N, p->N, p->K, wpk, st));
+  }
+  const int bn = pick_bn(p->N);
+  Params<EpiBiasAct> q = {};
+  for (int g = 0; g < MAXG; ++g) {
+    const int s = g < p->groups ? g : 0;
+    VQA_TRY(operand_tmap(&q.tmA[g], p->X[s], false, p->M, p->K, p->ldx[s], BM));
+    if (pack) VQA_TRY(operand_tmap(&q.tmB[g], wpk + (size_t)s * p->N * Kp, false, p->N, p->K, Kp, bn));
+    else VQA_TRY(operand_tmap(&q.tmB[g], p->W[s], false, p->N, p->K, p->K, bn));
+    q.epi.Y[g] = p->Y[s]; q.epi.bias[g] = p->b[s]; q.epi.ld[g] = p->ldy[s];
+  }
+  q.M = (int)p->M; q.N = (int)p->N; q.K = (int)p->K; q.k_splits = 1; q.a_mn = 0; q.b_mn = 0;
+  q.drop_on = p->p > 0.0f;
+  fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
+  q.drop_ld = p->K;
+  q.epi.act = p->act;
+  q.epi.Nstore = (int)p->N;
+  return launch(q, p->groups, p->math == VQA_MATH_TF32X3, st, "tc_linear_fwd");
+}
+
+// ============================================================================================ linear bwd
+int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
+  using namespace tc;
+  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return VQA_TC_UNSUPPORTED;
+  if (p->M > INT32_MAX || p->K > INT32_MAX || p->N > INT32_MAX) return VQA_TC_UNSUPPORTED;
+  const bool x3 = p->math == VQA_MATH_TF32X3;
+  const int64_t ldz = roundup(p->N, 32);
+  const int64_t Kp = roundup(p->K, 4);
+  const size_t dz_bytes = align256((size_t)p->groups * p->M * ldz * sizeof(float));
+  bool any_w = false, any_x = false, pack = false;
+  for (int g = 0; g < p->groups; ++g) {
+    if (!tma_ok(p->X[g], p->ldx[g])) return VQA_TC_UNSUPPORTED;
+    any_w |= p->dW[g] != nullptr || p->db[g] != nullptr;
+    if (p->dX[g]) {
+      any_x = true;
+      pack |= !tma_ok(p->W[g], p->K);
+    }
+  }
+  const size_t need = dz_bytes + (pack ? (size_t)p->groups * p->N * Kp * sizeof(float) : 0);
+  if (!p->workspace || p->workspace_bytes < need) return VQA_TC_UNSUPPORTED;
+  float* dz = reinterpret_cast<float*>(p->workspace);
+  float* wpk = reinterpret_cast<float*>(reinterpret_cast<char*>(p->workspace) + dz_bytes);
+  if (reinterpret_cast<uintptr_t>(dz) % 16 != 0) return VQA_TC_UNSUPPORTED;
+  if (pack) VQA_TRY(pack_weights(p->W, p->groups, p->N, p->N, p->K, wpk, st));
+
+  // 1. dZ (padded) + bias gradient
+  {
+    DzArgs a = {};
+    for (int g = 0; g < MAXG; ++g) {
+      const int s = g < p->groups ? g : 0;
+      a.dY[g] = p->dY[s]; a.Y[g] = p->Y[s]; a.lddy[g] = p->lddy[s]; a.ldy[g] = p->ldy[s];
+      a.dZ[g] = dz + (size_t)s * p->M * ldz; a.db[g] = p->db[s];
+    }
+    if (!p->accumulate_w)
+      for (int g = 0; g < p->groups; ++g)
+        if (p->db[g]) cudaMemsetAsync(p->db[g], 0, (size_t)p->N * sizeof(float), st);
+    const int rows_per_cta = 64;
+    dim3 grid((unsigned)cdiv(ldz, 32), (unsigned)cdiv(p->M, rows_per_cta), (unsigned)p->groups);
+    dz_colsum_kernel<<<grid, 256, 0, st>>>(a, p->M, p->N, ldz, p->act, rows_per_cta);
+    VQA_TRY(check_launch("tc_linear_bwd.dz"));
+  }
+  // 2. wgrad: D'[K_in, N_out] = X~^T . dZ  (both operands MN-major views of row-major [M, .] tensors)
+  if (any_w) {
+    Params<EpiWgradT> q = {};
+    const int bn = pick_bn(p->N);
+    for (int g = 0; g < MAXG; ++g) {
+      const int s = g < p->groups ? g : 0;
+      VQA_TRY(operand_tmap(&q.tmA[g], p->X[s], true, p->K, p->M, p->ldx[s], BM));
+      VQA_TRY(operand_tmap(&q.tmB[g], dz + (size_t)s * p->M * ldz, true, p->N, p->M, ldz, bn));
+      q.epi.dW[g] = p->dW[s];
+    }
+    q.epi.ldw = p->K;
+    q.M = (int)p->K; q.N = (int)p->N; q.K = (int)p->M; q.a_mn = 1; q.b_mn = 1;
+    q.drop_on = p->p > 0.0f;
+    fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
+    q.drop_ld = p->K;
+    // split the reduction (over the M rows) so that the grid covers the chip
+    const int64_t tiles = cdiv(p->K, BM) * cdiv(p->N, bn) * p->groups;
+    const int64_t kb = cdiv(p->M, BK);
+    int64_t splits = cdiv((int64_t)sm_count(), tiles);
+    if (splits > kb / 4) splits = kb / 4;
+    if (splits < 1) splits = 1;
+    q.k_splits = (int)splits;
+    if (!p->accumulate_w)
+      for (int g = 0; g < p->groups; ++g)
+        if (p->dW[g]) cudaMemsetAsync(p->dW[g], 0, (size_t)p->N * p->K * sizeof(float), st);
+    VQA_TRY(launch(q, p->groups, x3, st, "tc_linear_bwd.wgrad"));
+  }
+  // 3. dgrad: dX[M, K_in] = dZ[M, N_out] . W[N_out, K_in]   (W is the MN-major B operand as stored)
+  if (any_x) {
+    Params<EpiDgrad> q = {};
+    const int bn = pick_bn(p->K);
+    for (int g = 0; g < MAXG; ++g) {
+      const int s = g < p->groups ? g : 0;
+      VQA_TRY(operand_tmap(&q.tmA[g], dz + (size_t)s * p->M * ldz, false, p->M, p->N, ldz, BM));
+      if (pack) VQA_TRY(operand_tmap(&q.tmB[g], wpk + (size_t)s * p->N * Kp, true, p->K, p->N, Kp, bn));
+      else VQA_TRY(operand_tmap(&q.tmB[g], p->W[s], true, p->K, p->N, p->K, bn));
+      q.epi.dX[g] = p->dX[s]; q.epi.ld[g] = p->lddx[s];
+    }
+    q.M = (int)p->M; q.N = (int)p->K; q.K = (int)p->N; q.k_splits = 1; q.a_mn = 0; q.b_mn = 1;
+    q.drop_on = 0;
+    fill_drop(q.drop, q.gd, 0.0f, p->seed, p->layer, p->drop_index_base, p->groups);
+    q.epi.accumulate = p->accumulate_x;
+    q.epi.drop_on = p->p > 0.0f;
+    fill_drop(q.epi.drop, q.epi.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
+    q.epi.drop_ld = p->K;
+    VQA_TRY(launch(q, p->groups, x3, st, "tc_linear_bwd.dgrad"));
+  }
+  return VQA_OK;
+}
+
+// ============================================================================================ Mutan
+// Workspace layout (floats): W1pk [R*Fp, K1p] | W2pk [R*Fp, K2p] | dH1cat [M, R*Fp] | dH2cat [Mh, R*Fp]
+struct MutanWs {
+  float *w1pk, *w2pk, *dh1, *dh2;
+  size_t bytes;
+};
+static MutanWs mutan_ws(void* base, int R, int64_t M, int64_t Mh, int64_t K1, int64_t K2, int64_t F, bool bwd) {
+  using namespace tc;
+  const int64_t Fp = roundup(F, 32), K1p = roundup(K1, 4), K2p = roundup(K2, 4);
+  char* b = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  MutanWs w;
+  auto take = [&](int64_t n) { float* p = b ? reinterpret_cast<float*>(b + off) : nullptr; off += align256((size_t)n * 4); return p; };
+  w.w1pk = take(R * Fp * K1p);
+  w.w2pk = take(R * Fp * K2p);
+  w.dh1 = bwd ? take(M * R * Fp) : nullptr;
+  w.dh2 = bwd ? take(Mh * R * Fp) : nullptr;
+  w.bytes = off;
+  return w;
+}
+size_t tc_mutan_ws(int math, int R, int64_t M, int64_t rows_per, int64_t K1, int64_t K2, int64_t F, int bwd) {
+  if (math == VQA_MATH_FP32_SIMT) return 0;
+  return mutan_ws(nullptr, R, M, M / rows_per, K1, K2, F, bwd != 0).bytes;
+}
+
+int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
+  using namespace tc;
+  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return VQA_TC_UNSUPPORTED;
+  if (!tma_ok(p->X1, p->ldx1) || !tma_ok(p->X2, p->ldx2) || p->M > INT32_MAX) return VQA_TC_UNSUPPORTED;
+  const int64_t Mh = p->M / p->rows_per_h2;
+  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, false);
+  if (!p->workspace || p->workspace_bytes < w.bytes || reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0)
+    return VQA_TC_UNSUPPORTED;
+  const bool x3 = p->math == VQA_MATH_TF32X3;
+  const int64_t Fp = roundup(p->F, 32), K1p = roundup(p->K1, 4), K2p = roundup(p->K2, 4);
+  VQA_TRY(pack_weights(p->W1, p->R, p->F, Fp, p->K1, w.w1pk, st));
+  VQA_TRY(pack_weights(p->W2, p->R, p->F, Fp, p->K2, w.w2pk, st));
+  const int bn = pick_bn(p->F);
+  {  // H2_r = X2 . W2_r^T + b2_r  (grouped over r)
+    Params<EpiBiasAct> q = {};
+    for (int g = 0; g < MAXG; ++g) {
+      const int s = g < p->R ? g : 0;
+      VQA_TRY(operand_tmap(&q.tmA[g], p->X2, false, Mh, p->K2, p->ldx2, BM));
+      VQA_TRY(operand_tmap(&q.tmB[g], w.w2pk + (size_t)s * Fp * K2p, false, p->F, p->K2, K2p, bn));
+      q.epi.Y[g] = p->H2 + (size_t)s * Mh * p->F; q.epi.bias[g] = p->b2[s]; q.epi.ld[g] = p->F;
+    }
+    q.M = (int)Mh; q.N = (int)p->F; q.K = (int)p->K2; q.k_splits = 1;
+    q.epi.act = VQA_ACT_NONE; q.epi.Nstore = (int)p->F;
+    VQA_TRY(launch(q, p->R, x3, st, "tc_mutan_fwd.h2"));
+  }
+  for (int r = 0; r < p->R; ++r) {   // rank by rank: Y is read-modify-written in stream order
+    Params<EpiMutan> q = {};
+    for (int g = 0; g < MAXG; ++g) {
+      VQA_TRY(operand_tmap(&q.tmA[g], p->X1, false, p->M, p->K1, p->ldx1, BM));
+      VQA_TRY(operand_tmap(&q.tmB[g], w.w1pk + (size_t)r * Fp * K1p, false, p->F, p->K1, K1p, bn));
+    }
+    q.M = (int)p->M; q.N = (int)p->F; q.K = (int)p->K1; q.k_splits = 1;
+    q.epi.bias = p->b1[r]; q.epi.H2 = p->H2 + (size_t)r * Mh * p->F;
+    q.epi.H1 = p->H1 ? p->H1 + (size_t)r * p->M * p->F : nullptr;
+    q.epi.Y = p->Y; q.epi.ldh = p->F; q.epi.ldy = p->ldy; q.epi.rows_per = p->rows_per_h2; q.epi.accumulate = r > 0;
+    VQA_TRY(launch(q, 1, x3, st, "tc_mutan_fwd.h1"));
+  }
+  return VQA_OK;
+}
+
+int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
+  using namespace tc;
+  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return VQA_TC_UNSUPPORTED;
+  if (!tma_ok(p->X1, p->ldx1) || !tma_ok(p->X2, p->ldx2) || p->M > INT32_MAX) return VQA_TC_UNSUPPORTED;
+  const int64_t Mh = p->M / p->rows_per_h2;
+  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, true);
+  if (!p->workspace || p->workspace_bytes < w.bytes || reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0)
+    return VQA_TC_UNSUPPORTED;
+  const bool x3 = p->math == VQA_MATH_TF32X3;
+  const int R = p->R;
+  const int64_t Fp = roundup(p->F, 32), K1p = roundup(p->K1, 4), K2p = roundup(p->K2, 4), RF = R * Fp;
+  VQA_TRY(pack_weights(p->W1, R, p->F, Fp, p->K1, w.w1pk, st));
+  VQA_TRY(pack_weights(p->W2, R, p->F, Fp, p->K2, w.w2pk, st));
+  if (!p->accumulate_w)
+    for (int r = 0; r < R; ++r) {
+      if (p->db1[r]) cudaMemsetAsync(p->db1[r], 0, (size_t)p->F * 4, st);
+      if (p->db2[r]) cudaMemsetAsync(p->db2[r], 0, (size_t)p->F * 4, st);
+      if (p->dW1[r]) cudaMemsetAsync(p->dW1[r], 0, (size_t)p->F * p->K1 * 4, st);
+      if (p->dW2[r]) cudaMemsetAsync(p->dW2[r], 0, (size_t)p->F * p->K2 * 4, st);
+    }
+  DbTable db1 = {}, db2 = {};
+  for (int r = 0; r < R; ++r) { db1.p[r] = p->db1[r]; db2.p[r] = p->db2[r]; }
+  mutan_dh2cat_kernel<<<dim3((unsigned)Mh, (unsigned)R), 256, 0, st>>>(p->M, p->F, Fp, p->rows_per_h2, R, p->dY,
+                                                                       p->lddy, p->H1, w.dh2, db2);
+  VQA_TRY(check_launch("tc_mutan_bwd.dh2"));
+  {
+    const int rows_per_cta = 64;
+    dim3 grid((unsigned)cdiv(Fp, 32), (unsigned)cdiv(p->M, rows_per_cta), (unsigned)R);
+    mutan_dh1_kernel<<<grid, 256, 0, st>>>(p->M, p->F, Fp, p->rows_per_h2, R, p->dY, p->lddy, p->H2, w.dh1, db1,
+                                           rows_per_cta);
+    VQA_TRY(check_launch("tc_mutan_bwd.dh1"));
+  }
+  auto wgrad = [&](const float* X, int64_t ldx, int64_t Krows, int64_t Kin, const float* dHcat, float* const* dW,
+                   const char* what) -> int {
+    // D'[Kin, F] = X^T[Kin, Krows] . dH_r[Krows, F], grouped over r
+    Params<EpiWgradT> q = {};
+    const int bn = pick_bn(p->F);
+    for (int g = 0; g < MAXG; ++g) {
+      const int s = g < R ? g : 0;
+      VQA_TRY(operand_tmap(&q.tmA[g], X, true, Kin, Krows, ldx, BM));
+      VQA_TRY(operand_tmap(&q.tmB[g], dHcat + (size_t)s * Fp, true, p->F, Krows, RF, bn));
+      q.epi.dW[g] = dW[s];
+    }
+    q.epi.ldw = Kin;
+    q.M = (int)Kin; q.N = (int)p->F; q.K = (int)Krows; q.a_mn = 1; q.b_mn = 1;
+    const int64_t tiles = cdiv(Kin, BM) * cdiv(p->F, bn) * R;
+    const int64_t kb = cdiv(Krows, BK);
+    int64_t splits = cdiv((int64_t)sm_count(), tiles);
+    if (splits > kb / 4) splits = kb / 4;
+    if (splits < 1) splits = 1;
+    q.k_splits = (int)splits;
+    return launch(q, R, x3, st, what);
+  };
+  auto dgrad = [&](const float* dHcat, int64_t rows, const float* Wpk, int64_t Kin, int64_t Kinp, float* dX,
+                   int64_t lddx, int accumulate, const char* what) -> int {
+    // dX[rows, Kin] = dHcat[rows, R*Fp] . Wpk[R*Fp, Kin]
+    Params<EpiDgrad> q = {};
+    const int bn = pick_bn(Kin);
+    for (int g = 0; g < MAXG; ++g) {
+      VQA_TRY(operand_tmap(&q.tmA[g], dHcat, false, rows, RF, RF, BM));
+      VQA_TRY(operand_tmap(&q.tmB[g], Wpk, true, Kin, RF, Kinp, bn));
+      q.epi.dX[g] = dX; q.epi.ld[g] = lddx;
+    }
+    q.M = (int)rows; q.N = (int)Kin; q.K = (int)RF; q.k_splits = 1; q.a_mn = 0; q.b_mn = 1;
+    q.epi.accumulate = accumulate; q.epi.drop_on = 0;
+    return launch(q, 1, x3, st, what);
+  };
+  VQA_TRY(wgrad(p->X1, p->ldx1, p->M, p->K1, w.dh1, p->dW1, "tc_mutan_bwd.dw1"));
+  if (p->dX1) VQA_TRY(dgrad(w.dh1, p->M, w.w1pk, p->K1, K1p, p->dX1, p->lddx1, p->accumulate_x1, "tc_mutan_bwd.dx1"));
+  VQA_TRY(wgrad(p->X2, p->ldx2, Mh, p->K2, w.dh2, p->dW2, "tc_mutan_bwd.dw2"));
+  if (p->dX2) VQA_TRY(dgrad(w.dh2, Mh, w.w2pk, p->K2, K2p, p->dX2, p->lddx2, p->accumulate_x2, "tc_mutan_bwd.dx2"));
+  return VQA_OK;
+}
+
+size_t tc_linear_fwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N) {
+  (void)M;
+  if (math == VQA_MATH_FP32_SIMT || K % 4 == 0) return 0;
+  return tc::align256((size_t)groups * N * tc::roundup(K, 4) * sizeof(float));
+}
+size_t tc_linear_bwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N) {
+  if (math == VQA_MATH_FP32_SIMT) return 0;
+  size_t b = tc::align256((size_t)groups * M * tc::roundup(N, 32) * sizeof(float));
+  if (K % 4 != 0) b += tc::align256((size_t)groups * N * tc::roundup(K, 4) * sizeof(float));
+  return b;
+}
+
 }  // namespace vqa

@@ -114,6 +114,13 @@ struct DgradStore {
 
 using namespace vqa;
 
+extern "C" size_t vqa_linear_fwd_workspace_bytes(int math, int groups, int64_t M, int64_t K, int64_t N) {
+  return tc_linear_fwd_ws(math, groups, M, K, N);
+}
+extern "C" size_t vqa_linear_bwd_workspace_bytes(int math, int groups, int64_t M, int64_t K, int64_t N) {
+  return tc_linear_bwd_ws(math, groups, M, K, N);
+}
+
 extern "C" int vqa_linear_fwd(const vqa_linear_fwd_params* p, void* stream) {
   VQA_REQUIRE(p != nullptr, "vqa_linear_fwd: null params");
   VQA_REQUIRE(p->groups >= 1 && p->groups <= VQA_MAX_GROUPS, "vqa_linear_fwd: groups=%d out of range", p->groups);

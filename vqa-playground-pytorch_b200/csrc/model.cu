@@ -7,6 +7,8 @@
 namespace vqa {
 
 constexpr int64_t H = 310, F = 510, A = 620, AG = 155, Q = 2400, D = 2048;
+// padded row strides of intermediates that are TMA operands of the tensor-core GEMMs (16-byte multiples)
+constexpr int64_t HP = 320, XP = 512;
 constexpr float P_DROP = 0.5f;
 
 // ---- state_dict indices -------------------------------------------------------------------------
@@ -44,31 +46,43 @@ struct Cor2Ws {
       *pooled2, *ff_H1, *ff_H2, *xf;
   float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled2, *dalpha2, *dz2, *dfuse2, *dv2, *dv2l, *d_f2_H2, *dql, *dg1, *dg2, *dhq1,
       *dhq2, *dalpha_ext, *dpooled1, *dalpha1, *dz1, *dfuse1, *dvl, *d_f1_H2;
+  float* lin_ws; size_t lin_ws_bytes;
   size_t bytes;
 };
 
-static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N) {
+// scratch shared by every linear call of a plan (dZ of the tensor-core backward + padded weight copies)
+static int64_t lin_scratch_floats(int64_t B, int64_t N, int64_t C) {
+  const int64_t M = B * N;
+  const int64_t Cp = ((C + 31) / 32) * 32;
+  // linear bwd: dZ + padded weights; Mutan bwd: stacked padded weights + dH1cat [M, R*512] + dH2cat [B, R*512]
+  const int64_t lin = M * 320 + 4 * B * 2048 + B * Cp + 2 * 2048 * 320 + C * 512;
+  const int64_t mut = 2 * 5 * 512 * 1240 + M * 1024 + B * 5 * 512 + 65536;
+  return (lin > mut ? lin : mut) + 4096;
+}
+
+static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N, int64_t C) {
   Carver c{reinterpret_cast<char*>(base), 0};
   const int64_t M = B * N;
   Cor2Ws w;
-  w.ql = c.take(B * H); w.hq1 = c.take(B * H); w.hq2 = c.take(B * H); w.qf = c.take(B * H);
+  w.ql = c.take(B * HP); w.hq1 = c.take(B * HP); w.hq2 = c.take(B * HP); w.qf = c.take(B * HP);
   w.g1 = c.take(B * D); w.g2 = c.take(B * D);
-  w.vl = c.take(M * H);
+  w.vl = c.take(M * HP);
   w.f1_H1 = c.take(2 * M * F); w.f1_H2 = c.take(2 * B * F); w.fuse1 = c.take(M * F);
   w.pooled1 = c.take(B * G * D);
   w.vf = c.take(B * 2 * A);
-  w.v2l = c.take(M * H);
+  w.v2l = c.take(M * HP);
   w.f2_H1 = c.take(2 * M * F); w.f2_H2 = c.take(2 * B * F); w.fuse2 = c.take(M * F);
   w.pooled2 = c.take(B * G * D);
-  w.ff_H1 = c.take(2 * B * F); w.ff_H2 = c.take(2 * B * F); w.xf = c.take(B * F);
+  w.ff_H1 = c.take(2 * B * F); w.ff_H2 = c.take(2 * B * F); w.xf = c.take(B * XP);
   // backward temporaries
-  w.dxf = c.take(B * F); w.dvf = c.take(B * 2 * A); w.dqf = c.take(B * H); w.d_ff_H2 = c.take(2 * B * F);
+  w.dxf = c.take(B * XP); w.dvf = c.take(B * 2 * A); w.dqf = c.take(B * HP); w.d_ff_H2 = c.take(2 * B * F);
   w.dpooled2 = c.take(B * G * D); w.dalpha2 = c.take(M * G); w.dz2 = c.take(M * G);
-  w.dfuse2 = c.take(M * F); w.dv2 = c.take(M * D); w.dv2l = c.take(M * H); w.d_f2_H2 = c.take(2 * B * F);
-  w.dql = c.take(B * H); w.dg1 = c.take(B * D); w.dg2 = c.take(B * D); w.dhq1 = c.take(B * H); w.dhq2 = c.take(B * H);
+  w.dfuse2 = c.take(M * F); w.dv2 = c.take(M * D); w.dv2l = c.take(M * HP); w.d_f2_H2 = c.take(2 * B * F);
+  w.dql = c.take(B * HP); w.dg1 = c.take(B * D); w.dg2 = c.take(B * D); w.dhq1 = c.take(B * HP); w.dhq2 = c.take(B * HP);
   w.dalpha_ext = c.take(B);
   w.dpooled1 = c.take(B * G * D); w.dalpha1 = c.take(M * G); w.dz1 = c.take(M * G);
-  w.dfuse1 = c.take(M * F); w.dvl = c.take(M * H); w.d_f1_H2 = c.take(2 * B * F);
+  w.dfuse1 = c.take(M * F); w.dvl = c.take(M * HP); w.d_f1_H2 = c.take(2 * B * F);
+  w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
   w.bytes = c.off;
   return w;
 }
@@ -76,19 +90,21 @@ static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N) {
 struct OdaWs {
   float *vl, *ql, *qf, *wsum, *pooled, *vf, *ff_H1, *ff_H2, *xf;
   float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled, *dalpha, *dz, *dwsum, *dvl, *dql;
+  float* lin_ws; size_t lin_ws_bytes;
   size_t bytes;
 };
 
-static OdaWs carve_oda(void* base, int64_t B, int64_t N) {
+static OdaWs carve_oda(void* base, int64_t B, int64_t N, int64_t C) {
   Carver c{reinterpret_cast<char*>(base), 0};
   const int64_t M = B * N;
   OdaWs w;
-  w.vl = c.take(M * H); w.ql = c.take(B * H); w.qf = c.take(B * H); w.wsum = c.take(G * H);
+  w.vl = c.take(M * H); w.ql = c.take(B * H); w.qf = c.take(B * HP); w.wsum = c.take(G * H);
   w.pooled = c.take(B * G * D); w.vf = c.take(B * A);
-  w.ff_H1 = c.take(5 * B * F); w.ff_H2 = c.take(5 * B * F); w.xf = c.take(B * F);
-  w.dxf = c.take(B * F); w.dvf = c.take(B * A); w.dqf = c.take(B * H); w.d_ff_H2 = c.take(5 * B * F);
+  w.ff_H1 = c.take(5 * B * F); w.ff_H2 = c.take(5 * B * F); w.xf = c.take(B * XP);
+  w.dxf = c.take(B * XP); w.dvf = c.take(B * A); w.dqf = c.take(B * HP); w.d_ff_H2 = c.take(5 * B * F);
   w.dpooled = c.take(B * G * D); w.dalpha = c.take(M * G); w.dz = c.take(M * G); w.dwsum = c.take(G * H);
   w.dvl = c.take(M * H); w.dql = c.take(B * H);
+  w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
   w.bytes = c.off;
   return w;
 }
@@ -100,6 +116,7 @@ struct Ctx {
   const float* const* W;      // parameter table
   float* const* dW;           // gradient table (backward) or nullptr
   int accumulate;
+  void* lin_ws; size_t lin_ws_bytes;
   float pdrop() const { return p->train ? P_DROP : 0.0f; }
   float* grad(int idx) const { return dW ? dW[idx] : nullptr; }
 };
@@ -114,6 +131,7 @@ static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
     lp.X[g] = X[g]; lp.ldx[g] = ldx[g]; lp.W[g] = c.W[widx[g]]; lp.b[g] = c.W[widx[g] + 1];
     lp.Y[g] = Y[g]; lp.ldy[g] = ldy[g]; lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
   }
+  lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
   return vqa_linear_fwd(&lp, c.stream);
 }
 
@@ -131,36 +149,41 @@ static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
     lp.dX[g] = dX ? dX[g] : nullptr; lp.lddx[g] = lddx ? lddx[g] : 0;
     lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
   }
+  lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
   return vqa_linear_bwd(&lp, c.stream);
 }
 
 static int mutan_fwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int64_t rows_per, const float* X1,
-                     const float* X2, int l1, int l2, float* H1, float* H2, float* Y) {
+                     int64_t ldx1, const float* X2, int64_t ldx2, int l1, int l2, float* H1, float* H2, float* Y,
+                     int64_t ldy) {
   vqa_mutan_fwd_params mp = {};
   mp.R = R; mp.M = M; mp.K1 = K1; mp.K2 = K2; mp.F = F; mp.rows_per_h2 = rows_per; mp.math = c.p->math;
-  mp.X1 = X1; mp.ldx1 = K1; mp.X2 = X2; mp.ldx2 = K2;
+  mp.X1 = X1; mp.ldx1 = ldx1; mp.X2 = X2; mp.ldx2 = ldx2;
   for (int r = 0; r < R; ++r) {
     mp.W1[r] = c.W[l1 + 2 * r]; mp.b1[r] = c.W[l1 + 2 * r + 1];
     mp.W2[r] = c.W[l2 + 2 * r]; mp.b2[r] = c.W[l2 + 2 * r + 1];
   }
-  mp.H1 = H1; mp.H2 = H2; mp.Y = Y; mp.ldy = F;
+  mp.H1 = H1; mp.H2 = H2; mp.Y = Y; mp.ldy = ldy;
+  mp.workspace = c.lin_ws; mp.workspace_bytes = c.lin_ws_bytes;
   return vqa_mutan_fwd(&mp, c.stream);
 }
 
 static int mutan_bwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int64_t rows_per, const float* X1,
-                     const float* X2, int l1, int l2, const float* H1, const float* H2, const float* dY, float* dH2,
-                     float* dX1, float* dX2, int accumulate_x2) {
+                     int64_t ldx1, const float* X2, int64_t ldx2, int l1, int l2, const float* H1, const float* H2,
+                     const float* dY, int64_t lddy, float* dH2, float* dX1, int64_t lddx1, float* dX2, int64_t lddx2,
+                     int accumulate_x2) {
   vqa_mutan_bwd_params mp = {};
   mp.R = R; mp.M = M; mp.K1 = K1; mp.K2 = K2; mp.F = F; mp.rows_per_h2 = rows_per; mp.math = c.p->math;
   mp.accumulate_w = c.accumulate; mp.accumulate_x1 = 0; mp.accumulate_x2 = accumulate_x2;
-  mp.X1 = X1; mp.ldx1 = K1; mp.X2 = X2; mp.ldx2 = K2;
+  mp.X1 = X1; mp.ldx1 = ldx1; mp.X2 = X2; mp.ldx2 = ldx2;
   for (int r = 0; r < R; ++r) {
     mp.W1[r] = c.W[l1 + 2 * r]; mp.W2[r] = c.W[l2 + 2 * r];
     mp.dW1[r] = c.grad(l1 + 2 * r); mp.db1[r] = c.grad(l1 + 2 * r + 1);
     mp.dW2[r] = c.grad(l2 + 2 * r); mp.db2[r] = c.grad(l2 + 2 * r + 1);
   }
-  mp.H1 = H1; mp.H2 = H2; mp.dY = dY; mp.lddy = F; mp.dH2 = dH2;
-  mp.dX1 = dX1; mp.lddx1 = K1; mp.dX2 = dX2; mp.lddx2 = K2;
+  mp.H1 = H1; mp.H2 = H2; mp.dY = dY; mp.lddy = lddy; mp.dH2 = dH2;
+  mp.dX1 = dX1; mp.lddx1 = lddx1; mp.dX2 = dX2; mp.lddx2 = lddx2;
+  mp.workspace = c.lin_ws; mp.workspace_bytes = c.lin_ws_bytes;
   return vqa_mutan_bwd(&mp, c.stream);
 }
 
@@ -205,33 +228,32 @@ using namespace vqa;
 
 // ====================================================================================== CoR2
 extern "C" size_t vqa_cor2_workspace_bytes(int64_t B, int64_t N, int64_t C) {
-  (void)C;
-  return carve_cor2(nullptr, B, N).bytes;
+  return carve_cor2(nullptr, B, N, C).bytes;
 }
 
 extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
-  VQA_TRY(check_model(p, p ? carve_cor2(nullptr, p->B, p->N).bytes : 0, "vqa_cor2_fwd", true));
+  VQA_TRY(check_model(p, p ? carve_cor2(nullptr, p->B, p->N, p->C).bytes : 0, "vqa_cor2_fwd", true));
   using namespace cor2;
   const int64_t B = p->B, N = p->N, M = B * N;
-  Cor2Ws w = carve_cor2(p->workspace, B, N);
-  Ctx c{p, stream, p->params, nullptr, 0};
+  Cor2Ws w = carve_cor2(p->workspace, B, N, p->C);
+  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes};
   {  // four 2400->310 question projections in one launch (config/CoR2.py:211,195,196,228)
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
     int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
-    int64_t ldy[4] = {H, H, H, H}; uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
+    int64_t ldy[4] = {HP, HP, HP, HP}; uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
     { ProfScope ps_(stream, "q_proj4.fwd"); VQA_TRY(lin_fwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
   {  // gates g1, g2 = sigmoid(310->2048) (config/CoR2.py:195-196)
-    const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {H, H}; int widx[2] = {EQ1, EQ2};
+    const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {HP, HP}; int widx[2] = {EQ1, EQ2};
     float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; uint32_t layer[2] = {L_EQ1, L_EQ2};
     { ProfScope ps_(stream, "gates.fwd"); VQA_TRY(lin_fwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer)); }
   }
   {  // compress_v (config/CoR2.py:213)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
-    int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
+    int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
     { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
-  { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, w.ql, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1)); }   // fusion_vq1 :214
+  { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1, F)); }   // fusion_vq1 :214
   {  // att1 on raw v (:214)
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
@@ -249,10 +271,10 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   }
   {  // compress_v2 (:218)
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; float* Y[1] = {w.v2l};
-    int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V2};
+    int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V2};
     { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
-  { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, w.ql, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2)); }  // fusion_vq2 :219
+  { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2, F)); }  // fusion_vq2 :219
   {  // att2 on v2 (:219)
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
@@ -262,9 +284,9 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     { ProfScope ps_(stream, "att2.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
   }
   { ProfScope ps_(stream, "att2.glimpse.fwd"); VQA_TRY(glimpse_fwd(c, B, w.pooled2, ATT2_G, w.vf, 2 * A, A, L_ATT2_G)); }
-  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 2, B, 2 * A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf)); }    // fusion_final :233
+  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 2, B, 2 * A, H, 1, w.vf, 2 * A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf, XP)); }    // fusion_final :233
   {  // linear_classif (:236)
-    const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
+    const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
     { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer)); }
   }
@@ -274,19 +296,19 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
 extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
   VQA_REQUIRE(bp != nullptr, "vqa_cor2_bwd: null params");
   const vqa_model_fwd_params* p = &bp->fwd;
-  VQA_TRY(check_model(p, carve_cor2(nullptr, p->B, p->N).bytes, "vqa_cor2_bwd", true));
+  VQA_TRY(check_model(p, carve_cor2(nullptr, p->B, p->N, p->C).bytes, "vqa_cor2_bwd", true));
   VQA_REQUIRE(bp->dlogits && bp->grads, "vqa_cor2_bwd: null dlogits / grads");
   using namespace cor2;
   const int64_t B = p->B, N = p->N, M = B * N;
-  Cor2Ws w = carve_cor2(p->workspace, B, N);
-  Ctx c{p, stream, p->params, bp->grads, bp->accumulate};
+  Cor2Ws w = carve_cor2(p->workspace, B, N, p->C);
+  Ctx c{p, stream, p->params, bp->grads, bp->accumulate, w.lin_ws, w.lin_ws_bytes};
   {  // linear_classif
-    const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
+    const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
-    float* dX[1] = {w.dxf}; int64_t lddx[1] = {F}; uint32_t layer[1] = {L_CLASSIF};
+    float* dX[1] = {w.dxf}; int64_t lddx[1] = {XP}; uint32_t layer[1] = {L_CLASSIF};
     { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer)); }
   }
-  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 2, B, 2 * A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, w.d_ff_H2, w.dvf, w.dqf, 0)); }
+  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 2, B, 2 * A, H, 1, w.vf, 2 * A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, XP, w.d_ff_H2, w.dvf, 2 * A, w.dqf, HP, 0)); }
   // ---- att2 branch
   { ProfScope ps_(stream, "att2.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled2, ATT2_G, w.vf, w.dvf, 2 * A, A, w.dpooled2, L_ATT2_G)); }
   {
@@ -299,10 +321,10 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     ap.dWc = c.grad(ATT2_CONV); ap.dbc = c.grad(ATT2_CONV + 1); ap.dfuse = w.dfuse2; ap.dx = w.dv2;
     { ProfScope ps_(stream, "att2.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
-  { ProfScope ps_(stream, "fusion_vq2.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, w.ql, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, w.d_f2_H2, w.dv2l, w.dql, 0)); }
+  { ProfScope ps_(stream, "fusion_vq2.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, F, w.d_f2_H2, w.dv2l, HP, w.dql, HP, 0)); }
   {  // compress_v2: dgrad accumulates into dv2 (v2 feeds both compress_v2 and att2's pooling)
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; const float* Y[1] = {w.v2l};
-    int64_t ldy[1] = {H}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {H};
+    int64_t ldy[1] = {HP}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {HP};
     float* dX[1] = {w.dv2}; int64_t lddx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V2};
     { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 1, layer)); }
   }
@@ -315,9 +337,9 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     { ProfScope ps_(stream, "compound.bwd"); VQA_TRY(vqa_cor_compound_bwd(&cp, stream)); }
   }
   {  // gates
-    const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {H, H}; int widx[2] = {EQ1, EQ2};
+    const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {HP, HP}; int widx[2] = {EQ1, EQ2};
     const float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; const float* dY[2] = {w.dg1, w.dg2};
-    int64_t lddy[2] = {D, D}; float* dX[2] = {w.dhq1, w.dhq2}; int64_t lddx[2] = {H, H};
+    int64_t lddy[2] = {D, D}; float* dX[2] = {w.dhq1, w.dhq2}; int64_t lddx[2] = {HP, HP};
     uint32_t layer[2] = {L_EQ1, L_EQ2};
     { ProfScope ps_(stream, "gates.bwd"); VQA_TRY(lin_bwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer)); }
   }
@@ -331,16 +353,16 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     ap.dWc = c.grad(ATT1_CONV); ap.dbc = c.grad(ATT1_CONV + 1); ap.dfuse = w.dfuse1; ap.dx = nullptr;
     { ProfScope ps_(stream, "att1.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
-  { ProfScope ps_(stream, "fusion_vq1.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, w.ql, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, w.d_f1_H2, w.dvl, w.dql, 1)); }
+  { ProfScope ps_(stream, "fusion_vq1.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, F, w.d_f1_H2, w.dvl, HP, w.dql, HP, 1)); }
   {  // compress_v: v is a graph input, no dgrad
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
-    int64_t ldy[1] = {H}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
+    int64_t ldy[1] = {HP}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
     { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
   {  // the four question projections
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
     int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; const float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
-    int64_t ldy[4] = {H, H, H, H}; const float* dY[4] = {w.dql, w.dhq1, w.dhq2, w.dqf}; int64_t lddy[4] = {H, H, H, H};
+    int64_t ldy[4] = {HP, HP, HP, HP}; const float* dY[4] = {w.dql, w.dhq1, w.dhq2, w.dqf}; int64_t lddy[4] = {HP, HP, HP, HP};
     uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
     { ProfScope ps_(stream, "q_proj4.bwd"); VQA_TRY(lin_bwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
@@ -349,16 +371,15 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
 
 // ====================================================================================== ODA
 extern "C" size_t vqa_oda_workspace_bytes(int64_t B, int64_t N, int64_t C) {
-  (void)C;
-  return carve_oda(nullptr, B, N).bytes;
+  return carve_oda(nullptr, B, N, C).bytes;
 }
 
 extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
-  VQA_TRY(check_model(p, p ? carve_oda(nullptr, p->B, p->N).bytes : 0, "vqa_oda_fwd", false));
+  VQA_TRY(check_model(p, p ? carve_oda(nullptr, p->B, p->N, p->C).bytes : 0, "vqa_oda_fwd", false));
   using namespace oda;
   const int64_t B = p->B, N = p->N, M = B * N;
-  OdaWs w = carve_oda(p->workspace, B, N);
-  Ctx c{p, stream, p->params, nullptr, 0};
+  OdaWs w = carve_oda(p->workspace, B, N, p->C);
+  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes};
   {  // compress_v (config/ODA.py:211)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
@@ -366,7 +387,7 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   }
   {  // compress_q + linear_q (:214, :233)
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
-    float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, H}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
+    float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, HP}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
     { ProfScope ps_(stream, "q_proj2.fwd"); VQA_TRY(lin_fwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
   {  // pairwise differences + conv_att + softmax + pooling (:216-226)
@@ -378,9 +399,9 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
     { ProfScope ps_(stream, "oda_pair_attn.fwd"); VQA_TRY(vqa_oda_pair_attn_fwd(&ap, stream)); }
   }
   { ProfScope ps_(stream, "att.glimpse.fwd"); VQA_TRY(glimpse_fwd(c, B, w.pooled, ATT_G, w.vf, A, 0, L_ATT_G)); }
-  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 5, B, A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf)); }       // fusion_final :236
+  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 5, B, A, H, 1, w.vf, A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf, XP)); }       // fusion_final :236
   {  // linear_classif (:239)
-    const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
+    const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
     { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer)); }
   }
@@ -390,19 +411,19 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
 extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
   VQA_REQUIRE(bp != nullptr, "vqa_oda_bwd: null params");
   const vqa_model_fwd_params* p = &bp->fwd;
-  VQA_TRY(check_model(p, carve_oda(nullptr, p->B, p->N).bytes, "vqa_oda_bwd", false));
+  VQA_TRY(check_model(p, carve_oda(nullptr, p->B, p->N, p->C).bytes, "vqa_oda_bwd", false));
   VQA_REQUIRE(bp->dlogits && bp->grads, "vqa_oda_bwd: null dlogits / grads");
   using namespace oda;
   const int64_t B = p->B, N = p->N, M = B * N;
-  OdaWs w = carve_oda(p->workspace, B, N);
-  Ctx c{p, stream, p->params, bp->grads, bp->accumulate};
+  OdaWs w = carve_oda(p->workspace, B, N, p->C);
+  Ctx c{p, stream, p->params, bp->grads, bp->accumulate, w.lin_ws, w.lin_ws_bytes};
   {
-    const float* X[1] = {w.xf}; int64_t ldx[1] = {F}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
+    const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
-    float* dX[1] = {w.dxf}; int64_t lddx[1] = {F}; uint32_t layer[1] = {L_CLASSIF};
+    float* dX[1] = {w.dxf}; int64_t lddx[1] = {XP}; uint32_t layer[1] = {L_CLASSIF};
     { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer)); }
   }
-  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 5, B, A, H, 1, w.vf, w.qf, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, w.d_ff_H2, w.dvf, w.dqf, 0)); }
+  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 5, B, A, H, 1, w.vf, A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, XP, w.d_ff_H2, w.dvf, A, w.dqf, HP, 0)); }
   { ProfScope ps_(stream, "att.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled, ATT_G, w.vf, w.dvf, A, 0, w.dpooled, L_ATT_G)); }
   {
     vqa_oda_pair_attn_bwd_params ap = {};
@@ -421,8 +442,8 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
   }
   {
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
-    const float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, H}; const float* dY[2] = {w.dql, w.dqf};
-    int64_t lddy[2] = {H, H}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
+    const float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, HP}; const float* dY[2] = {w.dql, w.dqf};
+    int64_t lddy[2] = {H, HP}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
     { ProfScope ps_(stream, "q_proj2.bwd"); VQA_TRY(lin_bwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
   return VQA_OK;

@@ -1,6 +1,7 @@
 // Mutan bilinear fusion forward/backward (include/vqacore.h: vqa_mutan_fwd / vqa_mutan_bwd).
 // Replaces MutanFusion.forward and the per-sample bmul loop (putils/__init__.py:205-241, :98-104).
 #include "gemm_simt.cuh"
+#include "gemm_tc.h"
 
 namespace vqa {
 
@@ -170,6 +171,11 @@ struct DH2_Loader {         // dgrad A(mh, k'=r*F+f) = dH2[r,mh,f]
 
 using namespace vqa;
 
+extern "C" size_t vqa_mutan_workspace_bytes(int math, int R, int64_t M, int64_t rows_per_h2, int64_t K1, int64_t K2,
+                                            int64_t F, int bwd) {
+  return tc_mutan_ws(math, R, M, rows_per_h2 > 0 ? rows_per_h2 : 1, K1, K2, F, bwd);
+}
+
 extern "C" int vqa_mutan_fwd(const vqa_mutan_fwd_params* p, void* stream) {
   VQA_REQUIRE(p != nullptr, "vqa_mutan_fwd: null params");
   VQA_REQUIRE(p->R >= 1 && p->R <= VQA_MAX_GROUPS, "vqa_mutan_fwd: R=%d out of range", p->R);
@@ -180,6 +186,10 @@ extern "C" int vqa_mutan_fwd(const vqa_mutan_fwd_params* p, void* stream) {
   for (int r = 0; r < p->R; ++r) VQA_REQUIRE(p->W1[r] && p->W2[r], "vqa_mutan_fwd: null weight for rank %d", r);
   if (p->M == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->math != VQA_MATH_FP32_SIMT) {
+    int rc = tc_mutan_fwd(p, st);
+    if (rc != VQA_TC_UNSUPPORTED) return rc;
+  }
   const int64_t Mh = p->M / p->rows_per_h2;
   {
     PlainLoader a{p->X2, p->ldx2};
@@ -219,6 +229,10 @@ extern "C" int vqa_mutan_bwd(const vqa_mutan_bwd_params* p, void* stream) {
   for (int r = 0; r < p->R; ++r) VQA_REQUIRE(p->W1[r] && p->W2[r], "vqa_mutan_bwd: null weight for rank %d", r);
   if (p->M == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->math != VQA_MATH_FP32_SIMT) {
+    int rc = tc_mutan_bwd(p, st);
+    if (rc != VQA_TC_UNSUPPORTED) return rc;
+  }
   const int64_t Mh = p->M / p->rows_per_h2;
   const int64_t RF = (int64_t)p->R * p->F;
 

@@ -1,0 +1,361 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:   D[M,N] = A[M,K] . B[N,K]^T   fp32 storage, TF32 tensor-core
+// math with fp32 accumulation in TMEM, optionally error-compensated 3xTF32 (x = hi + lo, three MMAs),
+// which is what the "fp32 parity" mode needs (single TF32 misses the 1e-4 tolerance).
+//
+// One CTA computes a 128 x BN tile.  Warp roles (192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a STAGES-deep smem ring
+//   warp 1      TMEM allocator + the single thread that issues tcgen05.mma and tcgen05.commit
+//   warps 2-5   operand transform in shared memory between TMA landing and MMA issue
+//               (Philox input-dropout on A, hi/lo split for 3xTF32), then the epilogue:
+//               tcgen05.ld the accumulator rows, apply the epilogue functor, store
+// Operands are described by TMA tensor maps and may be K-major (row-major [rows,K]) or MN-major
+// (row-major [K,rows], i.e. the transposed view used by wgrad/dgrad) — no transposed copies are made.
+// Shared-memory/instruction descriptor layouts follow cute/arch/mma_sm100_desc.hpp and
+// cute/atom/mma_traits_sm100.hpp (make_umma_desc).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace vqa {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                    // fp32 elements per k-block = 128 bytes = one swizzle row
+constexpr int A_TILE_BYTES = BM * 128;
+constexpr int ATOM_BYTES = BK * 128;      // one MN-major swizzle atom column: 32 k-rows x 128 B
+constexpr int NUM_THREADS = 192;
+constexpr int XFORM_THREADS = 128;
+constexpr int MAXG = VQA_MAX_GROUPS;
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem] . B[smem], TF32 inputs, fp32 accumulate. One thread issues.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread (thread = lane = row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------ descriptors
+// UMMA shared-memory descriptor, SWIZZLE_128B, sm_100 version bit set.
+//   K-major : rows of 128 B (32 tf32 along K), 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: 32-bit operands must use SWIZZLE_128B_BASE32B (cutlass sm100_common.inl: "for mn-major tf32
+//             operands, SW128_32B is the only available smem layout"): rows of 128 B (32 elements along MN),
+//             32-byte chunks XOR-ed with (row & 3); 4-row k-groups 512 B apart (SBO), next 32 MN elements
+//             ATOM_BYTES apart (LBO).  TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool mn_major) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)(mn_major ? (ATOM_BYTES >> 4) : 1u) << 16;
+  d |= (uint64_t)(mn_major ? (512u >> 4) : (1024u >> 4)) << 32;
+  d |= 1ull << 46;                      // descriptor version (Blackwell)
+  d |= (mn_major ? 1ull : 2ull) << 61;  // SWIZZLE_128B_BASE32B : SWIZZLE_128B
+  return d;
+}
+// kind::tf32 instruction descriptor: fp32 accumulate, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc(int bn, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ params
+struct GroupDrop {
+  uint32_t layer[MAXG];
+  uint64_t base[MAXG];
+};
+
+template <class Epi>
+struct Params {
+  CUtensorMap tmA[MAXG];
+  CUtensorMap tmB[MAXG];
+  int M, N, K;            // D is MxN, reduction length K
+  int k_splits;           // blockIdx.z = group * k_splits + split
+  int a_mn, b_mn;         // operand major-ness
+  int drop_on;            // Philox dropout on the A operand
+  Drop drop;              // seed / thr / scale (layer + base per group below)
+  GroupDrop gd;
+  int64_t drop_ld;        // row length of the logical tensor the mask is indexed in
+  Epi epi;
+};
+
+template <int BN, bool X3>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 256 ? 256 : 512)));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(STAGES >= 2, "tile too large");
+  static_assert(BN % 32 == 0 && BN <= 256, "BN");
+};
+
+// split a 16-byte chunk in place into tf32-representable hi and the fp32 residual lo
+__device__ __forceinline__ void split4(float4& v, float4& lo) {
+  float4 hi;
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+  v = hi;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int BN, bool X3, class Epi>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ Params<Epi> p) {
+  using C = Cfg<BN, X3>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                      // TMA bytes landed
+  uint64_t* ready = bars + C::STAGES;         // transform done (only when p needs a transform)
+  uint64_t* empty = bars + 2 * C::STAGES;     // MMAs that read the stage have completed
+  uint64_t* accum_full = bars + 3 * C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.z / p.k_splits, split = blockIdx.z % p.k_splits;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_per = (kb_total + p.k_splits - 1) / p.k_splits;
+  const int kb_begin = split * kb_per;
+  const int kb_end = min(kb_total, kb_begin + kb_per);
+  const int nkb = max(0, kb_end - kb_begin);
+  const bool need_xform = X3 || p.drop_on;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], XFORM_THREADS);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmA[g]);
+    tma_prefetch_desc(&p.tmB[g]);
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto stage_a = [&](int s) { return smem + s * C::STAGE_BYTES; };
+  auto stage_alo = [&](int s) { return smem + s * C::STAGE_BYTES + A_TILE_BYTES; };
+  auto stage_b = [&](int s) { return smem + s * C::STAGE_BYTES + (X3 ? 2 : 1) * A_TILE_BYTES; };
+  auto stage_blo = [&](int s) { return smem + s * C::STAGE_BYTES + 2 * A_TILE_BYTES + C::B_TILE_BYTES; };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % C::STAGES;
+        const uint32_t ph = (it / C::STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], A_TILE_BYTES + C::B_TILE_BYTES);
+        const int k0 = (kb_begin + it) * BK;
+        if (!p.a_mn) {
+          tma_load_2d(stage_a(s), &p.tmA[g], &full[s], k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(stage_a(s) + j * ATOM_BYTES, &p.tmA[g], &full[s], m0 + j * 32, k0);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(stage_b(s), &p.tmB[g], &full[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(stage_b(s) + j * ATOM_BYTES, &p.tmB[g], &full[s], n0 + j * 32, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN, p.a_mn != 0, p.b_mn != 0);
+      const uint32_t a_step = p.a_mn ? 1024u : 32u;   // bytes per k-step of 8 tf32
+      const uint32_t b_step = p.b_mn ? 1024u : 32u;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % C::STAGES;
+        const uint32_t ph = (it / C::STAGES) & 1;
+        mbar_wait(need_xform ? &ready[s] : &full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(stage_a(s)), b_addr = smem_u32(stage_b(s));
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t da = make_smem_desc(a_addr + k * a_step, p.a_mn != 0);
+          const uint64_t db = make_smem_desc(b_addr + k * b_step, p.b_mn != 0);
+          umma_tf32(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (X3) {
+            const uint64_t dal = make_smem_desc(smem_u32(stage_alo(s)) + k * a_step, p.a_mn != 0);
+            const uint64_t dbl = make_smem_desc(smem_u32(stage_blo(s)) + k * b_step, p.b_mn != 0);
+            umma_tf32(tmem_base, da, dbl, idesc, 1u);
+            umma_tf32(tmem_base, dal, db, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum_full);
+    }
+  } else {
+    // ===================================================== transform warps, then epilogue
+    const int t = threadIdx.x - 64;
+    if (need_xform) {
+      Drop d = p.drop;
+      d.layer = p.gd.layer[g];
+      d.base = p.gd.base[g];
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % C::STAGES;
+        const uint32_t ph = (it / C::STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        const int k0 = (kb_begin + it) * BK;
+        if (X3 || p.drop_on) {
+          uint8_t* a = stage_a(s);
+          uint8_t* alo = stage_alo(s);
+#pragma unroll 4
+          for (int ch = t; ch < A_TILE_BYTES / 16; ch += XFORM_THREADS) {
+            float4 v = *reinterpret_cast<float4*>(a + ch * 16);
+            if (p.drop_on) {
+              const int pc = ch & 7;
+              int64_t row, col;
+              if (!p.a_mn) {
+                const int r = ch >> 3;
+                row = m0 + r;
+                col = k0 + ((pc ^ (r & 7)) << 2);
+              } else {
+                // 128B_ATOM_32B swizzle: 32-byte chunk index XOR (row & 3), 16-byte half unchanged
+                const int j = ch >> 8, r = (ch >> 3) & 31;
+                const int lc = ((((pc >> 1) ^ (r & 3)) << 1) | (pc & 1));
+                row = k0 + r;
+                col = m0 + j * 32 + (lc << 2);
+              }
+              const uint64_t idx = d.base + (uint64_t)(row * p.drop_ld + col);
+              uint32_t w[4];
+              philox_words4(d.seed, d.layer, idx, w);
+              v.x = w[0] >= d.thr ? v.x * d.scale : 0.0f;
+              v.y = w[1] >= d.thr ? v.y * d.scale : 0.0f;
+              v.z = w[2] >= d.thr ? v.z * d.scale : 0.0f;
+              v.w = w[3] >= d.thr ? v.w * d.scale : 0.0f;
+            }
+            if (X3) {
+              float4 lo;
+              split4(v, lo);
+              *reinterpret_cast<float4*>(alo + ch * 16) = lo;
+            }
+            *reinterpret_cast<float4*>(a + ch * 16) = v;
+          }
+        }
+        if (X3) {
+          uint8_t* b = stage_b(s);
+          uint8_t* blo = stage_blo(s);
+#pragma unroll 4
+          for (int ch = t; ch < C::B_TILE_BYTES / 16; ch += XFORM_THREADS) {
+            float4 v = *reinterpret_cast<float4*>(b + ch * 16);
+            float4 lo;
+            split4(v, lo);
+            *reinterpret_cast<float4*>(blo + ch * 16) = lo;
+            *reinterpret_cast<float4*>(b + ch * 16) = v;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&ready[s]);
+      }
+    }
+    // ---- epilogue: TMEM lane quadrant of this warp is (warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait(accum_full, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
+        p.epi(g, (int64_t)m0 + row, p.M, n0 + cb * 32, p.N, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+}  // namespace tc
+}  // namespace vqa

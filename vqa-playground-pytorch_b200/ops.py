@@ -50,6 +50,10 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def _workspace(nbytes, device):
+    return torch.empty((int(nbytes),), device=device, dtype=torch.uint8) if nbytes else None
+
+
 def _math(math):
     return _lib.MATH_BY_NAME[math] if isinstance(math, str) else int(math)
 
@@ -71,6 +75,8 @@ def linear_forward(xs, ws, bs, act, p, seed, layers, math=0, outs=None):
         pr.W[i], pr.b[i] = ws[i].data_ptr(), _p(bs[i])
         pr.Y[i], pr.ldy[i] = outs[i].data_ptr(), outs[i].stride(0)
         pr.layer[i], pr.drop_index_base[i] = int(layers[i]), 0
+    ws = _workspace(_lib.lib().vqa_linear_fwd_workspace_bytes(pr.math, g, M, K, N), xs[0].device)
+    pr.workspace, pr.workspace_bytes = _p(ws), (ws.numel() if ws is not None else 0)
     _lib.check(_lib.lib().vqa_linear_fwd(C.byref(pr), _stream()), "vqa_linear_fwd")
     return outs
 
@@ -98,6 +104,8 @@ def linear_backward(xs, ws, ys, dys, act, p, seed, layers, need_dx, math=0, dws=
         pr.dW[i], pr.db[i] = _p(dws[i]), _p(dbs[i])
         pr.dX[i], pr.lddx[i] = _p(dxs[i]), (dxs[i].stride(0) if dxs[i] is not None else K)
         pr.layer[i], pr.drop_index_base[i] = int(layers[i]), 0
+    ws = _workspace(_lib.lib().vqa_linear_bwd_workspace_bytes(pr.math, g, M, K, N), dev)
+    pr.workspace, pr.workspace_bytes = _p(ws), (ws.numel() if ws is not None else 0)
     _lib.check(_lib.lib().vqa_linear_bwd(C.byref(pr), _stream()), "vqa_linear_bwd")
     return dws, dbs, dxs
 
@@ -158,6 +166,8 @@ class MutanFn(torch.autograd.Function):
         for r in range(R):
             pr.W1[r], pr.b1[r], pr.W2[r], pr.b2[r] = W1[r].data_ptr(), _p(b1[r]), W2[r].data_ptr(), _p(b2[r])
         pr.H1, pr.H2, pr.Y, pr.ldy = H1.data_ptr(), H2.data_ptr(), y.data_ptr(), Fd
+        ws = _workspace(_lib.lib().vqa_mutan_workspace_bytes(pr.math, R, M, M // Mh, K1, K2, Fd, 0), dev)
+        pr.workspace, pr.workspace_bytes = _p(ws), (ws.numel() if ws is not None else 0)
         _lib.check(_lib.lib().vqa_mutan_fwd(C.byref(pr), _stream()), "vqa_mutan_fwd")
         ctx.save_for_backward(a, c, H1, H2, *wb)
         ctx.meta = (math, R, x1.shape, x2.shape)
@@ -186,6 +196,8 @@ class MutanFn(torch.autograd.Function):
             pr.dW2[r], pr.db2[r] = grads[2 * R + 2 * r].data_ptr(), grads[2 * R + 2 * r + 1].data_ptr()
         pr.H1, pr.H2, pr.dY, pr.lddy, pr.dH2 = H1.data_ptr(), H2.data_ptr(), dy2.data_ptr(), Fd, dH2.data_ptr()
         pr.dX1, pr.lddx1, pr.dX2, pr.lddx2 = _p(dx1), K1, _p(dx2), K2
+        ws = _workspace(_lib.lib().vqa_mutan_workspace_bytes(pr.math, R, M, M // Mh, K1, K2, Fd, 1), dev)
+        pr.workspace, pr.workspace_bytes = _p(ws), (ws.numel() if ws is not None else 0)
         _lib.check(_lib.lib().vqa_mutan_bwd(C.byref(pr), _stream()), "vqa_mutan_bwd")
         return (dx1.reshape(x1shape) if dx1 is not None else None,
                 dx2.reshape(x2shape) if dx2 is not None else None, None, None, *grads)

@@ -362,6 +362,11 @@ int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream);
 int vqa_cor2_bwd(const vqa_model_bwd_params* p, void* stream);
 
 size_t vqa_oda_workspace_bytes(int64_t B, int64_t N, int64_t C);
+/* Introspection for tests: where a ReLU output of the forward plan lives inside the workspace.
+ * model: 0 = CoR2, 1 = ODA; name: "compress_v", "compress_v2", "compress_q", "compress_q_1", "compress_q_2",
+ * "linear_q", "glimpses" (the concatenated glimpse-linear outputs). */
+int vqa_stash_info(int model, const char* name, int64_t B, int64_t N, int64_t C, size_t* offset_bytes,
+                   int64_t* rows, int64_t* cols, int64_t* ld);
 int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream);
 int vqa_oda_bwd(const vqa_model_bwd_params* p, void* stream);
 

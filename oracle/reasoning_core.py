@@ -73,30 +73,61 @@ class PhiloxDrop:
 
 
 # ----------------------------------------------------------------------------- blocks
-def my_conv1d(x, w, b, p, af, drop, layer_id, dim=None):
+class ReluTies:
+    """ReLU is not differentiable at 0, so two correct fp32 implementations whose pre-activations differ by a
+    rounding error can disagree on relu'(z) where z ~ 0, and ONE such tie moves a weight-gradient row by
+    ~1/sqrt(rows).  To compare gradients meaningfully the oracle can replay a given activation pattern
+    (`masks[name]`, the pattern the implementation under test produced) and records its own pre-activations
+    (`pre[name]`) so the test can assert that the patterns differ only where |z| is at rounding level."""
+
+    def __init__(self, masks=None):
+        self.masks = masks or {}
+        self.pre = {}
+
+    def relu(self, z, name, cols=None):
+        if cols is None:
+            self.pre[name] = z.detach()
+        else:
+            self.pre.setdefault(name, {})[cols] = z.detach()
+        if name in self.masks:
+            m = self.masks[name]
+            if cols is not None:
+                m = m[:, cols[0]:cols[1]]
+            return z * m.reshape(z.shape).to(z.dtype)
+        return torch.relu(z)
+
+
+_NO_TIES = None
+
+
+def _activate(x, af, ties, name, cols=None, dim=None):
+    if af == "softmax":
+        return F.softmax(x, dim=dim)
+    if af == "relu" and ties is not None and name is not None:
+        return ties.relu(x, name, cols)
+    if af:
+        return getattr(torch, af)(x)
+    return x
+
+
+def my_conv1d(x, w, b, p, af, drop, layer_id, dim=None, ties=None, name=None):
     """config/CoR2.py:72-88 == config/ODA.py:89-105. w is [Cout, Cin, 1]."""
     if x.dim() != 3:
         raise ValueError("input_dim (%s) should equal to 3" % x.dim())
     if p:
         x = drop(x, p, layer_id)
     x = F.conv1d(x.transpose(1, 2), w, b).transpose(1, 2)
-    if af == "softmax":
-        x = F.softmax(x, dim=dim)
-    elif af:
-        x = getattr(torch, af)(x)
-    return x
+    return _activate(x, af, ties, name, dim=dim)
 
 
-def my_linear(x, w, b, p, af, drop, layer_id):
+def my_linear(x, w, b, p, af, drop, layer_id, ties=None, name=None, cols=None):
     """config/CoR2.py:106-119 == config/ODA.py:123-136."""
     if x.size(-1) != w.size(1):
         raise ValueError("last dimension of input(%s) should equal to in_features(%s)" % (x.size(-1), w.size(1)))
     if p:
         x = drop(x, p, layer_id)
     x = F.linear(x, w, b)
-    if af:
-        x = getattr(torch, af)(x)
-    return x
+    return _activate(x, af, ties, name, cols)
 
 
 def mutan_fusion(sd, prefix, x1, x2, R):
@@ -111,7 +142,7 @@ def mutan_fusion(sd, prefix, x1, x2, R):
     return total
 
 
-def my_att(sd, prefix, inputs, fuse, drop, layer_ids):
+def my_att(sd, prefix, inputs, fuse, drop, layer_ids, ties=None, col0=0):
     """config/CoR2.py:137-154 == config/ODA.py:154-171. Returns (x_v [B,620], x_att [B,N,G], tmp [B,G,D])."""
     x_att = my_conv1d(fuse, sd[f"{prefix}.conv_att.conv.weight"], sd[f"{prefix}.conv_att.conv.bias"],
                       0.5, "softmax", drop, layer_ids[f"{prefix}.conv_att"], dim=1)
@@ -119,64 +150,72 @@ def my_att(sd, prefix, inputs, fuse, drop, layer_ids):
     list_v = []
     for g in range(x_att.size(2)):
         name = f"{prefix}.list_linear_v_fusion.{g}"
-        list_v.append(my_linear(tmp[:, g, :], sd[f"{name}.linear.weight"], sd[f"{name}.linear.bias"],
-                                0.5, "relu", drop, layer_ids[name]))
+        w_ = sd[f"{name}.linear.weight"]
+        list_v.append(my_linear(tmp[:, g, :], w_, sd[f"{name}.linear.bias"], 0.5, "relu", drop, layer_ids[name],
+                                ties, "glimpses", (col0 + g * w_.size(0), col0 + (g + 1) * w_.size(0))))
     return torch.cat(list_v, 1), x_att, tmp
 
 
 # ----------------------------------------------------------------------------- models
-def oda_forward(sd, v, q, drop=no_drop, num_regions=36):
+def oda_forward(sd, v, q, drop=no_drop, num_regions=36, ties=None):
     """config/ODA.py:200-240 (q is the 2400-d question embedding, i.e. seq2vec's output).
     Returns (logits, alpha_dict) with alpha_dict as the reference sets it (:228-230)."""
     L = ODA_LAYER_ID
     N = num_regions
     v = v.contiguous().view(-1, N, D_DIM)
     b = v.size(0)
-    vl = my_conv1d(v, sd["compress_v.conv.weight"], sd["compress_v.conv.bias"], 0.5, "relu", drop, L["compress_v"])
-    ql = my_linear(q, sd["compress_q.linear.weight"], sd["compress_q.linear.bias"], 0.5, "relu", drop, L["compress_q"])
+    vl = my_conv1d(v, sd["compress_v.conv.weight"], sd["compress_v.conv.bias"], 0.5, "relu", drop, L["compress_v"],
+                   ties=ties, name="compress_v")
+    ql = my_linear(q, sd["compress_q.linear.weight"], sd["compress_q.linear.bias"], 0.5, "relu", drop, L["compress_q"],
+                   ties, "compress_q")
     # :216-222  vq[b,i,j*H+k] = (vl[b,i,k]-vl[b,j,k]) * ql[b,k]
     vq = ((vl.unsqueeze(2) - vl.unsqueeze(1)) * ql.view(b, 1, 1, -1)).reshape(b, N, N * vl.size(-1))
-    v_final, x_att, _ = my_att(sd, "att", v, vq, drop, L)
+    v_final, x_att, _ = my_att(sd, "att", v, vq, drop, L, ties)
     alpha_dict = {"alphas": x_att[:, :, 0:1]}
-    q_final = my_linear(q, sd["linear_q.linear.weight"], sd["linear_q.linear.bias"], 0.5, "relu", drop, L["linear_q"])
+    q_final = my_linear(q, sd["linear_q.linear.weight"], sd["linear_q.linear.bias"], 0.5, "relu", drop, L["linear_q"],
+                        ties, "linear_q")
     x = mutan_fusion(sd, "fusion_final", v_final, q_final, 5)
     x = my_linear(x, sd["linear_classif.linear.weight"], sd["linear_classif.linear.bias"], 0.5, None, drop,
                   L["linear_classif"])
     return x, alpha_dict
 
 
-def decare_cat(sd, block1, block2, guidance, drop):
+def decare_cat(sd, block1, block2, guidance, drop, ties=None):
     """config/CoR2.py:191-199: [B,m,m,d] = block1[b,i,:]*g1[b,:] + block2[b,j,:]*g2[b,:]."""
     L = COR2_LAYER_ID
     b, m, d = block1.size()
     f1 = block1.view(-1, m, 1, d).expand(b, m, m, d)
     f2 = block2.view(-1, 1, m, d).expand(b, m, m, d)
     g1 = my_linear(my_linear(guidance, sd["compress_q_1.linear.weight"], sd["compress_q_1.linear.bias"], 0.5, "relu",
-                             drop, L["compress_q_1"]),
+                             drop, L["compress_q_1"], ties, "compress_q_1"),
                    sd["expand_q_1.linear.weight"], sd["expand_q_1.linear.bias"], 0.5, "sigmoid", drop, L["expand_q_1"])
     g2 = my_linear(my_linear(guidance, sd["compress_q_2.linear.weight"], sd["compress_q_2.linear.bias"], 0.5, "relu",
-                             drop, L["compress_q_2"]),
+                             drop, L["compress_q_2"], ties, "compress_q_2"),
                    sd["expand_q_2.linear.weight"], sd["expand_q_2.linear.bias"], 0.5, "sigmoid", drop, L["expand_q_2"])
     return f1 * g1.view(b, 1, 1, d) + f2 * g2.view(b, 1, 1, d)
 
 
-def cor2_forward(sd, v, q, drop=no_drop, num_regions=36):
+def cor2_forward(sd, v, q, drop=no_drop, num_regions=36, ties=None):
     """config/CoR2.py:201-237. Returns (logits, alpha_dict)."""
     L = COR2_LAYER_ID
     N = num_regions
     v = v.contiguous().view(-1, N, D_DIM)
     b = v.size(0)
-    ql = my_linear(q, sd["compress_q.linear.weight"], sd["compress_q.linear.bias"], 0.5, "relu", drop, L["compress_q"])
-    vl = my_conv1d(v, sd["compress_v.conv.weight"], sd["compress_v.conv.bias"], 0.5, "relu", drop, L["compress_v"])
-    v1_att, alpha1, _ = my_att(sd, "att1", v, mutan_fusion(sd, "fusion_vq1", vl, ql, 2), drop, L)
-    v2_cat = decare_cat(sd, v, v, q, drop)
+    ql = my_linear(q, sd["compress_q.linear.weight"], sd["compress_q.linear.bias"], 0.5, "relu", drop, L["compress_q"],
+                   ties, "compress_q")
+    vl = my_conv1d(v, sd["compress_v.conv.weight"], sd["compress_v.conv.bias"], 0.5, "relu", drop, L["compress_v"],
+                   ties=ties, name="compress_v")
+    v1_att, alpha1, _ = my_att(sd, "att1", v, mutan_fusion(sd, "fusion_vq1", vl, ql, 2), drop, L, ties, 0)
+    v2_cat = decare_cat(sd, v, v, q, drop, ties)
     v2 = (alpha1[:, :, 0].contiguous().view(b, N, 1, 1) * v2_cat).sum(1)          # :216
-    v2l = my_conv1d(v2, sd["compress_v2.conv.weight"], sd["compress_v2.conv.bias"], 0.5, "relu", drop, L["compress_v2"])
-    v2_att, alpha2, _ = my_att(sd, "att2", v2, mutan_fusion(sd, "fusion_vq2", v2l, ql, 2), drop, L)
+    v2l = my_conv1d(v2, sd["compress_v2.conv.weight"], sd["compress_v2.conv.bias"], 0.5, "relu", drop, L["compress_v2"],
+                    ties=ties, name="compress_v2")
+    v2_att, alpha2, _ = my_att(sd, "att2", v2, mutan_fusion(sd, "fusion_vq2", v2l, ql, 2), drop, L, ties, A_DIM)
     alpha_dict = {"alpha1": torch.split(alpha1, 1, dim=2), "alpha2": torch.split(alpha2, 1, dim=2),
                   "feature": v2[:, [0, 1], :]}
     v_f = torch.cat([v1_att, v2_att], dim=1)
-    q_final = my_linear(q, sd["linear_q.linear.weight"], sd["linear_q.linear.bias"], 0.5, "relu", drop, L["linear_q"])
+    q_final = my_linear(q, sd["linear_q.linear.weight"], sd["linear_q.linear.bias"], 0.5, "relu", drop, L["linear_q"],
+                        ties, "linear_q")
     x = mutan_fusion(sd, "fusion_final", v_f, q_final, 2)
     x = my_linear(x, sd["linear_classif.linear.weight"], sd["linear_classif.linear.bias"], 0.5, None, drop,
                   L["linear_classif"])
@@ -257,12 +296,12 @@ FORWARD = {"ODA": oda_forward, "CoR2": cor2_forward}
 LAYERS = {"ODA": ODA_LAYERS, "CoR2": COR2_LAYERS}
 
 
-def step(model, sd, v, q, a, drop=no_drop, num_regions=36, want_input_grads=False):
+def step(model, sd, v, q, a, drop=no_drop, num_regions=36, want_input_grads=False, ties=None):
     """One fwd+bwd (train.py:63-78 without the optimizer). Returns dict(logits, loss, alpha_dict, grads)."""
     sd = {k: t.detach().clone().requires_grad_(True) for k, t in sd.items()}
     v = v.detach().clone().requires_grad_(want_input_grads)
     q = q.detach().clone().requires_grad_(want_input_grads)
-    logits, alpha = FORWARD[model](sd, v, q, drop, num_regions)
+    logits, alpha = FORWARD[model](sd, v, q, drop, num_regions, ties)
     loss = kld_loss(logits, a)
     loss.backward()
     grads = {k: (t.grad if t.grad is not None else torch.zeros_like(t)) for k, t in sd.items()}

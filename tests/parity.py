@@ -64,12 +64,44 @@ def flatten_alpha(alpha_dict):
 
 
 def oracle_case(model, B, num_ans, N=36, train_seed=None, weight_seed=10, input_seed=1234, want_input_grads=False,
-                gain=1.0):
+                gain=1.0, run=True, ties=None):
     sd = rc.synth_state_dict(model, num_ans, seed=weight_seed, num_regions=N, gain=gain)
     v, q, a = rc.synth_inputs(B, N, num_ans, seed=input_seed)
+    if not run:
+        return sd, (v, q, a), None
     drop = rc.no_drop if train_seed is None else rc.PhiloxDrop(train_seed)
-    ref = rc.step(model, sd, v, q, a, drop=drop, num_regions=N, want_input_grads=want_input_grads)
+    ref = rc.step(model, sd, v, q, a, drop=drop, num_regions=N, want_input_grads=want_input_grads, ties=ties)
     return sd, (v, q, a), ref
+
+
+RELU_STASHES = {"CoR2": ["compress_v", "compress_v2", "compress_q", "compress_q_1", "compress_q_2", "linear_q",
+                         "glimpses"],
+                "ODA": ["compress_v", "compress_q", "linear_q", "glimpses"]}
+
+
+def oracle_with_same_relu_pattern(model, sd, v, q, a, out, N=36, train_seed=None, tie_tol=1e-4):
+    """Oracle fwd+bwd replaying the ReLU activation pattern the CUDA path produced (out['relu_masks']), after
+    checking that the two patterns differ only at pre-activations within `tie_tol` of zero (relative to the
+    layer's max |z|) — i.e. only at genuine rounding-level ties.  See oracle.reasoning_core.ReluTies."""
+    ties = rc.ReluTies(masks=out["relu_masks"])
+    drop = rc.no_drop if train_seed is None else rc.PhiloxDrop(train_seed)
+    ref = rc.step(model, sd, v, q, a, drop=drop, num_regions=N, ties=ties)
+    nflips = 0
+    for name, mask in out["relu_masks"].items():
+        z = ties.pre[name]
+        if isinstance(z, dict):
+            zz = torch.zeros(mask.shape)
+            for (c0, c1), t in z.items():
+                zz[:, c0:c1] = t
+            z = zz
+        z = z.reshape(mask.shape)
+        flipped = (z > 0) != mask
+        if flipped.any():
+            worst = z[flipped].abs().max().item() / max(z.abs().max().item(), 1e-30)
+            assert worst <= tie_tol, "ReLU pattern of %s differs at |z|/max|z| = %.3e (not a rounding tie)" % (name, worst)
+            nflips += int(flipped.sum())
+    ref["relu_ties"] = nflips
+    return ref
 
 
 def run_cuda_model(model, sd, v, q, a, N=36, train_seed=None, precision="fp32", device="cuda:0"):
@@ -91,6 +123,7 @@ def run_cuda_model(model, sd, v, q, a, N=36, train_seed=None, precision="fp32", 
     loss.backward()
     torch.cuda.synchronize()
     grads = {n: p.grad.detach().cpu() for n, p in m.named_parameters()}
-    return {"logits": logits.detach().cpu(), "loss": loss.detach().cpu(), "alpha_dict":
+    masks = {name: (ops.stash_tensor(name) > 0).cpu() for name in RELU_STASHES[model]}
+    return {"relu_masks": masks, "logits": logits.detach().cpu(), "loss": loss.detach().cpu(), "alpha_dict":
             {k: (tuple(t.cpu() for t in val) if isinstance(val, tuple) else val.cpu()) for k, val in m.alpha_dict.items()},
             "grads": grads, "model": m}

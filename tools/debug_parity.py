@@ -20,8 +20,10 @@ def main():
     prec = sys.argv[5] if len(sys.argv) > 5 else "fp32"
     seed = None if seed < 0 else seed
     C = 2000 if model == "CoR2" else 3000
-    sd, (v, q, a), ref = parity.oracle_case(model, B, C, N=N, train_seed=seed)
+    sd, (v, q, a), _ = parity.oracle_case(model, B, C, N=N, run=False)
     out = parity.run_cuda_model(model, sd, v, q, a, N=N, train_seed=seed, precision=prec)
+    ref = parity.oracle_with_same_relu_pattern(model, sd, v, q, a, out, N=N, train_seed=seed, tie_tol=1e-3)
+    print("relu ties replayed:", ref["relu_ties"])
     print("== %s B=%d N=%d seed=%s precision=%s" % (model, B, N, seed, prec))
     print("loss ref %.6f new %.6f" % (ref["loss"].item(), out["loss"].item()))
     print("logits err %.3e" % parity.rel_err(out["logits"], ref["logits"]))

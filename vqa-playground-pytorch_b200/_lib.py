@@ -143,6 +143,8 @@ SYMBOLS = {
     "vqa_cor2_fwd": _OP(ModelFwd), "vqa_cor2_bwd": _OP(ModelBwd),
     "vqa_oda_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "vqa_oda_fwd": _OP(ModelFwd), "vqa_oda_bwd": _OP(ModelBwd),
+    "vqa_stash_info": (C.c_int, [C.c_int, C.c_char_p, i64, i64, i64, C.POINTER(C.c_size_t), C.POINTER(i64),
+                                 C.POINTER(i64), C.POINTER(i64)]),
 }
 
 _lib = None

@@ -88,23 +88,31 @@ pool_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* 
   const float* xr = x + (b * N + i) * D;
   const float* dp = dpooled + b * G * D;
   float* dxr = dx ? dx + (b * N + i) * D : nullptr;
-  for (int64_t c = lane * 4; c < D; c += 128) {
-    const float4 xv = ld_stream4(xr + c);
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int U = 4;
+  for (int64_t c0 = lane * 4; c0 < D; c0 += 128 * U) {
+    float4 xv[U];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const float4 d = __ldg(reinterpret_cast<const float4*>(dp + g * D + c));
-      dot[g] = fmaf(xv.x, d.x, fmaf(xv.y, d.y, fmaf(xv.z, d.z, fmaf(xv.w, d.w, dot[g]))));
-      o.x = fmaf(a[g], d.x, o.x); o.y = fmaf(a[g], d.y, o.y);
-      o.z = fmaf(a[g], d.z, o.z); o.w = fmaf(a[g], d.w, o.w);
-    }
-    if (dxr) {
-      float4* dst = reinterpret_cast<float4*>(dxr + c);
-      if (accumulate_x) {
-        const float4 old = *dst;
-        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+    for (int u = 0; u < U; ++u) xv[u] = (c0 + u * 128 < D) ? ld_stream4(xr + c0 + u * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t c = c0 + u * 128;
+      if (c >= D) break;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dp + g * D + c));
+        dot[g] = fmaf(xv[u].x, d.x, fmaf(xv[u].y, d.y, fmaf(xv[u].z, d.z, fmaf(xv[u].w, d.w, dot[g]))));
+        o.x = fmaf(a[g], d.x, o.x); o.y = fmaf(a[g], d.y, o.y);
+        o.z = fmaf(a[g], d.z, o.z); o.w = fmaf(a[g], d.w, o.w);
       }
-      *dst = o;
+      if (dxr) {
+        float4* dst = reinterpret_cast<float4*>(dxr + c);
+        if (accumulate_x) {
+          const float4 old = *dst;
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *dst = o;
+      }
     }
   }
 #pragma unroll

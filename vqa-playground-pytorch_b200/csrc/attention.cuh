@@ -15,12 +15,21 @@ struct FuseGeneric {
     return d.mul((uint64_t)((b * N + i) * Ff + c));
   }
   __device__ __forceinline__ float raw(int64_t b, int64_t i, int64_t c) const { return fuse[(b * N + i) * Ff + c]; }
+  // multipliers of 4 consecutive elements c..c+3 of row (b,i)
+  __device__ __forceinline__ void mul4(int64_t b, int64_t i, int64_t c, float (&m)[4]) const {
+    if (!d.on) { m[0] = m[1] = m[2] = m[3] = 1.0f; return; }
+    uint32_t w[4];
+    philox_words4(d.seed, d.layer, d.base + (uint64_t)((b * N + i) * Ff + c), w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m[e] = w[e] >= d.thr ? d.scale : 0.0f;
+  }
 };
 // ODA, eval mode: fuse_eff[b,i,k] = vl[b,i,k]*ql[b,k] against Wsum[g,k] = sum_j W[g,j*H+k]
 // (the -vl[b,j,k] part is constant over i and cancels in the region softmax).
 struct FuseOdaEval {
   const float* vl; const float* ql; int64_t N, Ff;   // Ff == H
   __device__ __forceinline__ float mul(int64_t, int64_t, int64_t) const { return 1.0f; }
+  __device__ __forceinline__ void mul4(int64_t, int64_t, int64_t, float (&m)[4]) const { m[0] = m[1] = m[2] = m[3] = 1.0f; }
   __device__ __forceinline__ float raw(int64_t b, int64_t i, int64_t c) const {
     return vl[(b * N + i) * Ff + c] * ql[b * Ff + c];
   }
@@ -46,7 +55,9 @@ __device__ __forceinline__ void softmax_regions_smem(float* z, int N) {
 }
 
 // z[b,i,g] = sum_c Wc[g,c]*fuse~[b,i,c] + bc[g]; alpha = softmax_i z.   grid = B.
-// dynamic smem: G*Ff (weights) + N*G (logits)
+// dynamic smem: G*Ff (weights) + N*G (logits).  One warp per region row; a lane owns quads of 4 consecutive
+// elements (one Philox call per quad when the row start is 4-aligned, two otherwise) and issues all of its
+// loads for the row before using them.
 template <class FS>
 __global__ void __launch_bounds__(ATT_THREADS)
 att_logits_softmax_kernel(FS fs, int64_t N, int64_t Ff, const float* __restrict__ Wc, const float* __restrict__ bc,
@@ -58,14 +69,35 @@ att_logits_softmax_kernel(FS fs, int64_t N, int64_t Ff, const float* __restrict_
   for (int64_t t = threadIdx.x; t < G * Ff; t += ATT_THREADS) w_s[t] = Wc[t];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int QPL = 4;                       // quads per lane per pass: 32 lanes * 4 quads * 4 = 512 elements
   for (int64_t i = warp; i < N; i += ATT_THREADS / 32) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int64_t c = lane; c < Ff; c += 32) {
-      const float f = fs.raw(b, i, c) * fs.mul(b, i, c);
-      a0 = fmaf(w_s[c], f, a0);
-      a1 = fmaf(w_s[Ff + c], f, a1);
-      a2 = fmaf(w_s[2 * Ff + c], f, a2);
-      a3 = fmaf(w_s[3 * Ff + c], f, a3);
+    for (int64_t c0 = 0; c0 < Ff; c0 += 32 * QPL * 4) {
+      float f[QPL][4];
+#pragma unroll
+      for (int j = 0; j < QPL; ++j) {
+        const int64_t c = c0 + (int64_t)(lane + 32 * j) * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) f[j][e] = (c + e < Ff) ? fs.raw(b, i, c + e) : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < QPL; ++j) {
+        const int64_t c = c0 + (int64_t)(lane + 32 * j) * 4;
+        if (c < Ff) {
+          float mul[4];
+          fs.mul4(b, i, c, mul);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (c + e < Ff) {
+              const float v = f[j][e] * mul[e];
+              a0 = fmaf(w_s[c + e], v, a0);
+              a1 = fmaf(w_s[Ff + c + e], v, a1);
+              a2 = fmaf(w_s[2 * Ff + c + e], v, a2);
+              a3 = fmaf(w_s[3 * Ff + c + e], v, a3);
+            }
+          }
+        }
+      }
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
     if (lane == 0) {
@@ -140,22 +172,33 @@ att_logits_softmax_bwd_kernel(FS fs, int64_t B, int64_t N, int64_t Ff, const flo
     }
     if (active) {
       float dq = 0.0f;
-      for (int64_t i = 0; i < N; ++i) {
-        const float4 z4 = *reinterpret_cast<const float4*>(&dz_s[i * G]);
-        const float mul = fs.mul(b, i, c);
-        const float f = fs.raw(b, i, c) * mul;
-        accw[0] = fmaf(z4.x, f, accw[0]);
-        accw[1] = fmaf(z4.y, f, accw[1]);
-        accw[2] = fmaf(z4.z, f, accw[2]);
-        accw[3] = fmaf(z4.w, f, accw[3]);
-        const float df = (z4.x * w[0] + z4.y * w[1] + z4.z * w[2] + z4.w * w[3]) * mul;
-        if constexpr (ODA_EVAL) {
-          // fuse_eff = vl*ql: dvl = df*ql, dql += df*vl
-          const float qv = fs.ql[b * Ff + c], vv = fs.vl[(b * N + i) * Ff + c];
-          dfuse[(b * N + i) * Ff + c] = df * qv;
-          dq = fmaf(df, vv, dq);
-        } else {
-          if (dfuse) dfuse[(b * N + i) * Ff + c] = df;
+      constexpr int U = 6;
+      for (int64_t i0 = 0; i0 < N; i0 += U) {
+        float fr[U], mu[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) fr[u] = (i0 + u < N) ? fs.raw(b, i0 + u, c) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) mu[u] = (i0 + u < N) ? fs.mul(b, i0 + u, c) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = i0 + u;
+          if (i < N) {
+            const float4 z4 = *reinterpret_cast<const float4*>(&dz_s[i * G]);
+            const float f = fr[u] * mu[u];
+            accw[0] = fmaf(z4.x, f, accw[0]);
+            accw[1] = fmaf(z4.y, f, accw[1]);
+            accw[2] = fmaf(z4.z, f, accw[2]);
+            accw[3] = fmaf(z4.w, f, accw[3]);
+            const float df = (z4.x * w[0] + z4.y * w[1] + z4.z * w[2] + z4.w * w[3]) * mu[u];
+            if constexpr (ODA_EVAL) {
+              // fuse_eff = vl*ql: dvl = df*ql, dql += df*vl
+              const float qv = fs.ql[b * Ff + c], vv = fs.vl[(b * N + i) * Ff + c];
+              dfuse[(b * N + i) * Ff + c] = df * qv;
+              dq = fmaf(df, vv, dq);
+            } else {
+              if (dfuse) dfuse[(b * N + i) * Ff + c] = df;
+            }
+          }
         }
       }
       if constexpr (ODA_EVAL) dql[b * Ff + c] = dq;

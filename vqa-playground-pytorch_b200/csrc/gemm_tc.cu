@@ -3,6 +3,8 @@
 // math = VQA_MATH_TF32X3 or VQA_MATH_TF32).  Kernel: tc_gemm.cuh.
 #include "gemm_tc.h"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "tc_gemm.cuh"
@@ -66,43 +68,82 @@ static int operand_tmap(CUtensorMap* out, const float* ptr, bool mn_major, int64
 // ------------------------------------------------------------------------------------------ epilogues
 // Each receives 32 consecutive accumulator columns [n0, n0+32) of row m.
 
-// y = act(acc + bias), row-major store; columns in [N, Nstore) are written as zeros (padding that later
-// GEMMs read through TMA).
+// 4 consecutive row elements with whatever vector width the destination alignment allows; nv = valid count
+__device__ __forceinline__ void store4(float* dst, const float (&o)[4], int nv) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+  if (nv == 4 && (a & 15) == 0) {
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  } else if (nv == 4 && (a & 7) == 0) {
+    *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+    *reinterpret_cast<float2*>(dst + 2) = make_float2(o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (e < nv) dst[e] = o[e];
+  }
+}
+__device__ __forceinline__ void load4(const float* src, float (&o)[4], int nv) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+  if (nv == 4 && (a & 15) == 0) {
+    const float4 t = *reinterpret_cast<const float4*>(src);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = e < nv ? src[e] : 0.0f;
+  }
+}
+
+// y = act(acc + bias), row-major store.  With k-splits (atomic != 0) the partial sums are accumulated into a
+// zeroed Y with red.global.add, split 0 contributes the bias, and the activation is applied afterwards by
+// act_inplace_kernel.
 struct EpiBiasAct {
+  static constexpr bool kStaged = true;
   float* Y[MAXG];
   const float* bias[MAXG];
   int64_t ld[MAXG];
   int act;
-  int Nstore;
-  __device__ __forceinline__ void operator()(int g, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
-    if (m >= M) return;
-    float* y = Y[g] + m * ld[g];
+  int atomic;
+  __device__ __forceinline__ void row4(int g, int split, int64_t m, int n, int N, const float4 v) const {
+    float* y = Y[g] + m * ld[g] + n;
     const float* b = bias[g];
-    const bool vec = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const int nv = N - n < 4 ? N - n : 4;
+    float o[4] = {v.x, v.y, v.z, v.w};
+    if (b && (!atomic || split == 0)) {
 #pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      const int n = n0 + c;
-      if (n >= Nstore) break;
-      float o[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = (n + e < N) ? act_apply(act, v[c + e] + (b ? __ldg(b + n + e) : 0.0f)) : 0.0f;
-      if (vec && n + 3 < Nstore) {
-        *reinterpret_cast<float4*>(y + n) = make_float4(o[0], o[1], o[2], o[3]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (n + e < Nstore) y[n + e] = o[e];
-      }
+      for (int e = 0; e < 4; ++e)
+        if (e < nv) o[e] += __ldg(b + n + e);
     }
+    if (atomic) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (e < nv) atomicAdd(y + e, o[e]);
+      return;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = act_apply(act, o[e]);
+    store4(y, o, nv);
   }
 };
+
+// y = act(y) in place over a [M, N] window of row stride ld; grid.z = group
+struct ActArgs { float* Y[MAXG]; int64_t ld[MAXG]; };
+__global__ void act_inplace_kernel(ActArgs a, int64_t M, int64_t N, int act) {
+  float* y = a.Y[blockIdx.z];
+  const int64_t ld = a.ld[blockIdx.z];
+  const int64_t total = M * N;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / N, n = t - m * N;
+    y[m * ld + n] = act_apply(act, y[m * ld + n]);
+  }
+}
 
 // wgrad: D'(m' = input feature k, n' = output feature n) accumulated into dW[n, k] (row stride ldw) with
 // red.global.add (split-K partials and the "+=" of a flat gradient buffer are the same operation).
 struct EpiWgradT {
+  static constexpr bool kStaged = false;
   float* dW[MAXG];
   int64_t ldw;
-  __device__ __forceinline__ void operator()(int g, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
+  __device__ __forceinline__ void operator()(int g, int, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
     if (m >= M) return;
     float* w = dW[g];
     if (!w) return;
@@ -116,44 +157,40 @@ struct EpiWgradT {
 
 // dgrad: dX[m, n] (=|+=) acc * mask(m*drop_ld + n) / (1-p)
 struct EpiDgrad {
+  static constexpr bool kStaged = true;
   float* dX[MAXG];
   int64_t ld[MAXG];
   int accumulate;
+  int atomic;       // k-splits: every partial is masked and added with red.global.add (dX zeroed or "+=")
   int drop_on;
   Drop drop;
   GroupDrop gd;
   int64_t drop_ld;
-  __device__ __forceinline__ void operator()(int g, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
-    if (m >= M) return;
+  __device__ __forceinline__ void row4(int g, int, int64_t m, int n, int N, const float4 v) const {
     float* x = dX[g];
     if (!x) return;
-    x += m * ld[g];
-    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    x += m * ld[g] + n;
+    const int nv = N - n < 4 ? N - n : 4;
+    float o[4] = {v.x, v.y, v.z, v.w};
+    if (drop_on) {
+      uint32_t wd[4];
+      philox_words4(drop.seed, gd.layer[g], gd.base[g] + (uint64_t)(m * drop_ld + n), wd);
 #pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      const int n = n0 + c;
-      if (n >= N) break;
-      float o[4] = {v[c], v[c + 1], v[c + 2], v[c + 3]};
-      if (drop_on) {
-        const uint64_t idx = gd.base[g] + (uint64_t)(m * drop_ld + n);
-        uint32_t wd[4];
-        philox_words4(drop.seed, gd.layer[g], idx, wd);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = wd[e] >= drop.thr ? o[e] * drop.scale : 0.0f;
-      }
-      if (vec && n + 3 < N) {
-        float4* dst = reinterpret_cast<float4*>(x + n);
-        if (accumulate) {
-          const float4 old = *dst;
-          o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
-        }
-        *dst = make_float4(o[0], o[1], o[2], o[3]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (n + e < N) x[n + e] = accumulate ? x[n + e] + o[e] : o[e];
-      }
+      for (int e = 0; e < 4; ++e) o[e] = wd[e] >= drop.thr ? o[e] * drop.scale : 0.0f;
     }
+    if (atomic) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (e < nv) atomicAdd(x + e, o[e]);
+      return;
+    }
+    if (accumulate) {
+      float old[4];
+      load4(x, old, nv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] += old[e];
+    }
+    store4(x, o, nv);
   }
 };
 
@@ -174,8 +211,32 @@ static inline int pick_bn(int64_t N) {
   return w160 < w128 ? 160 : 128;
 }
 
+static void zero_window(float* y, int64_t ld, int64_t M, int64_t N, cudaStream_t st) {
+  if (ld == N) cudaMemsetAsync(y, 0, (size_t)M * N * sizeof(float), st);
+  else cudaMemset2DAsync(y, (size_t)ld * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st);
+}
+
+static int rewrite_hi_flag() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VQA_TC_REWRITE_HI");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+// k-splits for problems whose output tiles alone cannot fill the chip
+static int pick_splits(int64_t tiles, int64_t K) {
+  const int64_t kb = cdiv(K, BK);
+  if (tiles * 2 > (int64_t)sm_count()) return 1;
+  int64_t s = cdiv((int64_t)sm_count(), tiles);
+  if (s > kb / 4) s = kb / 4;
+  return (int)(s < 1 ? 1 : s);
+}
+
 template <class Epi>
-static int launch(const Params<Epi>& p, int groups, bool x3, cudaStream_t st, const char* what) {
+static int launch(Params<Epi> p, int groups, bool x3, cudaStream_t st, const char* what) {
+  p.rewrite_hi = rewrite_hi_flag();
   const int bn = pick_bn(p.N);
   if (bn == 160) return x3 ? launch_cfg<160, true>(p, groups, st, what) : launch_cfg<160, false>(p, groups, st, what);
   return x3 ? launch_cfg<128, true>(p, groups, st, what) : launch_cfg<128, false>(p, groups, st, what);
@@ -259,25 +320,46 @@ static int pack_weights(const float* const* W, int groups, int64_t rows, int64_t
 }
 
 // ------------------------------------------------------------------------------------------ Mutan pieces
-// forward epilogue for rank r: h1 = acc + b1_r;  H1_r[m,n] = h1;  Y[m,n] (r ? += : =) h1 * H2_r[m / rows_per, n]
+// forward epilogue for rank r = group: h1 = acc + b1_r;  H1_r[m,n] = h1;  Y[m,n] += h1 * H2_r[m / rows_per, n].
+// Non-atomic mode runs rank by rank in stream order (r == 0 stores, r > 0 read-modify-writes Y);
+// atomic mode (k-splits, small M) accumulates every partial into zeroed Y / H1 with red.global.add.
 struct EpiMutan {
-  const float* bias; const float* H2; float* H1; float* Y;
-  int64_t ldh, ldy, rows_per; int accumulate;
-  __device__ __forceinline__ void operator()(int, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
-    if (m >= M) return;
-    const float* h2 = H2 + (m / rows_per) * ldh;
-    float* h1 = H1 ? H1 + m * ldh : nullptr;
-    float* y = Y + m * ldy;
+  static constexpr bool kStaged = true;
+  const float* bias[MAXG]; const float* H2[MAXG]; float* H1[MAXG]; float* Y;
+  int64_t ldh, ldy, rows_per; int accumulate; int atomic;
+  __device__ __forceinline__ void row4(int g, int split, int64_t m, int n, int N, const float4 v) const {
+    const int nv = N - n < 4 ? N - n : 4;
+    const float* h2 = H2[g] + (m / rows_per) * ldh + n;
+    const float* b = bias[g];
+    float* y = Y + m * ldy + n;
+    float h[4] = {v.x, v.y, v.z, v.w}, o[4];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int n = n0 + c;
-      if (n < N) {
-        const float h = v[c] + (bias ? __ldg(bias + n) : 0.0f);
-        if (h1) h1[n] = h;
-        const float o = h * __ldg(h2 + n);
-        y[n] = accumulate ? y[n] + o : o;
+    for (int e = 0; e < 4; ++e) {
+      if (e < nv) {
+        if (b && split == 0) h[e] += __ldg(b + n + e);
+        o[e] = h[e] * __ldg(h2 + e);
+      } else {
+        o[e] = 0.0f;
       }
     }
+    float* h1 = H1[g] ? H1[g] + m * ldh + n : nullptr;
+    if (atomic) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (e < nv) {
+          if (h1) atomicAdd(h1 + e, h[e]);
+          atomicAdd(y + e, o[e]);
+        }
+      return;
+    }
+    if (h1) store4(h1, h, nv);
+    if (accumulate) {
+      float old[4];
+      load4(y, old, nv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] += old[e];
+    }
+    store4(y, o, nv);
   }
 };
 
@@ -295,11 +377,25 @@ mutan_dh1_kernel(int64_t M, int64_t F, int64_t Fp, int64_t rows_per, int R, cons
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
   float s = 0.0f;
-  for (int64_t m = r0 + ty; m < r1; m += 8) {
-    float v = 0.0f;
-    if (f < F) v = dY[m * lddy + f] * H2[((int64_t)r * Mh + m / rows_per) * F + f];
-    if (f < Fp) dH1cat[m * (R * Fp) + r * Fp + f] = v;
-    s += v;
+  constexpr int U = 4;
+  for (int64_t mb = r0 + ty; mb < r1; mb += 8 * U) {
+    float dy[U], h2[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t m = mb + 8 * u;
+      const bool ok = m < r1 && f < F;
+      dy[u] = ok ? dY[m * lddy + f] : 0.0f;
+      h2[u] = ok ? H2[((int64_t)r * Mh + m / rows_per) * F + f] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t m = mb + 8 * u;
+      if (m < r1) {
+        const float v = dy[u] * h2[u];
+        if (f < Fp) dH1cat[m * (R * Fp) + r * Fp + f] = v;
+        s += v;
+      }
+    }
   }
   red[ty][tx] = s;
   __syncthreads();
@@ -321,9 +417,18 @@ __global__ void mutan_dh2cat_kernel(int64_t M, int64_t F, int64_t Fp, int64_t ro
   for (int64_t f = threadIdx.x; f < Fp; f += blockDim.x) {
     float s = 0.0f;
     if (f < F) {
-      for (int64_t j = 0; j < rows_per; ++j) {
-        const int64_t m = mh * rows_per + j;
-        s = fmaf(dY[m * lddy + f], H1[((int64_t)r * M + m) * F + f], s);
+      constexpr int U = 6;
+      for (int64_t j0 = 0; j0 < rows_per; j0 += U) {
+        float dy[U], h1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t m = mh * rows_per + j0 + u;
+          const bool ok = j0 + u < rows_per;
+          dy[u] = ok ? dY[m * lddy + f] : 0.0f;
+          h1[u] = ok ? H1[((int64_t)r * M + m) * F + f] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) s = fmaf(dy[u], h1[u], s);
       }
       if (db.p[r]) atomicAdd(db.p[r] + f, s);
     }
@@ -360,13 +465,25 @@ int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
     else VQA_TRY(operand_tmap(&q.tmB[g], p->W[s], false, p->N, p->K, p->K, bn));
     q.epi.Y[g] = p->Y[s]; q.epi.bias[g] = p->b[s]; q.epi.ld[g] = p->ldy[s];
   }
-  q.M = (int)p->M; q.N = (int)p->N; q.K = (int)p->K; q.k_splits = 1; q.a_mn = 0; q.b_mn = 0;
+  q.M = (int)p->M; q.N = (int)p->N; q.K = (int)p->K; q.a_mn = 0; q.b_mn = 0;
+  q.k_splits = pick_splits(cdiv(p->M, BM) * cdiv(p->N, bn) * p->groups, p->K);
   q.drop_on = p->p > 0.0f;
   fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
   q.drop_ld = p->K;
   q.epi.act = p->act;
-  q.epi.Nstore = (int)p->N;
-  return launch(q, p->groups, p->math == VQA_MATH_TF32X3, st, "tc_linear_fwd");
+  q.epi.atomic = q.k_splits > 1;
+  if (q.epi.atomic)
+    for (int g = 0; g < p->groups; ++g) zero_window(p->Y[g], p->ldy[g], p->M, p->N, st);
+  VQA_TRY(launch(q, p->groups, p->math == VQA_MATH_TF32X3, st, "tc_linear_fwd"));
+  if (q.epi.atomic && p->act != VQA_ACT_NONE) {
+    ActArgs a = {};
+    for (int g = 0; g < MAXG; ++g) { const int s = g < p->groups ? g : 0; a.Y[g] = p->Y[s]; a.ld[g] = p->ldy[s]; }
+    int64_t blocks = cdiv(p->M * p->N, 256);
+    if (blocks > 1024) blocks = 1024;
+    act_inplace_kernel<<<dim3((unsigned)blocks, 1, (unsigned)p->groups), 256, 0, st>>>(a, p->M, p->N, p->act);
+    VQA_TRY(check_launch("tc_linear_fwd.act"));
+  }
+  return VQA_OK;
 }
 
 // ============================================================================================ linear bwd
@@ -448,10 +565,15 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
       else VQA_TRY(operand_tmap(&q.tmB[g], p->W[s], true, p->K, p->N, p->K, bn));
       q.epi.dX[g] = p->dX[s]; q.epi.ld[g] = p->lddx[s];
     }
-    q.M = (int)p->M; q.N = (int)p->K; q.K = (int)p->N; q.k_splits = 1; q.a_mn = 0; q.b_mn = 1;
+    q.M = (int)p->M; q.N = (int)p->K; q.K = (int)p->N; q.a_mn = 0; q.b_mn = 1;
+    q.k_splits = pick_splits(cdiv(p->M, BM) * cdiv(p->K, bn) * p->groups, p->N);
     q.drop_on = 0;
     fill_drop(q.drop, q.gd, 0.0f, p->seed, p->layer, p->drop_index_base, p->groups);
     q.epi.accumulate = p->accumulate_x;
+    q.epi.atomic = q.k_splits > 1;
+    if (q.epi.atomic && !p->accumulate_x)
+      for (int g = 0; g < p->groups; ++g)
+        if (p->dX[g]) zero_window(p->dX[g], p->lddx[g], p->M, p->K, st);
     q.epi.drop_on = p->p > 0.0f;
     fill_drop(q.epi.drop, q.epi.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
     q.epi.drop_ld = p->K;
@@ -506,21 +628,40 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
       VQA_TRY(operand_tmap(&q.tmB[g], w.w2pk + (size_t)s * Fp * K2p, false, p->F, p->K2, K2p, bn));
       q.epi.Y[g] = p->H2 + (size_t)s * Mh * p->F; q.epi.bias[g] = p->b2[s]; q.epi.ld[g] = p->F;
     }
-    q.M = (int)Mh; q.N = (int)p->F; q.K = (int)p->K2; q.k_splits = 1;
-    q.epi.act = VQA_ACT_NONE; q.epi.Nstore = (int)p->F;
+    q.M = (int)Mh; q.N = (int)p->F; q.K = (int)p->K2;
+    q.k_splits = pick_splits(cdiv(Mh, BM) * cdiv(p->F, bn) * p->R, p->K2);
+    q.epi.act = VQA_ACT_NONE; q.epi.atomic = q.k_splits > 1;
+    if (q.epi.atomic) cudaMemsetAsync(p->H2, 0, (size_t)p->R * Mh * p->F * sizeof(float), st);
     VQA_TRY(launch(q, p->R, x3, st, "tc_mutan_fwd.h2"));
   }
-  for (int r = 0; r < p->R; ++r) {   // rank by rank: Y is read-modify-written in stream order
-    Params<EpiMutan> q = {};
+  const int splits = pick_splits(cdiv(p->M, BM) * cdiv(p->F, bn) * p->R, p->K1);
+  auto fill = [&](Params<EpiMutan>& q, int r0) -> int {
     for (int g = 0; g < MAXG; ++g) {
+      const int r = (r0 + g) < p->R ? (r0 + g) : r0;
       VQA_TRY(operand_tmap(&q.tmA[g], p->X1, false, p->M, p->K1, p->ldx1, BM));
       VQA_TRY(operand_tmap(&q.tmB[g], w.w1pk + (size_t)r * Fp * K1p, false, p->F, p->K1, K1p, bn));
+      q.epi.bias[g] = p->b1[r]; q.epi.H2[g] = p->H2 + (size_t)r * Mh * p->F;
+      q.epi.H1[g] = p->H1 ? p->H1 + (size_t)r * p->M * p->F : nullptr;
     }
-    q.M = (int)p->M; q.N = (int)p->F; q.K = (int)p->K1; q.k_splits = 1;
-    q.epi.bias = p->b1[r]; q.epi.H2 = p->H2 + (size_t)r * Mh * p->F;
-    q.epi.H1 = p->H1 ? p->H1 + (size_t)r * p->M * p->F : nullptr;
-    q.epi.Y = p->Y; q.epi.ldh = p->F; q.epi.ldy = p->ldy; q.epi.rows_per = p->rows_per_h2; q.epi.accumulate = r > 0;
-    VQA_TRY(launch(q, 1, x3, st, "tc_mutan_fwd.h1"));
+    q.M = (int)p->M; q.N = (int)p->F; q.K = (int)p->K1;
+    q.epi.Y = p->Y; q.epi.ldh = p->F; q.epi.ldy = p->ldy; q.epi.rows_per = p->rows_per_h2;
+    return VQA_OK;
+  };
+  if (splits > 1) {
+    // small M: all ranks and k-splits in one launch, partials accumulated atomically into zeroed Y / H1
+    Params<EpiMutan> q = {};
+    VQA_TRY(fill(q, 0));
+    q.k_splits = splits; q.epi.atomic = 1; q.epi.accumulate = 1;
+    zero_window(p->Y, p->ldy, p->M, p->F, st);
+    if (p->H1) cudaMemsetAsync(p->H1, 0, (size_t)p->R * p->M * p->F * sizeof(float), st);
+    VQA_TRY(launch(q, p->R, x3, st, "tc_mutan_fwd.h1"));
+  } else {
+    for (int r = 0; r < p->R; ++r) {   // rank by rank: Y is read-modify-written in stream order
+      Params<EpiMutan> q = {};
+      VQA_TRY(fill(q, r));
+      q.k_splits = 1; q.epi.atomic = 0; q.epi.accumulate = r > 0;
+      VQA_TRY(launch(q, 1, x3, st, "tc_mutan_fwd.h1"));
+    }
   }
   return VQA_OK;
 }
@@ -588,8 +729,10 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
       VQA_TRY(operand_tmap(&q.tmB[g], Wpk, true, Kin, RF, Kinp, bn));
       q.epi.dX[g] = dX; q.epi.ld[g] = lddx;
     }
-    q.M = (int)rows; q.N = (int)Kin; q.K = (int)RF; q.k_splits = 1; q.a_mn = 0; q.b_mn = 1;
-    q.epi.accumulate = accumulate; q.epi.drop_on = 0;
+    q.M = (int)rows; q.N = (int)Kin; q.K = (int)RF; q.a_mn = 0; q.b_mn = 1;
+    q.k_splits = pick_splits(cdiv(rows, BM) * cdiv(Kin, bn), RF);
+    q.epi.accumulate = accumulate; q.epi.drop_on = 0; q.epi.atomic = q.k_splits > 1;
+    if (q.epi.atomic && !accumulate) zero_window(dX, lddx, rows, Kin, st);
     return launch(q, 1, x3, st, what);
   };
   VQA_TRY(wgrad(p->X1, p->ldx1, p->M, p->K1, w.dh1, p->dW1, "tc_mutan_bwd.dw1"));

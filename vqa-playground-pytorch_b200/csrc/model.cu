@@ -2,6 +2,8 @@
 // (include/vqacore.h: vqa_cor2_{fwd,bwd}, vqa_oda_{fwd,bwd}).
 // Reference: config/CoR2.py:201-237 (+ decare_cat :191-199), config/ODA.py:200-240.
 // Parameter tables follow the reference's state_dict order (seq2vec.* excluded).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace vqa {
@@ -225,6 +227,39 @@ static int check_model(const vqa_model_fwd_params* p, size_t need, const char* w
 }  // namespace vqa
 
 using namespace vqa;
+
+// ====================================================================================== introspection
+// Location of a forward stash tensor inside the caller's workspace (used by the parity tests to read the
+// ReLU activation patterns the kernels actually produced).
+extern "C" int vqa_stash_info(int model, const char* name, int64_t B, int64_t N, int64_t C, size_t* offset_bytes,
+                              int64_t* rows, int64_t* cols, int64_t* ld) {
+  VQA_REQUIRE(name && offset_bytes && rows && cols && ld, "vqa_stash_info: null pointer");
+  const int64_t M = B * N;
+  char* base = reinterpret_cast<char*>(0x1000);   // fake base: only offsets are used
+  struct Ent { const char* n; const float* p; int64_t r, c, l; };
+  if (model == 0) {
+    Cor2Ws w = carve_cor2(base, B, N, C);
+    const Ent tab[] = {{"compress_v", w.vl, M, H, HP}, {"compress_v2", w.v2l, M, H, HP}, {"compress_q", w.ql, B, H, HP},
+                       {"compress_q_1", w.hq1, B, H, HP}, {"compress_q_2", w.hq2, B, H, HP}, {"linear_q", w.qf, B, H, HP},
+                       {"glimpses", w.vf, B, 2 * A, 2 * A}};
+    for (const Ent& e : tab)
+      if (strcmp(e.n, name) == 0) {
+        *offset_bytes = (size_t)(reinterpret_cast<const char*>(e.p) - base); *rows = e.r; *cols = e.c; *ld = e.l;
+        return VQA_OK;
+      }
+  } else {
+    OdaWs w = carve_oda(base, B, N, C);
+    const Ent tab[] = {{"compress_v", w.vl, M, H, H}, {"compress_q", w.ql, B, H, H}, {"linear_q", w.qf, B, H, HP},
+                       {"glimpses", w.vf, B, A, A}};
+    for (const Ent& e : tab)
+      if (strcmp(e.n, name) == 0) {
+        *offset_bytes = (size_t)(reinterpret_cast<const char*>(e.p) - base); *rows = e.r; *cols = e.c; *ld = e.l;
+        return VQA_OK;
+      }
+  }
+  set_error("vqa_stash_info: unknown stash tensor '%s'", name);
+  return VQA_EINVAL;
+}
 
 // ====================================================================================== CoR2
 extern "C" size_t vqa_cor2_workspace_bytes(int64_t B, int64_t N, int64_t C) {

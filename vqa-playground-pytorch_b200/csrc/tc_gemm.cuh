@@ -2,12 +2,13 @@
 // math with fp32 accumulation in TMEM, optionally error-compensated 3xTF32 (x = hi + lo, three MMAs),
 // which is what the "fp32 parity" mode needs (single TF32 misses the 1e-4 tolerance).
 //
-// One CTA computes a 128 x BN tile.  Warp roles (192 threads):
+// One CTA computes a 128 x BN tile (of one k-split).  Warp roles (320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a STAGES-deep smem ring
 //   warp 1      TMEM allocator + the single thread that issues tcgen05.mma and tcgen05.commit
-//   warps 2-5   operand transform in shared memory between TMA landing and MMA issue
-//               (Philox input-dropout on A, hi/lo split for 3xTF32), then the epilogue:
-//               tcgen05.ld the accumulator rows, apply the epilogue functor, store
+//   warps 2-9   operand transform in shared memory between TMA landing and MMA issue
+//               (Philox input-dropout on A, hi/lo split for 3xTF32; every thread keeps several independent
+//               16-byte chunks in flight), then the epilogue: tcgen05.ld the accumulator rows (two warps per
+//               TMEM lane quadrant, splitting the columns), apply the epilogue functor, store
 // Operands are described by TMA tensor maps and may be K-major (row-major [rows,K]) or MN-major
 // (row-major [K,rows], i.e. the transposed view used by wgrad/dgrad) — no transposed copies are made.
 // Shared-memory/instruction descriptor layouts follow cute/arch/mma_sm100_desc.hpp and
@@ -24,12 +25,25 @@ constexpr int BM = 128;
 constexpr int BK = 32;                    // fp32 elements per k-block = 128 bytes = one swizzle row
 constexpr int A_TILE_BYTES = BM * 128;
 constexpr int ATOM_BYTES = BK * 128;      // one MN-major swizzle atom column: 32 k-rows x 128 B
-constexpr int NUM_THREADS = 192;
-constexpr int XFORM_THREADS = 128;
+constexpr int XFORM_THREADS = 256;
+constexpr int NUM_THREADS = 64 + XFORM_THREADS;
 constexpr int MAXG = VQA_MAX_GROUPS;
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// explicit shared-space 128-bit accesses (generic LD/ST on a casted pointer take the slow global path)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -149,6 +163,7 @@ struct Params {
   int M, N, K;            // D is MxN, reduction length K
   int k_splits;           // blockIdx.z = group * k_splits + split
   int a_mn, b_mn;         // operand major-ness
+  int rewrite_hi;         // 3xTF32: store the truncated hi part back (0: rely on the MMA ignoring the low 13 bits)
   int drop_on;            // Philox dropout on the A operand
   Drop drop;              // seed / thr / scale (layer + base per group below)
   GroupDrop gd;
@@ -281,18 +296,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       Drop d = p.drop;
       d.layer = p.gd.layer[g];
       d.base = p.gd.base[g];
+      constexpr int A_CH = A_TILE_BYTES / 16 / XFORM_THREADS;                       // 4
+      constexpr int B_CH = (C::B_TILE_BYTES / 16 + XFORM_THREADS - 1) / XFORM_THREADS;
       for (int it = 0; it < nkb; ++it) {
         const int s = it % C::STAGES;
         const uint32_t ph = (it / C::STAGES) & 1;
         mbar_wait(&full[s], ph);
         const int k0 = (kb_begin + it) * BK;
-        if (X3 || p.drop_on) {
-          uint8_t* a = stage_a(s);
-          uint8_t* alo = stage_alo(s);
-#pragma unroll 4
-          for (int ch = t; ch < A_TILE_BYTES / 16; ch += XFORM_THREADS) {
-            float4 v = *reinterpret_cast<float4*>(a + ch * 16);
-            if (p.drop_on) {
+        {
+          const uint32_t a = smem_u32(stage_a(s));
+          const uint32_t alo = smem_u32(stage_alo(s));
+          float4 v[A_CH];
+#pragma unroll
+          for (int i = 0; i < A_CH; ++i) v[i] = lds128(a + (t + i * XFORM_THREADS) * 16);
+          if (p.drop_on) {
+            uint32_t w[A_CH][4];
+#pragma unroll
+            for (int i = 0; i < A_CH; ++i) {
+              const int ch = t + i * XFORM_THREADS;
               const int pc = ch & 7;
               int64_t row, col;
               if (!p.a_mn) {
@@ -302,53 +323,94 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
               } else {
                 // 128B_ATOM_32B swizzle: 32-byte chunk index XOR (row & 3), 16-byte half unchanged
                 const int j = ch >> 8, r = (ch >> 3) & 31;
-                const int lc = ((((pc >> 1) ^ (r & 3)) << 1) | (pc & 1));
                 row = k0 + r;
-                col = m0 + j * 32 + (lc << 2);
+                col = m0 + j * 32 + (((((pc >> 1) ^ (r & 3)) << 1) | (pc & 1)) << 2);
               }
-              const uint64_t idx = d.base + (uint64_t)(row * p.drop_ld + col);
-              uint32_t w[4];
-              philox_words4(d.seed, d.layer, idx, w);
-              v.x = w[0] >= d.thr ? v.x * d.scale : 0.0f;
-              v.y = w[1] >= d.thr ? v.y * d.scale : 0.0f;
-              v.z = w[2] >= d.thr ? v.z * d.scale : 0.0f;
-              v.w = w[3] >= d.thr ? v.w * d.scale : 0.0f;
+              philox_words4(d.seed, d.layer, d.base + (uint64_t)(row * p.drop_ld + col), w[i]);
             }
+#pragma unroll
+            for (int i = 0; i < A_CH; ++i) {
+              v[i].x = w[i][0] >= d.thr ? v[i].x * d.scale : 0.0f;
+              v[i].y = w[i][1] >= d.thr ? v[i].y * d.scale : 0.0f;
+              v[i].z = w[i][2] >= d.thr ? v[i].z * d.scale : 0.0f;
+              v[i].w = w[i][3] >= d.thr ? v[i].w * d.scale : 0.0f;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < A_CH; ++i) {
+            const int off = (t + i * XFORM_THREADS) * 16;
             if (X3) {
               float4 lo;
-              split4(v, lo);
-              *reinterpret_cast<float4*>(alo + ch * 16) = lo;
+              split4(v[i], lo);
+              sts128(alo + off, lo);
+              if (p.rewrite_hi || p.drop_on) sts128(a + off, v[i]);
+            } else {
+              sts128(a + off, v[i]);
             }
-            *reinterpret_cast<float4*>(a + ch * 16) = v;
           }
         }
         if (X3) {
-          uint8_t* b = stage_b(s);
-          uint8_t* blo = stage_blo(s);
-#pragma unroll 4
-          for (int ch = t; ch < C::B_TILE_BYTES / 16; ch += XFORM_THREADS) {
-            float4 v = *reinterpret_cast<float4*>(b + ch * 16);
-            float4 lo;
-            split4(v, lo);
-            *reinterpret_cast<float4*>(blo + ch * 16) = lo;
-            *reinterpret_cast<float4*>(b + ch * 16) = v;
+          const uint32_t b = smem_u32(stage_b(s));
+          const uint32_t blo = smem_u32(stage_blo(s));
+          float4 v[B_CH];
+#pragma unroll
+          for (int i = 0; i < B_CH; ++i) {
+            const int ch = t + i * XFORM_THREADS;
+            if (ch < C::B_TILE_BYTES / 16) v[i] = lds128(b + ch * 16);
+          }
+#pragma unroll
+          for (int i = 0; i < B_CH; ++i) {
+            const int ch = t + i * XFORM_THREADS;
+            if (ch < C::B_TILE_BYTES / 16) {
+              float4 lo;
+              split4(v[i], lo);
+              sts128(blo + ch * 16, lo);
+              if (p.rewrite_hi) sts128(b + ch * 16, v[i]);
+            }
           }
         }
         fence_proxy_async();
         mbar_arrive(&ready[s]);
       }
     }
-    // ---- epilogue: TMEM lane quadrant of this warp is (warp % 4)
+    // ---- epilogue: two warps per TMEM lane quadrant (warp % 4), each takes half of the column blocks
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    constexpr int NCB = BN / 32;
+    const int cb0 = half == 0 ? 0 : (NCB + 1) / 2;
+    const int cb1 = half == 0 ? (NCB + 1) / 2 : NCB;
     if (nkb > 0) {
       mbar_wait(accum_full, 0);
       tc_fence_after();
+      if constexpr (Epi::kStaged) {
+        // accumulator rows -> shared (the pipeline stages are free now) -> coalesced row-major epilogue
+        constexpr int LDC = BN + 4;
+        const uint32_t cs = smem_u32(smem);
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 32; ++cb) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
-        p.epi(g, (int64_t)m0 + row, p.M, n0 + cb * 32, p.N, v);
+        for (int cb = cb0; cb < cb1; ++cb) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            sts128(cs + (uint32_t)(row * LDC + cb * 32 + c) * 4u, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+        }
+        named_bar_sync(1, XFORM_THREADS);
+        constexpr int V4 = BN / 4;
+#pragma unroll 2
+        for (int e = t; e < BM * V4; e += XFORM_THREADS) {
+          const int r = e / V4, c4 = e - r * V4;
+          const int64_t m = (int64_t)m0 + r;
+          const int n = n0 + c4 * 4;
+          if (m < p.M && n < p.N) p.epi.row4(g, split, m, n, p.N, lds128(cs + (uint32_t)(r * LDC + c4 * 4) * 4u));
+        }
+      } else {
+#pragma unroll 1
+        for (int cb = cb0; cb < cb1; ++cb) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
+          p.epi(g, split, (int64_t)m0 + row, p.M, n0 + cb * 32, p.N, v);
+        }
       }
     }
   }

@@ -292,6 +292,16 @@ _MODEL = {
 }
 
 
+def stash_tensor(name):
+    """A ReLU output of the most recent forward plan, as a [rows, cols] view into its workspace (tests only)."""
+    model, B, N, Cc, ws = ModelCoreFn.last_workspace
+    off, rows, cols, ld = C.c_size_t(), C.c_int64(), C.c_int64(), C.c_int64()
+    _lib.check(_lib.lib().vqa_stash_info(0 if model == "CoR2" else 1, name.encode(), B, N, Cc, C.byref(off),
+                                         C.byref(rows), C.byref(cols), C.byref(ld)), "vqa_stash_info")
+    flat = ws[off.value:off.value + rows.value * ld.value * 4].view(torch.float32)
+    return flat.view(rows.value, ld.value)[:, :cols.value]
+
+
 def _fill_model_params(pr, B, N, Cc, train, math, seed, v, q, ptab, logits, alpha1, alpha2, v2, ws):
     pr.B, pr.N, pr.C, pr.train, pr.math, pr.seed = B, N, Cc, int(train), _math(math), int(seed)
     pr.v, pr.q, pr.params = v.data_ptr(), q.data_ptr(), ptab
@@ -303,6 +313,7 @@ class ModelCoreFn(torch.autograd.Function):
     """Model.forward of config/CoR2.py:201-237 or config/ODA.py:200-240 as ONE C call (and one more
     for the whole backward).  Returns (logits, alpha1, alpha2, v2); the last three are
     non-differentiable side outputs feeding `alpha_dict`."""
+    last_workspace = None
 
     @staticmethod
     def forward(ctx, model, v, q, train, math, seed, num_regions, num_ans, grad_sink, *params):
@@ -327,6 +338,7 @@ class ModelCoreFn(torch.autograd.Function):
         _fill_model_params(pr, B, N, Cc, train, math, seed, vc, qc, ptab, logits, alpha1, alpha2, v2, ws)
         _lib.check(getattr(L, fwd)(C.byref(pr), _stream()), fwd)
         ctx.model, ctx.meta, ctx.grad_sink = model, (B, N, Cc, train, math, seed), grad_sink
+        ModelCoreFn.last_workspace = (model, B, N, Cc, ws)      # test introspection (vqa_stash_info)
         ctx.keep = (vc, qc, params, ws, logits, alpha1, alpha2, v2)
         if cor2:
             ctx.mark_non_differentiable(alpha1, alpha2, v2)

@@ -273,12 +273,13 @@ def run_ours(args):
 
     # ---- per-op timing (same step, CUDA events around every plan op) -> roofline of the dominant op
     roof, breakdown = None, None
+    nprof = min(args.steps, 10)
     if rank == 0:
         L.vqa_profile_begin()
-        nprof = min(args.steps, 10)
-        for i in range(nprof):
-            step(*resident[i % 4])
-        torch.cuda.synchronize()
+    for i in range(nprof):                 # every rank steps (the step holds the gradient all-reduce)
+        step(*resident[i % 4])
+    torch.cuda.synchronize()
+    if rank == 0:
         buf = ctypes.create_string_buffer(1 << 16)
         L.vqa_profile_end(buf, len(buf))
         per_op = {}

@@ -1,0 +1,93 @@
+"""Host-side logic of the data-parallel engine on CPU tensors with the gloo backend (world_size 2):
+flat gradient buffer layout, bucket plan, SUM all-reduce semantics."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import reasoning_core as rc
+
+
+class FakeModel(torch.nn.Module):
+    """Parameter container with the reference's state_dict layout (no compute)."""
+
+    def __init__(self, name, C):
+        super().__init__()
+        self.MODEL = name
+        self.plist = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(s)) for _, s in rc.param_shapes(name, C)])
+        self.grad_sink = None
+
+    def core_parameters(self):
+        return list(self.plist)
+
+
+def test_bucket_plan_covers_everything():
+    from vqa_playground_pytorch_b200.parallel import COMPLETION_ORDER, GradSink, plan_buckets
+    assert plan_buckets([5, 5, 5, 5], 2) == [(0, 2), (2, 4)]
+    assert plan_buckets([100], 4) == [(0, 1)]
+    assert plan_buckets([], 4) == []
+    for name, C in (("CoR2", 2000), ("ODA", 3000)):
+        n = len(rc.param_shapes(name, C))
+        order = [i for g in COMPLETION_ORDER[name] for i in g]
+        assert sorted(order) == list(range(n))
+        m = FakeModel(name, C)
+        sink = GradSink(m.core_parameters(), name, num_buckets=4)
+        assert 1 <= len(sink.bucket_ranges) <= 4
+        # buckets tile the flat buffer exactly, in order
+        pos = 0
+        for lo, hi in sink.bucket_ranges:
+            assert lo == pos and hi > lo
+            pos = hi
+        assert pos == sink.flat.numel() == sum(p.numel() for p in m.core_parameters())
+        # every p.grad is a view of the flat buffer with the parameter's shape
+        for p in m.core_parameters():
+            assert p.grad.shape == p.shape
+            assert p.grad.untyped_storage().data_ptr() == sink.flat.untyped_storage().data_ptr()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, name, C):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vqa_playground_pytorch_b200.parallel import DataParallelEngine
+    torch.manual_seed(rank)
+    m = FakeModel(name, C)
+    for p in m.parameters():
+        p.data.normal_()
+    eng = DataParallelEngine(m, num_buckets=3)
+    eng.broadcast_parameters()
+    ref0 = [p.data.clone() for p in m.parameters()]
+    # "backward": each rank writes rank-dependent gradients straight into the sink slices
+    for i, s in enumerate(eng.slices):
+        s.fill_(float(rank + 1) * (i + 1))
+    eng.after_backward()
+    eng.wait()
+    ok = True
+    for i, p in enumerate(m.core_parameters()):
+        expect = float(sum(r + 1 for r in range(world)) * (i + 1))        # SUM, not mean (train.py:541)
+        ok &= bool(torch.all(p.grad == expect))
+    # parameters identical across ranks after the broadcast
+    for p, r in zip(m.parameters(), ref0):
+        t = p.data.clone()
+        dist.broadcast(t, 0)
+        ok &= bool(torch.equal(t, p.data))
+    flag = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    assert flag.item() == 1.0
+
+
+@pytest.mark.parametrize("name,C", [("CoR2", 2000), ("ODA", 3000)])
+def test_gloo_world_size_2(name, C):
+    mp.spawn(_worker, args=(2, _free_port(), name, C), nprocs=2, join=True)

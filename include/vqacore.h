@@ -22,10 +22,13 @@
  *
  * Dropout (train mode).  The reference calls F.dropout(p) on the INPUT of every MyLinear /
  * MyConv1d (config/CoR2.py:77-78,115-116; config/ODA.py:94-95,128-129).  Here the mask is
- * never stored: it is regenerated from a counter-based Philox4x32-10 stream,
- *     keep(seed, layer, idx) = Philox(key=seed, ctr=(idx>>2, layer, 0))[idx&3] >= floor(p*2^32),
- * idx = row-major linear index of the element in the logical tensor the reference drops,
- * scale 1/(1-p).  oracle/philox.py is the CPU twin used by the parity tests.
+ * never stored: it is regenerated from a counter-based Philox4x32-10 stream.  One Philox call covers 16
+ * consecutive elements, one byte each:
+ *     out  = Philox4x32-10(key = seed, ctr = (idx>>4 lo, idx>>4 hi, layer, 0))         (4 x 32 bits)
+ *     byte = (out[(idx>>2)&3] >> 8*(idx&3)) & 0xFF;    keep(seed, layer, idx) = byte >= floor(p*256)
+ * idx = row-major linear index of the element in the logical tensor the reference drops, scale 1/(1-p)
+ * (p = 0.5, the only rate the reference uses, is represented exactly).  oracle/philox.py is the CPU twin used
+ * by the parity tests.
  */
 #ifndef VQACORE_H_
 #define VQACORE_H_
@@ -77,6 +80,12 @@ typedef struct {
   uint64_t seed;      /* Philox key; change it every step */
 } vqa_dropout;
 
+/* Packed dropout keep-bits: bit (i & 7) of out[i >> 3] = keep(seed, layer, i) for i < n (n rounded up to 16).
+ * A cache of the Philox contract above for large inputs that several kernels drop with the SAME mask (the
+ * forward GEMM, the wgrad GEMM and the dgrad epilogue of one layer): 1 bit per element instead of one Philox
+ * call per 16 elements in every one of them.  out must hold (n + 15) / 16 * 2 bytes. */
+int vqa_dropout_bits(float p, uint64_t seed, uint32_t layer, uint64_t n, uint8_t* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Grouped linear:  Y_g = act( dropout_g(X_g) . W_g^T + b_g ),  g < groups.
  * Replaces MyLinear.forward (config/CoR2.py:106-119 == config/ODA.py:123-136) and
@@ -100,6 +109,7 @@ typedef struct {
   float* Y[VQA_MAX_GROUPS];        int64_t ldy[VQA_MAX_GROUPS];
   uint32_t layer[VQA_MAX_GROUPS];
   uint64_t drop_index_base[VQA_MAX_GROUPS];
+  const uint8_t* drop_bits[VQA_MAX_GROUPS];  /* optional: packed keep-bits of X_g from vqa_dropout_bits() */
   void* workspace;          /* >= vqa_linear_fwd_workspace_bytes(); may be NULL when that is 0 */
   size_t workspace_bytes;
 } vqa_linear_fwd_params;
@@ -133,6 +143,7 @@ typedef struct {
   float* dX[VQA_MAX_GROUPS];       int64_t lddx[VQA_MAX_GROUPS];
   uint32_t layer[VQA_MAX_GROUPS];
   uint64_t drop_index_base[VQA_MAX_GROUPS];
+  const uint8_t* drop_bits[VQA_MAX_GROUPS];  /* optional, as in the forward */
   void* workspace;          /* >= vqa_linear_bwd_workspace_bytes() */
   size_t workspace_bytes;
 } vqa_linear_bwd_params;

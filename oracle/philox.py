@@ -10,10 +10,11 @@ Why it exists: the reference draws its dropout masks from torch's global generat
 be reproduced inside a fused kernel.  Train-mode parity is therefore checked by
 monkey-patching the reference's `F.dropout` with `dropout_mask` below.
 
-Mask definition (the contract, restated in include/vqacore.h):
-    word(seed, layer, idx) = Philox4x32-10(key = (seed_lo, seed_hi),
-                                           ctr = (q_lo, q_hi, layer, 0))[idx & 3],  q = idx >> 2
-    keep(seed, layer, idx) = word >= floor(p * 2**32)
+Mask definition (the contract, restated in include/vqacore.h): one Philox call covers a group of 16
+consecutive indices, each element owning one byte of the 128-bit output (little-endian over the 4 words):
+    out   = Philox4x32-10(key = (seed_lo, seed_hi), ctr = (g_lo, g_hi, layer, 0)),  g = idx >> 4
+    byte  = (out[(idx >> 2) & 3] >> (8 * (idx & 3))) & 0xFF
+    keep(seed, layer, idx) = byte >= floor(p * 256)        (p = 0.5, the reference's only rate, is exact)
 `idx` is the row-major linear index of the element in the LOGICAL tensor the reference
 applies dropout to (e.g. (b*N + i)*D + c for compress_v's input, ((b*N+i)*N+j)*H+k for
 ODA's pairwise tensor, config/ODA.py:222).
@@ -62,13 +63,26 @@ def words(seed, layer, n, start=0, stream=0):
 
 
 def threshold(p):
-    return min(int(np.floor(float(p) * 4294967296.0)), 0xFFFFFFFF)
+    return min(int(np.floor(float(p) * 256.0)), 255)
+
+
+def mask_bytes(seed, layer, n, start=0):
+    """uint8 byte for each linear index in [start, start+n): 16 indices per Philox call."""
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    g = idx >> np.uint64(4)
+    ug, inv = np.unique(g, return_inverse=True)
+    r = philox4x32_10(ug & _MASK32, ug >> _SH32, np.uint64(layer & 0xFFFFFFFF), np.uint64(0),
+                      int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
+    table = np.stack(r, axis=1)                                   # [groups, 4] uint32
+    word = table[inv, ((idx >> np.uint64(2)) & np.uint64(3)).astype(np.int64)]
+    shift = (np.uint32(8) * (idx & np.uint64(3)).astype(np.uint32))
+    return ((word >> shift) & np.uint32(0xFF)).astype(np.uint8)
 
 
 def dropout_mask(seed, layer, shape, p):
     """float32 {0,1} keep-mask of `shape` (row-major linear index = element index)."""
     n = int(np.prod(shape))
-    keep = words(seed, layer, n) >= np.uint32(threshold(p))
+    keep = mask_bytes(seed, layer, n) >= np.uint8(threshold(p))
     return keep.astype(np.float32).reshape(shape)
 
 

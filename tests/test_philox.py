@@ -28,5 +28,18 @@ def test_mask_is_index_addressed():
 
 
 def test_threshold():
-    assert philox.threshold(0.5) == 0x80000000
+    assert philox.threshold(0.5) == 128
     assert philox.threshold(0.0) == 0
+
+
+def test_mask_bytes_layout():
+    """Element idx owns byte (idx & 15) of the Philox output of group idx >> 4 (little-endian over the 4 words)."""
+    b = philox.mask_bytes(99, 7, 40, start=8)
+    for j, idx in enumerate(range(8, 48)):
+        g = idx >> 4
+        r = philox.philox4x32_10(np.array([g], dtype=np.uint64), 0, 7, 0, 99, 0)
+        w = int(r[(idx >> 2) & 3][0])
+        assert int(b[j]) == (w >> (8 * (idx & 3))) & 0xFF
+    m1 = philox.dropout_mask(5, 1, (3, 37), 0.5)
+    m2 = philox.dropout_mask(5, 1, (111,), 0.5)
+    assert np.array_equal(m1.reshape(-1), m2)

@@ -34,7 +34,8 @@ class LinearFwd(C.Structure):
     _fields_ = [("groups", C.c_int), ("M", i64), ("K", i64), ("N", i64), ("act", C.c_int), ("math", C.c_int),
                 ("p", C.c_float), ("seed", C.c_uint64),
                 ("X", PA), ("ldx", IA), ("W", PA), ("b", PA), ("Y", PA), ("ldy", IA),
-                ("layer", U32A), ("drop_index_base", U64A), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
+                ("layer", U32A), ("drop_index_base", U64A), ("drop_bits", PA), ("workspace", fp),
+                ("workspace_bytes", C.c_size_t)]
 
 
 class LinearBwd(C.Structure):
@@ -42,7 +43,7 @@ class LinearBwd(C.Structure):
                 ("p", C.c_float), ("seed", C.c_uint64), ("accumulate_w", C.c_int), ("accumulate_x", C.c_int),
                 ("X", PA), ("ldx", IA), ("W", PA), ("Y", PA), ("ldy", IA), ("dY", PA), ("lddy", IA),
                 ("dW", PA), ("db", PA), ("dX", PA), ("lddx", IA), ("layer", U32A), ("drop_index_base", U64A),
-                ("workspace", fp), ("workspace_bytes", C.c_size_t)]
+                ("drop_bits", PA), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
 class MutanFwd(C.Structure):
@@ -130,6 +131,7 @@ SYMBOLS = {
     "vqa_launch_count": (C.c_ulonglong, []),
     "vqa_profile_begin": (C.c_int, []),
     "vqa_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "vqa_dropout_bits": (C.c_int, [C.c_float, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
     "vqa_linear_fwd": _OP(LinearFwd), "vqa_linear_bwd": _OP(LinearBwd),
     "vqa_linear_fwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),
     "vqa_linear_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),

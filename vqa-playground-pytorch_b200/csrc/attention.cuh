@@ -17,11 +17,7 @@ struct FuseGeneric {
   __device__ __forceinline__ float raw(int64_t b, int64_t i, int64_t c) const { return fuse[(b * N + i) * Ff + c]; }
   // multipliers of 4 consecutive elements c..c+3 of row (b,i)
   __device__ __forceinline__ void mul4(int64_t b, int64_t i, int64_t c, float (&m)[4]) const {
-    if (!d.on) { m[0] = m[1] = m[2] = m[3] = 1.0f; return; }
-    uint32_t w[4];
-    philox_words4(d.seed, d.layer, d.base + (uint64_t)((b * N + i) * Ff + c), w);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) m[e] = w[e] >= d.thr ? d.scale : 0.0f;
+    d.mul4((uint64_t)((b * N + i) * Ff + c), m);
   }
 };
 // ODA, eval mode: fuse_eff[b,i,k] = vl[b,i,k]*ql[b,k] against Wsum[g,k] = sum_j W[g,j*H+k]

@@ -53,30 +53,35 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// The four words covering linear indices 4q .. 4q+3.
-__device__ __forceinline__ uint4 philox_quad(uint64_t seed, uint32_t layer, uint64_t q) {
-  return philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), layer, 0u),
+// One Philox call covers a GROUP of 16 consecutive linear indices: element idx owns byte (idx & 15) of the
+// 128-bit output (little-endian over the words x,y,z,w).  keep(idx) = byte >= thr8, thr8 = floor(p * 256)
+// (p = 0.5, the only rate the reference uses, is exact).  Contract: include/vqacore.h; twin: oracle/philox.py.
+__device__ __forceinline__ uint4 philox_group(uint64_t seed, uint32_t layer, uint64_t g) {
+  return philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), layer, 0u),
                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
-
-__device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint32_t layer, uint64_t idx) {
-  const uint4 r = philox_quad(seed, layer, idx >> 2);
-  const uint32_t s = (uint32_t)idx & 3u;
-  return s == 0 ? r.x : (s == 1 ? r.y : (s == 2 ? r.z : r.w));
+__device__ __forceinline__ uint32_t pick_word(const uint4& r, uint32_t i) {
+  return i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w));
 }
-
-// Words for four consecutive linear indices idx..idx+3 (idx need not be a multiple of 4).
-__device__ __forceinline__ void philox_words4(uint64_t seed, uint32_t layer, uint64_t idx, uint32_t (&w)[4]) {
-  const uint4 a = philox_quad(seed, layer, idx >> 2);
-  const uint32_t sh = (uint32_t)idx & 3u;
-  if (sh == 0) {
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    return;
-  }
-  const uint4 b = philox_quad(seed, layer, (idx >> 2) + 1);
-  const uint32_t t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+__device__ __forceinline__ uint32_t philox_byte(uint64_t seed, uint32_t layer, uint64_t idx) {
+  const uint4 r = philox_group(seed, layer, idx >> 4);
+  return (pick_word(r, ((uint32_t)idx >> 2) & 3u) >> (8u * ((uint32_t)idx & 3u))) & 0xFFu;
+}
+// the four bytes (packed, element e in bits [8e, 8e+8)) of 4 consecutive indices idx..idx+3
+__device__ __forceinline__ uint32_t philox_bytes4(uint64_t seed, uint32_t layer, uint64_t idx) {
+  if ((idx & 3) == 0) return pick_word(philox_group(seed, layer, idx >> 4), ((uint32_t)idx >> 2) & 3u);
+  // unaligned start (row length not a multiple of 4): the run straddles two words, possibly two groups
+  const uint4 r0 = philox_group(seed, layer, idx >> 4);
+  const uint64_t last = idx + 3;
+  const uint4 r1 = (last >> 4) == (idx >> 4) ? r0 : philox_group(seed, layer, last >> 4);
+  uint32_t out = 0;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) w[e] = t[sh + e];
+  for (int e = 0; e < 4; ++e) {
+    const uint64_t i = idx + e;
+    const uint4& r = (i >> 4) == (idx >> 4) ? r0 : r1;
+    out |= ((pick_word(r, ((uint32_t)i >> 2) & 3u) >> (8u * ((uint32_t)i & 3u))) & 0xFFu) << (8 * e);
+  }
+  return out;
 }
 
 // Device-side view of one dropout call site.
@@ -84,21 +89,28 @@ struct Drop {
   uint64_t seed;
   uint64_t base;      // added to the element index
   uint32_t layer;
-  uint32_t thr;       // keep iff word >= thr
+  uint32_t thr;       // keep iff byte >= thr (0..255)
   float scale;        // 1/(1-p)
   int on;
   // multiplier (0 or scale) for logical element idx
   __device__ __forceinline__ float mul(uint64_t idx) const {
     if (!on) return 1.0f;
-    return philox_word(seed, layer, base + idx) >= thr ? scale : 0.0f;
+    return philox_byte(seed, layer, base + idx) >= thr ? scale : 0.0f;
+  }
+  // multipliers for 4 consecutive elements idx..idx+3
+  __device__ __forceinline__ void mul4(uint64_t idx, float (&m)[4]) const {
+    if (!on) { m[0] = m[1] = m[2] = m[3] = 1.0f; return; }
+    const uint32_t b = philox_bytes4(seed, layer, base + idx);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m[e] = ((b >> (8 * e)) & 0xFFu) >= thr ? scale : 0.0f;
   }
 };
 
 static inline uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
+  double t = (double)p * 256.0;
   if (t < 0) t = 0;
-  if (t > 4294967295.0) t = 4294967295.0;
-  return (uint32_t)t;   // floor
+  if (t > 255.0) t = 255.0;
+  return (uint32_t)t;   // floor(p * 256)
 }
 
 static inline Drop make_drop(float p, uint64_t seed, uint32_t layer, uint64_t base, int train_on = 1) {

@@ -166,17 +166,22 @@ struct EpiDgrad {
   Drop drop;
   GroupDrop gd;
   int64_t drop_ld;
+  const uint8_t* bits[MAXG];
   __device__ __forceinline__ void row4(int g, int, int64_t m, int n, int N, const float4 v) const {
     float* x = dX[g];
     if (!x) return;
     x += m * ld[g] + n;
     const int nv = N - n < 4 ? N - n : 4;
     float o[4] = {v.x, v.y, v.z, v.w};
-    if (drop_on) {
-      uint32_t wd[4];
-      philox_words4(drop.seed, gd.layer[g], gd.base[g] + (uint64_t)(m * drop_ld + n), wd);
+    if (drop_on && bits[g]) {
+      const uint64_t e = (uint64_t)(m * drop_ld + n);
+      const uint32_t nb = ((uint32_t)__ldg(bits[g] + (e >> 3)) >> (uint32_t)(e & 4)) & 0xFu;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = wd[e] >= drop.thr ? o[e] * drop.scale : 0.0f;
+      for (int j = 0; j < 4; ++j) o[j] = ((nb >> j) & 1u) ? o[j] * drop.scale : 0.0f;
+    } else if (drop_on) {
+      const uint32_t bt = philox_bytes4(drop.seed, gd.layer[g], gd.base[g] + (uint64_t)(m * drop_ld + n));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = ((bt >> (8 * e)) & 0xFFu) >= drop.thr ? o[e] * drop.scale : 0.0f;
     }
     if (atomic) {
 #pragma unroll
@@ -237,6 +242,10 @@ static int pick_splits(int64_t tiles, int64_t K) {
 template <class Epi>
 static int launch(Params<Epi> p, int groups, bool x3, cudaStream_t st, const char* what) {
   p.rewrite_hi = rewrite_hi_flag();
+  {
+    const char* e = getenv("VQA_TC_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   const int bn = pick_bn(p.N);
   if (bn == 160) return x3 ? launch_cfg<160, true>(p, groups, st, what) : launch_cfg<160, false>(p, groups, st, what);
   return x3 ? launch_cfg<128, true>(p, groups, st, what) : launch_cfg<128, false>(p, groups, st, what);
@@ -317,6 +326,19 @@ static int pack_weights(const float* const* W, int groups, int64_t rows, int64_t
   if (blocks > 4096) blocks = 4096;
   pack_rows_kernel<<<dim3((unsigned)blocks, (unsigned)groups), 256, 0, st>>>(a, dst, rows, rows_pad, K, Kp);
   return check_launch("pack_rows");
+}
+
+// keep-bits: thread per group of 16 elements -> 2 bytes
+__global__ void dropout_bits_kernel(uint64_t seed, uint32_t layer, uint32_t thr, uint64_t ngroups,
+                                    uint16_t* __restrict__ out) {
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 r = philox_group(seed, layer, g);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) bits |= (((w[e >> 2] >> (8 * (e & 3))) & 0xFFu) >= thr ? 1u : 0u) << e;
+    out[g] = (uint16_t)bits;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ Mutan pieces
@@ -469,7 +491,8 @@ int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
   q.k_splits = pick_splits(cdiv(p->M, BM) * cdiv(p->N, bn) * p->groups, p->K);
   q.drop_on = p->p > 0.0f;
   fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
-  q.drop_ld = p->K;
+  q.drop_ld = p->K; q.drop_rows = p->M;
+  for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
   q.epi.act = p->act;
   q.epi.atomic = q.k_splits > 1;
   if (q.epi.atomic)
@@ -541,7 +564,8 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
     q.M = (int)p->K; q.N = (int)p->N; q.K = (int)p->M; q.a_mn = 1; q.b_mn = 1;
     q.drop_on = p->p > 0.0f;
     fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
-    q.drop_ld = p->K;
+    q.drop_ld = p->K; q.drop_rows = p->M;
+    for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
     // split the reduction (over the M rows) so that the grid covers the chip
     const int64_t tiles = cdiv(p->K, BM) * cdiv(p->N, bn) * p->groups;
     const int64_t kb = cdiv(p->M, BK);
@@ -577,6 +601,7 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
     q.epi.drop_on = p->p > 0.0f;
     fill_drop(q.epi.drop, q.epi.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
     q.epi.drop_ld = p->K;
+    for (int g = 0; g < MAXG; ++g) q.epi.bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
     VQA_TRY(launch(q, p->groups, x3, st, "tc_linear_bwd.dgrad"));
   }
   return VQA_OK;
@@ -740,6 +765,16 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
   VQA_TRY(wgrad(p->X2, p->ldx2, Mh, p->K2, w.dh2, p->dW2, "tc_mutan_bwd.dw2"));
   if (p->dX2) VQA_TRY(dgrad(w.dh2, Mh, w.w2pk, p->K2, K2p, p->dX2, p->lddx2, p->accumulate_x2, "tc_mutan_bwd.dx2"));
   return VQA_OK;
+}
+
+int tc_dropout_bits(float pdrop, uint64_t seed, uint32_t layer, uint64_t n, uint8_t* out, cudaStream_t st) {
+  const uint64_t ngroups = (n + 15) / 16;
+  if (ngroups == 0) return VQA_OK;
+  uint64_t blocks = (ngroups + 255) / 256;
+  if (blocks > 65535) blocks = 65535;
+  tc::dropout_bits_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed, layer, drop_threshold(pdrop), ngroups,
+                                                            reinterpret_cast<uint16_t*>(out));
+  return check_launch("dropout_bits");
 }
 
 size_t tc_linear_fwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N) {

@@ -114,6 +114,12 @@ struct DgradStore {
 
 using namespace vqa;
 
+extern "C" int vqa_dropout_bits(float p, uint64_t seed, uint32_t layer, uint64_t n, uint8_t* out, void* stream) {
+  VQA_REQUIRE(out != nullptr && p >= 0.0f && p < 1.0f, "vqa_dropout_bits: bad argument");
+  VQA_REQUIRE(reinterpret_cast<uintptr_t>(out) % 2 == 0, "vqa_dropout_bits: out must be 2-byte aligned");
+  return tc_dropout_bits(p, seed, layer, n, out, (cudaStream_t)stream);
+}
+
 extern "C" size_t vqa_linear_fwd_workspace_bytes(int math, int groups, int64_t M, int64_t K, int64_t N) {
   return tc_linear_fwd_ws(math, groups, M, K, N);
 }

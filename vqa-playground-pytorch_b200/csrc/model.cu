@@ -49,6 +49,7 @@ struct Cor2Ws {
   float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled2, *dalpha2, *dz2, *dfuse2, *dv2, *dv2l, *d_f2_H2, *dql, *dg1, *dg2, *dhq1,
       *dhq2, *dalpha_ext, *dpooled1, *dalpha1, *dz1, *dfuse1, *dvl, *d_f1_H2;
   float* lin_ws; size_t lin_ws_bytes;
+  uint8_t *bits_v, *bits_v2;   // packed dropout keep-bits of compress_v / compress_v2 inputs (train mode)
   size_t bytes;
 };
 
@@ -85,6 +86,7 @@ static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N, int64_t C) {
   w.dpooled1 = c.take(B * G * D); w.dalpha1 = c.take(M * G); w.dz1 = c.take(M * G);
   w.dfuse1 = c.take(M * F); w.dvl = c.take(M * HP); w.d_f1_H2 = c.take(2 * B * F);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
+  w.bits_v = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16)); w.bits_v2 = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16));
   w.bytes = c.off;
   return w;
 }
@@ -93,6 +95,7 @@ struct OdaWs {
   float *vl, *ql, *qf, *wsum, *pooled, *vf, *ff_H1, *ff_H2, *xf;
   float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled, *dalpha, *dz, *dwsum, *dvl, *dql;
   float* lin_ws; size_t lin_ws_bytes;
+  uint8_t* bits_v;
   size_t bytes;
 };
 
@@ -107,6 +110,7 @@ static OdaWs carve_oda(void* base, int64_t B, int64_t N, int64_t C) {
   w.dpooled = c.take(B * G * D); w.dalpha = c.take(M * G); w.dz = c.take(M * G); w.dwsum = c.take(G * H);
   w.dvl = c.take(M * H); w.dql = c.take(B * H);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
+  w.bits_v = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16));
   w.bytes = c.off;
   return w;
 }
@@ -125,13 +129,15 @@ struct Ctx {
 
 // single or grouped linear forward; weight index widx[g] (bias = widx[g]+1)
 static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
-                   const int64_t* ldx, const int* widx, float* const* Y, const int64_t* ldy, const uint32_t* layer) {
+                   const int64_t* ldx, const int* widx, float* const* Y, const int64_t* ldy, const uint32_t* layer,
+                   const uint8_t* bits = nullptr) {
   vqa_linear_fwd_params lp = {};
   lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
   lp.p = c.pdrop(); lp.seed = c.p->seed;
   for (int g = 0; g < groups; ++g) {
     lp.X[g] = X[g]; lp.ldx[g] = ldx[g]; lp.W[g] = c.W[widx[g]]; lp.b[g] = c.W[widx[g] + 1];
     lp.Y[g] = Y[g]; lp.ldy[g] = ldy[g]; lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
+    lp.drop_bits[g] = (c.p->train && groups == 1) ? bits : nullptr;
   }
   lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
   return vqa_linear_fwd(&lp, c.stream);
@@ -140,7 +146,7 @@ static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
 static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
                    const int64_t* ldx, const int* widx, const float* const* Y, const int64_t* ldy,
                    const float* const* dY, const int64_t* lddy, float* const* dX, const int64_t* lddx, int accumulate_x,
-                   const uint32_t* layer) {
+                   const uint32_t* layer, const uint8_t* bits = nullptr) {
   vqa_linear_bwd_params lp = {};
   lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
   lp.p = c.pdrop(); lp.seed = c.p->seed; lp.accumulate_w = c.accumulate; lp.accumulate_x = accumulate_x;
@@ -150,6 +156,7 @@ static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
     lp.dW[g] = c.grad(widx[g]); lp.db[g] = c.grad(widx[g] + 1);
     lp.dX[g] = dX ? dX[g] : nullptr; lp.lddx[g] = lddx ? lddx[g] : 0;
     lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
+    lp.drop_bits[g] = (c.p->train && groups == 1) ? bits : nullptr;
   }
   lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
   return vqa_linear_bwd(&lp, c.stream);
@@ -272,6 +279,11 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   const int64_t B = p->B, N = p->N, M = B * N;
   Cor2Ws w = carve_cor2(p->workspace, B, N, p->C);
   Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes};
+  if (p->train) {  // keep-bits of the two big dropout sites, shared by their fwd GEMM, wgrad GEMM and dgrad epilogue
+    ProfScope ps_(stream, "dropout_bits");
+    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
+    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, L_COMPRESS_V2, (uint64_t)M * D, w.bits_v2, stream));
+  }
   {  // four 2400->310 question projections in one launch (config/CoR2.py:211,195,196,228)
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
     int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
@@ -286,7 +298,7 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // compress_v (config/CoR2.py:213)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, w.bits_v)); }
   }
   { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1, F)); }   // fusion_vq1 :214
   {  // att1 on raw v (:214)
@@ -307,7 +319,7 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // compress_v2 (:218)
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V2};
-    { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, w.bits_v2)); }
   }
   { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2, F)); }  // fusion_vq2 :219
   {  // att2 on v2 (:219)
@@ -361,7 +373,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; const float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {HP};
     float* dX[1] = {w.dv2}; int64_t lddx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V2};
-    { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 1, layer)); }
+    { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 1, layer, w.bits_v2)); }
   }
   // ---- att1 branch: glimpse linears first (they initialise dpooled1), then the compound objects add to it
   { ProfScope ps_(stream, "att1.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled1, ATT1_G, w.vf, w.dvf, 2 * A, 0, w.dpooled1, L_ATT1_G)); }
@@ -392,7 +404,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
   {  // compress_v: v is a graph input, no dgrad
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
+    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer, w.bits_v)); }
   }
   {  // the four question projections
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
@@ -415,10 +427,14 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   const int64_t B = p->B, N = p->N, M = B * N;
   OdaWs w = carve_oda(p->workspace, B, N, p->C);
   Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes};
+  if (p->train) {
+    ProfScope ps_(stream, "dropout_bits");
+    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
+  }
   {  // compress_v (config/ODA.py:211)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, w.bits_v)); }
   }
   {  // compress_q + linear_q (:214, :233)
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
@@ -473,7 +489,7 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
   {
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
+    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer, w.bits_v)); }
   }
   {
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};

@@ -53,8 +53,8 @@ oda_pair_logits_train_kernel(int64_t N, int64_t H, Drop d, const float* __restri
   float acc[G] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t t = threadIdx.x; t < NH / 4; t += ODA_THREADS) {
     const int64_t e0 = t * 4;
-    const uint4 r = philox_quad(d.seed, d.layer, (base + (uint64_t)e0) >> 2);
-    const uint32_t wd[4] = {r.x, r.y, r.z, r.w};
+    const uint32_t bt = philox_bytes4(d.seed, d.layer, base + (uint64_t)e0);
+    const uint32_t wd[4] = {bt & 0xFFu, (bt >> 8) & 0xFFu, (bt >> 16) & 0xFFu, bt >> 24};
     int64_t j = e0 / H, k = e0 - j * H;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -127,7 +127,7 @@ __global__ void oda_pair_bwd_train_dv_kernel(int64_t N, int64_t H, Drop d, const
       float colj = 0.0f;
       for (int64_t i = 0; i < N; ++i) {
         const uint64_t idx = (uint64_t)((b * N + i) * NH + j * H + k);
-        if (philox_word(d.seed, d.layer, d.base + idx) >= d.thr) {
+        if (philox_byte(d.seed, d.layer, d.base + idx) >= d.thr) {
           const float* zz = dz_s + i * G;
           const float u = (zz[0] * w[0] + zz[1] * w[1] + zz[2] * w[2] + zz[3] * w[3]) * d.scale;
           colj -= u;
@@ -175,8 +175,8 @@ oda_pair_bwd_train_dw_kernel(int64_t B, int64_t N, int64_t H, Drop d, const floa
     for (int u = 0; u < 4; ++u) { qv[u] = ql[b * H + kk[u]]; vj[u] = vb[jj[u] * H + kk[u]]; }
     for (int64_t i = 0; i < N; ++i) {
       const uint64_t idx = d.base + (uint64_t)((b * N + i) * NH + e0);
-      const uint4 r = philox_quad(d.seed, d.layer, idx >> 2);
-      const uint32_t wd[4] = {r.x, r.y, r.z, r.w};
+      const uint32_t bt = philox_bytes4(d.seed, d.layer, idx);
+      const uint32_t wd[4] = {bt & 0xFFu, (bt >> 8) & 0xFFu, (bt >> 16) & 0xFFu, bt >> 24};
       const float4 z4 = *reinterpret_cast<const float4*>(&dz[(b * N + i) * G]);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

@@ -163,23 +163,35 @@ struct Params {
   int M, N, K;            // D is MxN, reduction length K
   int k_splits;           // blockIdx.z = group * k_splits + split
   int a_mn, b_mn;         // operand major-ness
+  int debug;              // timing experiments only (VQA_TC_DEBUG): 1 skip A transform, 2 skip B transform, 4 no transform stage
   int rewrite_hi;         // 3xTF32: store the truncated hi part back (0: rely on the MMA ignoring the low 13 bits)
   int drop_on;            // Philox dropout on the A operand
   Drop drop;              // seed / thr / scale (layer + base per group below)
   GroupDrop gd;
   int64_t drop_ld;        // row length of the logical tensor the mask is indexed in
+  int64_t drop_rows;      // its row count (bounds for the bit-mask loads)
+  const uint8_t* drop_bits[MAXG];   // optional packed keep-bits (vqa_dropout_bits); else Philox in registers
   Epi epi;
 };
 
+// Shared-memory rings.  The TMA-landed ("raw") tiles are prefetched NS_RAW deep to cover the L2/HBM latency;
+// the 3xTF32 residual ("lo") tiles are produced by the transform warps just ahead of the MMA and only need
+// NS_LO = 2 slots, which is what lets the raw ring be deep despite the 227 KB limit.
 template <int BN, bool X3>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int RAW_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int LO_BYTES = X3 ? RAW_BYTES : 0;
+  static constexpr int NS_LO = X3 ? 2 : 0;
+  static constexpr int BUDGET = 220 * 1024;
+  static constexpr int NS_RAW_ = (BUDGET - NS_LO * LO_BYTES) / RAW_BYTES;
+  static constexpr int NS_RAW = NS_RAW_ > 6 ? 6 : NS_RAW_;
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(STAGES >= 2, "tile too large");
+  static constexpr int TILE_BYTES = NS_RAW * RAW_BYTES + NS_LO * LO_BYTES;
+  static constexpr int SMEM_BYTES = TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(NS_RAW >= 2, "tile too large");
   static_assert(BN % 32 == 0 && BN <= 256, "BN");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 // split a 16-byte chunk in place into tf32-representable hi and the fp32 residual lo
@@ -199,12 +211,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
   using C = Cfg<BN, X3>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full = bars;                      // TMA bytes landed
-  uint64_t* ready = bars + C::STAGES;         // transform done (only when p needs a transform)
-  uint64_t* empty = bars + 2 * C::STAGES;     // MMAs that read the stage have completed
-  uint64_t* accum_full = bars + 3 * C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 1);
+  constexpr int NR = C::NS_RAW, NL = C::NS_LO > 0 ? C::NS_LO : 1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::TILE_BYTES);
+  uint64_t* full = bars;                      // [NR] TMA bytes landed in raw slot
+  uint64_t* empty = bars + NR;                // [NR] MMAs that read raw slot have completed
+  uint64_t* ready = bars + 2 * NR;            // [NR] transform of the k-block in raw slot done
+  uint64_t* lo_empty = bars + 3 * NR;         // [NL] MMAs that read lo slot have completed
+  uint64_t* accum_full = bars + 3 * NR + NL;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NR + NL + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.z / p.k_splits, split = blockIdx.z % p.k_splits;
@@ -214,14 +228,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
   const int kb_begin = split * kb_per;
   const int kb_end = min(kb_total, kb_begin + kb_per);
   const int nkb = max(0, kb_end - kb_begin);
-  const bool need_xform = X3 || p.drop_on;
+  const bool need_xform = (X3 || p.drop_on) && !(p.debug & 4);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < NR; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&ready[s], XFORM_THREADS);
       mbar_init(&empty[s], 1);
     }
+    for (int s = 0; s < NL; ++s) mbar_init(&lo_empty[s], 1);
     mbar_init(accum_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA[g]);
@@ -233,17 +248,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto stage_a = [&](int s) { return smem + s * C::STAGE_BYTES; };
-  auto stage_alo = [&](int s) { return smem + s * C::STAGE_BYTES + A_TILE_BYTES; };
-  auto stage_b = [&](int s) { return smem + s * C::STAGE_BYTES + (X3 ? 2 : 1) * A_TILE_BYTES; };
-  auto stage_blo = [&](int s) { return smem + s * C::STAGE_BYTES + 2 * A_TILE_BYTES + C::B_TILE_BYTES; };
+  auto stage_a = [&](int s) { return smem + s * C::RAW_BYTES; };
+  auto stage_b = [&](int s) { return smem + s * C::RAW_BYTES + A_TILE_BYTES; };
+  auto stage_alo = [&](int l) { return smem + NR * C::RAW_BYTES + l * C::LO_BYTES; };
+  auto stage_blo = [&](int l) { return smem + NR * C::RAW_BYTES + l * C::LO_BYTES + A_TILE_BYTES; };
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       for (int it = 0; it < nkb; ++it) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (it / C::STAGES) & 1;
+        const int s = it % NR;
+        const uint32_t ph = (it / NR) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], A_TILE_BYTES + C::B_TILE_BYTES);
         const int k0 = (kb_begin + it) * BK;
@@ -268,8 +283,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       const uint32_t a_step = p.a_mn ? 1024u : 32u;   // bytes per k-step of 8 tf32
       const uint32_t b_step = p.b_mn ? 1024u : 32u;
       for (int it = 0; it < nkb; ++it) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (it / C::STAGES) & 1;
+        const int s = it % NR, l = it % NL;
+        const uint32_t ph = (it / NR) & 1;
         mbar_wait(need_xform ? &ready[s] : &full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(stage_a(s)), b_addr = smem_u32(stage_b(s));
@@ -279,13 +294,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
           const uint64_t db = make_smem_desc(b_addr + k * b_step, p.b_mn != 0);
           umma_tf32(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           if (X3) {
-            const uint64_t dal = make_smem_desc(smem_u32(stage_alo(s)) + k * a_step, p.a_mn != 0);
-            const uint64_t dbl = make_smem_desc(smem_u32(stage_blo(s)) + k * b_step, p.b_mn != 0);
+            const uint64_t dal = make_smem_desc(smem_u32(stage_alo(l)) + k * a_step, p.a_mn != 0);
+            const uint64_t dbl = make_smem_desc(smem_u32(stage_blo(l)) + k * b_step, p.b_mn != 0);
             umma_tf32(tmem_base, da, dbl, idesc, 1u);
             umma_tf32(tmem_base, dal, db, idesc, 1u);
           }
         }
         umma_commit(&empty[s]);
+        if (X3) umma_commit(&lo_empty[l]);
       }
       umma_commit(accum_full);
     }
@@ -296,21 +312,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       Drop d = p.drop;
       d.layer = p.gd.layer[g];
       d.base = p.gd.base[g];
+      const uint8_t* __restrict__ bits = p.drop_bits[g];
       constexpr int A_CH = A_TILE_BYTES / 16 / XFORM_THREADS;                       // 4
       constexpr int B_CH = (C::B_TILE_BYTES / 16 + XFORM_THREADS - 1) / XFORM_THREADS;
       for (int it = 0; it < nkb; ++it) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (it / C::STAGES) & 1;
-        mbar_wait(&full[s], ph);
+        const int s = it % NR, l = it % NL;
+        const uint32_t ph = (it / NR) & 1;
         const int k0 = (kb_begin + it) * BK;
-        {
+        // keep-bits of this thread's 4 chunks, fetched BEFORE waiting for the tile so the loads overlap the wait
+        uint32_t nib[4] = {0xFu, 0xFu, 0xFu, 0xFu};
+        if (p.drop_on && bits) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ch = t + i * XFORM_THREADS;
+            const int pc = ch & 7;
+            int64_t row, col;
+            if (!p.a_mn) {
+              const int r = ch >> 3;
+              row = m0 + r;
+              col = k0 + ((pc ^ (r & 7)) << 2);
+            } else {
+              const int j = ch >> 8, r = (ch >> 3) & 31;
+              row = k0 + r;
+              col = m0 + j * 32 + (((((pc >> 1) ^ (r & 3)) << 1) | (pc & 1)) << 2);
+            }
+            if (row < p.drop_rows && col < p.drop_ld) {
+              const uint64_t e = (uint64_t)(row * p.drop_ld + col);
+              nib[i] = ((uint32_t)__ldg(bits + (e >> 3)) >> (uint32_t)(e & 4)) & 0xFu;
+            }
+          }
+        }
+        if (X3) mbar_wait(&lo_empty[l], ((it / NL) & 1) ^ 1);     // lo slot free (MMAs of k-block it-NL done)
+        mbar_wait(&full[s], ph);
+        if (!(p.debug & 1)) {
           const uint32_t a = smem_u32(stage_a(s));
-          const uint32_t alo = smem_u32(stage_alo(s));
+          const uint32_t alo = smem_u32(stage_alo(l));
           float4 v[A_CH];
 #pragma unroll
           for (int i = 0; i < A_CH; ++i) v[i] = lds128(a + (t + i * XFORM_THREADS) * 16);
-          if (p.drop_on) {
-            uint32_t w[A_CH][4];
+          if (p.drop_on && bits) {
+#pragma unroll
+            for (int i = 0; i < A_CH; ++i) {
+              v[i].x = (nib[i] & 1u) ? v[i].x * d.scale : 0.0f;
+              v[i].y = (nib[i] & 2u) ? v[i].y * d.scale : 0.0f;
+              v[i].z = (nib[i] & 4u) ? v[i].z * d.scale : 0.0f;
+              v[i].w = (nib[i] & 8u) ? v[i].w * d.scale : 0.0f;
+            }
+          } else if (p.drop_on) {
+            // The 4 lanes of a quartet hold the 4 chunks of one aligned 64-byte run (= 16 consecutive logical
+            // elements = one Philox group) in every pass; lane (t & 3) == i computes the group of pass i and the
+            // quartet shares it by shuffle: one Philox call per thread per k-block instead of four.
+            static_assert(A_CH == 4, "quartet sharing assumes 4 passes");
+            uint64_t idx[A_CH];
 #pragma unroll
             for (int i = 0; i < A_CH; ++i) {
               const int ch = t + i * XFORM_THREADS;
@@ -326,14 +379,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                 row = k0 + r;
                 col = m0 + j * 32 + (((((pc >> 1) ^ (r & 3)) << 1) | (pc & 1)) << 2);
               }
-              philox_words4(d.seed, d.layer, d.base + (uint64_t)(row * p.drop_ld + col), w[i]);
+              idx[i] = d.base + (uint64_t)(row * p.drop_ld + col);
             }
+            const int qi = t & 3;
+            const uint64_t my_idx = qi == 0 ? idx[0] : (qi == 1 ? idx[1] : (qi == 2 ? idx[2] : idx[3]));
+            uint4 mine;
+            const bool aligned = (p.drop_ld & 15) == 0 && (d.base & 15) == 0;   // groups never straddle quartets
+            if (aligned) mine = philox_group(d.seed, d.layer, my_idx >> 4);
 #pragma unroll
             for (int i = 0; i < A_CH; ++i) {
-              v[i].x = w[i][0] >= d.thr ? v[i].x * d.scale : 0.0f;
-              v[i].y = w[i][1] >= d.thr ? v[i].y * d.scale : 0.0f;
-              v[i].z = w[i][2] >= d.thr ? v[i].z * d.scale : 0.0f;
-              v[i].w = w[i][3] >= d.thr ? v[i].w * d.scale : 0.0f;
+              uint32_t bt;
+              if (aligned) {
+                const int src = (lane & ~3) | i;
+                uint4 r;
+                r.x = __shfl_sync(0xffffffffu, mine.x, src);
+                r.y = __shfl_sync(0xffffffffu, mine.y, src);
+                r.z = __shfl_sync(0xffffffffu, mine.z, src);
+                r.w = __shfl_sync(0xffffffffu, mine.w, src);
+                bt = pick_word(r, ((uint32_t)idx[i] >> 2) & 3u);
+              } else {
+                bt = philox_bytes4(d.seed, d.layer, idx[i]);
+              }
+              v[i].x = (bt & 0xFFu) >= d.thr ? v[i].x * d.scale : 0.0f;
+              v[i].y = ((bt >> 8) & 0xFFu) >= d.thr ? v[i].y * d.scale : 0.0f;
+              v[i].z = ((bt >> 16) & 0xFFu) >= d.thr ? v[i].z * d.scale : 0.0f;
+              v[i].w = (bt >> 24) >= d.thr ? v[i].w * d.scale : 0.0f;
             }
           }
 #pragma unroll
@@ -349,9 +419,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             }
           }
         }
-        if (X3) {
+        if (X3 && !(p.debug & 2)) {
           const uint32_t b = smem_u32(stage_b(s));
-          const uint32_t blo = smem_u32(stage_blo(s));
+          const uint32_t blo = smem_u32(stage_blo(l));
           float4 v[B_CH];
 #pragma unroll
           for (int i = 0; i < B_CH; ++i) {

@@ -59,7 +59,7 @@ def _math(math):
 
 
 # =========================================================================== grouped linear
-def linear_forward(xs, ws, bs, act, p, seed, layers, math=0, outs=None):
+def linear_forward(xs, ws, bs, act, p, seed, layers, math=0, outs=None, bits=None):
     """Y_g = act(dropout(X_g) W_g^T + b_g). xs/ws/bs: lists (one entry per group), X_g [M,K] (row stride
     may exceed K). Returns list of Y_g [M,N] (or writes into `outs`, which may be strided views)."""
     g = len(xs)
@@ -75,6 +75,7 @@ def linear_forward(xs, ws, bs, act, p, seed, layers, math=0, outs=None):
         pr.W[i], pr.b[i] = ws[i].data_ptr(), _p(bs[i])
         pr.Y[i], pr.ldy[i] = outs[i].data_ptr(), outs[i].stride(0)
         pr.layer[i], pr.drop_index_base[i] = int(layers[i]), 0
+        pr.drop_bits[i] = _p(bits[i]) if bits is not None else None
     ws = _workspace(_lib.lib().vqa_linear_fwd_workspace_bytes(pr.math, g, M, K, N), xs[0].device)
     pr.workspace, pr.workspace_bytes = _p(ws), (ws.numel() if ws is not None else 0)
     _lib.check(_lib.lib().vqa_linear_fwd(C.byref(pr), _stream()), "vqa_linear_fwd")
@@ -82,7 +83,7 @@ def linear_forward(xs, ws, bs, act, p, seed, layers, math=0, outs=None):
 
 
 def linear_backward(xs, ws, ys, dys, act, p, seed, layers, need_dx, math=0, dws=None, dbs=None, dxs=None,
-                    accumulate_w=False, accumulate_x=False):
+                    accumulate_w=False, accumulate_x=False, bits=None):
     g = len(xs)
     M, K = xs[0].shape
     N = ws[0].shape[0]
@@ -104,10 +105,19 @@ def linear_backward(xs, ws, ys, dys, act, p, seed, layers, need_dx, math=0, dws=
         pr.dW[i], pr.db[i] = _p(dws[i]), _p(dbs[i])
         pr.dX[i], pr.lddx[i] = _p(dxs[i]), (dxs[i].stride(0) if dxs[i] is not None else K)
         pr.layer[i], pr.drop_index_base[i] = int(layers[i]), 0
+        pr.drop_bits[i] = _p(bits[i]) if bits is not None else None
     ws = _workspace(_lib.lib().vqa_linear_bwd_workspace_bytes(pr.math, g, M, K, N), dev)
     pr.workspace, pr.workspace_bytes = _p(ws), (ws.numel() if ws is not None else 0)
     _lib.check(_lib.lib().vqa_linear_bwd(C.byref(pr), _stream()), "vqa_linear_bwd")
     return dws, dbs, dxs
+
+
+def dropout_bits(p, seed, layer, n, device):
+    """Packed keep-bits of n elements (vqa_dropout_bits)."""
+    out = torch.empty(((n + 15) // 16 * 2,), device=device, dtype=torch.uint8)
+    _lib.check(_lib.lib().vqa_dropout_bits(float(p), int(seed), int(layer), int(n), out.data_ptr(), _stream()),
+               "vqa_dropout_bits")
+    return out
 
 
 class LinearFn(torch.autograd.Function):

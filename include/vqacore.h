@@ -78,13 +78,30 @@ typedef struct {
   float p;            /* drop probability; 0 disables */
   uint32_t layer;     /* Philox counter word 2 */
   uint64_t seed;      /* Philox key; change it every step */
+  const uint64_t* seed_dev;  /* optional: when non-NULL the key is READ FROM DEVICE MEMORY at kernel run time and
+                                `seed` is ignored, so a captured CUDA graph draws a fresh mask on every replay
+                                (advance it with vqa_seed_advance inside the graph) */
 } vqa_dropout;
+/* *seed_dev += 1, enqueued on the stream. */
+int vqa_seed_advance(uint64_t* seed_dev, void* stream);
+
+/* Padded weight copies for the tensor-core paths.  TMA needs 16-byte row strides, which K = 310 / 510 weights do
+ * not have; vqa_pack_weights copies each segment src [rows, K] into dst [rows_pad, roundup(K,4)] (zero filled) in
+ * ONE launch, so a training step packs every such weight once and both its forward and backward reuse it
+ * (Wp / W1p / W2p fields below).  Without them the ops pack into their own workspace on every call. */
+typedef struct {
+  const float* src; float* dst;
+  int64_t rows, rows_pad, K;
+} vqa_pack_segment;
+#define VQA_MAX_PACK_SEGMENTS 24
+int vqa_pack_weights(const vqa_pack_segment* segs, int nsegs, void* stream);
 
 /* Packed dropout keep-bits: bit (i & 7) of out[i >> 3] = keep(seed, layer, i) for i < n (n rounded up to 16).
  * A cache of the Philox contract above for large inputs that several kernels drop with the SAME mask (the
  * forward GEMM, the wgrad GEMM and the dgrad epilogue of one layer): 1 bit per element instead of one Philox
  * call per 16 elements in every one of them.  out must hold (n + 15) / 16 * 2 bytes. */
-int vqa_dropout_bits(float p, uint64_t seed, uint32_t layer, uint64_t n, uint8_t* out, void* stream);
+int vqa_dropout_bits(float p, uint64_t seed, const uint64_t* seed_dev, uint32_t layer, uint64_t n, uint8_t* out,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Grouped linear:  Y_g = act( dropout_g(X_g) . W_g^T + b_g ),  g < groups.
@@ -103,6 +120,7 @@ typedef struct {
   int math;
   float p;
   uint64_t seed;
+  const uint64_t* seed_dev;                  /* optional device-resident key, see vqa_dropout */
   const float* X[VQA_MAX_GROUPS];  int64_t ldx[VQA_MAX_GROUPS];
   const float* W[VQA_MAX_GROUPS];            /* [N,K] row-major (nn.Linear / Conv1d k=1 layout) */
   const float* b[VQA_MAX_GROUPS];            /* [N] or NULL */
@@ -110,6 +128,7 @@ typedef struct {
   uint32_t layer[VQA_MAX_GROUPS];
   uint64_t drop_index_base[VQA_MAX_GROUPS];
   const uint8_t* drop_bits[VQA_MAX_GROUPS];  /* optional: packed keep-bits of X_g from vqa_dropout_bits() */
+  const float* Wp[VQA_MAX_GROUPS];           /* optional: W_g re-laid by vqa_pack_weights() as [N, roundup(K,4)] */
   void* workspace;          /* >= vqa_linear_fwd_workspace_bytes(); may be NULL when that is 0 */
   size_t workspace_bytes;
 } vqa_linear_fwd_params;
@@ -132,6 +151,7 @@ typedef struct {
   int math;
   float p;
   uint64_t seed;
+  const uint64_t* seed_dev;
   int accumulate_w;
   int accumulate_x;
   const float* X[VQA_MAX_GROUPS];  int64_t ldx[VQA_MAX_GROUPS];
@@ -144,6 +164,7 @@ typedef struct {
   uint32_t layer[VQA_MAX_GROUPS];
   uint64_t drop_index_base[VQA_MAX_GROUPS];
   const uint8_t* drop_bits[VQA_MAX_GROUPS];  /* optional, as in the forward */
+  const float* Wp[VQA_MAX_GROUPS];           /* optional, as in the forward */
   void* workspace;          /* >= vqa_linear_bwd_workspace_bytes() */
   size_t workspace_bytes;
 } vqa_linear_bwd_params;
@@ -170,6 +191,8 @@ typedef struct {
   float* H1;      /* [R,M,F] or NULL */
   float* H2;      /* [R,Mh,F] */
   float* Y; int64_t ldy;
+  const float* W1p;         /* optional: the R W1 matrices stacked by vqa_pack_weights as [R*roundup(F,32), roundup(K1,4)] */
+  const float* W2p;         /* optional: likewise for W2 */
   void* workspace;          /* >= vqa_mutan_workspace_bytes(.., bwd=0); 256-byte aligned */
   size_t workspace_bytes;
 } vqa_mutan_fwd_params;
@@ -198,6 +221,8 @@ typedef struct {
   float* dW2[VQA_MAX_GROUPS]; float* db2[VQA_MAX_GROUPS];
   float* dX1; int64_t lddx1;     /* NULL: skipped */
   float* dX2; int64_t lddx2;     /* NULL: skipped */
+  const float* W1p;         /* optional, as in the forward */
+  const float* W2p;
   void* workspace;          /* >= vqa_mutan_workspace_bytes(.., bwd=1); 256-byte aligned */
   size_t workspace_bytes;
 } vqa_mutan_bwd_params;
@@ -351,6 +376,7 @@ typedef struct {
   int train;                 /* 1: dropout on (Philox, `seed`) */
   int math;
   uint64_t seed;
+  const uint64_t* seed_dev;  /* optional device-resident Philox key (CUDA graphs), see vqa_dropout */
   const float* v;            /* [B,N,2048] */
   const float* q;            /* [B,2400] */
   const float* const* params;

@@ -128,3 +128,38 @@ def test_full_size_properties(cuda):
     m.fixed_seed = 99
     ts = m({"v": v[:32], "q_idxes": q[:32]})
     assert parity.rel_err(ts, t1[:32]) <= 1e-5
+
+
+def test_cuda_graph_step_matches_eager(cuda):
+    """engine.GraphedStep (fwd+loss+bwd captured once, replayed) gives the eager step's loss and gradients for the
+    same device-resident Philox key, and draws a fresh dropout mask on every replay."""
+    import torch
+    from oracle import reasoning_core as rc
+    from vqa_playground_pytorch_b200 import ops
+    from vqa_playground_pytorch_b200.config import CoR2
+    from vqa_playground_pytorch_b200.engine import GraphedStep, kld_loss
+    B, C = 8, 2000
+    sd = rc.synth_state_dict("CoR2", C, seed=3)
+    v, q, a = (t.cuda() for t in rc.synth_inputs(B, 36, C, seed=9))
+    m = CoR2.Model(None, C, precision="tf32x3")
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    sample = {"v": v, "q_idxes": q, "a": a}
+    step = GraphedStep(m, sample, warmup=2, seed=1000)
+    l1 = step(sample).item()
+    key1 = int(m.seed_device.item())
+    g1 = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    l2 = step(sample).item()
+    assert int(m.seed_device.item()) == key1 + 1
+    assert l1 != l2                                   # new key -> new mask -> different loss
+    # eager step with the key of the first replay
+    m2 = CoR2.Model(None, C, precision="tf32x3")
+    m2.load_state_dict(sd)
+    m2 = m2.cuda().train()
+    m2.fixed_seed = key1
+    loss = kld_loss(m2(sample), a)
+    loss.backward()
+    assert abs(loss.item() - l1) <= 1e-5 * abs(l1)
+    gmax = max(p.grad.abs().max().item() for p in m2.parameters())
+    for n, p in m2.named_parameters():
+        assert parity.rel_err(g1[n], p.grad, 1e-6 * gmax) <= 1e-4, n

@@ -27,30 +27,31 @@ U64A = C.c_uint64 * MAXG
 
 
 class Dropout(C.Structure):
-    _fields_ = [("p", C.c_float), ("layer", C.c_uint32), ("seed", C.c_uint64)]
+    _fields_ = [("p", C.c_float), ("layer", C.c_uint32), ("seed", C.c_uint64), ("seed_dev", fp)]
 
 
 class LinearFwd(C.Structure):
     _fields_ = [("groups", C.c_int), ("M", i64), ("K", i64), ("N", i64), ("act", C.c_int), ("math", C.c_int),
-                ("p", C.c_float), ("seed", C.c_uint64),
+                ("p", C.c_float), ("seed", C.c_uint64), ("seed_dev", fp),
                 ("X", PA), ("ldx", IA), ("W", PA), ("b", PA), ("Y", PA), ("ldy", IA),
-                ("layer", U32A), ("drop_index_base", U64A), ("drop_bits", PA), ("workspace", fp),
+                ("layer", U32A), ("drop_index_base", U64A), ("drop_bits", PA), ("Wp", PA), ("workspace", fp),
                 ("workspace_bytes", C.c_size_t)]
 
 
 class LinearBwd(C.Structure):
     _fields_ = [("groups", C.c_int), ("M", i64), ("K", i64), ("N", i64), ("act", C.c_int), ("math", C.c_int),
-                ("p", C.c_float), ("seed", C.c_uint64), ("accumulate_w", C.c_int), ("accumulate_x", C.c_int),
+                ("p", C.c_float), ("seed", C.c_uint64), ("seed_dev", fp), ("accumulate_w", C.c_int),
+                ("accumulate_x", C.c_int),
                 ("X", PA), ("ldx", IA), ("W", PA), ("Y", PA), ("ldy", IA), ("dY", PA), ("lddy", IA),
                 ("dW", PA), ("db", PA), ("dX", PA), ("lddx", IA), ("layer", U32A), ("drop_index_base", U64A),
-                ("drop_bits", PA), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
+                ("drop_bits", PA), ("Wp", PA), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
 class MutanFwd(C.Structure):
     _fields_ = [("R", C.c_int), ("M", i64), ("K1", i64), ("K2", i64), ("F", i64), ("rows_per_h2", i64),
                 ("math", C.c_int), ("X1", fp), ("ldx1", i64), ("X2", fp), ("ldx2", i64),
                 ("W1", PA), ("b1", PA), ("W2", PA), ("b2", PA), ("H1", fp), ("H2", fp), ("Y", fp), ("ldy", i64),
-                ("workspace", fp), ("workspace_bytes", C.c_size_t)]
+                ("W1p", fp), ("W2p", fp), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
 class MutanBwd(C.Structure):
@@ -60,7 +61,11 @@ class MutanBwd(C.Structure):
                 ("H1", fp), ("H2", fp), ("dY", fp), ("lddy", i64), ("dH2", fp),
                 ("dW1", PA), ("db1", PA), ("dW2", PA), ("db2", PA),
                 ("dX1", fp), ("lddx1", i64), ("dX2", fp), ("lddx2", i64),
-                ("workspace", fp), ("workspace_bytes", C.c_size_t)]
+                ("W1p", fp), ("W2p", fp), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
+
+
+class PackSegment(C.Structure):
+    _fields_ = [("src", fp), ("dst", fp), ("rows", i64), ("rows_pad", i64), ("K", i64)]
 
 
 class PoolFwd(C.Structure):
@@ -104,7 +109,7 @@ class KldParams(C.Structure):
 
 class ModelFwd(C.Structure):
     _fields_ = [("B", i64), ("N", i64), ("C", i64), ("train", C.c_int), ("math", C.c_int), ("seed", C.c_uint64),
-                ("v", fp), ("q", fp), ("params", C.POINTER(fp)), ("logits", fp), ("alpha1", fp), ("alpha2", fp),
+                ("seed_dev", fp), ("v", fp), ("q", fp), ("params", C.POINTER(fp)), ("logits", fp), ("alpha1", fp), ("alpha2", fp),
                 ("v2", fp), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
@@ -113,7 +118,7 @@ class ModelBwd(C.Structure):
 
 
 STRUCTS = {
-    "vqa_dropout": Dropout, "vqa_linear_fwd_params": LinearFwd, "vqa_linear_bwd_params": LinearBwd,
+    "vqa_dropout": Dropout, "vqa_pack_segment": PackSegment, "vqa_linear_fwd_params": LinearFwd, "vqa_linear_bwd_params": LinearBwd,
     "vqa_mutan_fwd_params": MutanFwd, "vqa_mutan_bwd_params": MutanBwd,
     "vqa_region_softmax_pool_fwd_params": PoolFwd, "vqa_region_softmax_pool_bwd_params": PoolBwd,
     "vqa_cor_compound_fwd_params": CompoundFwd, "vqa_cor_compound_bwd_params": CompoundBwd,
@@ -131,7 +136,10 @@ SYMBOLS = {
     "vqa_launch_count": (C.c_ulonglong, []),
     "vqa_profile_begin": (C.c_int, []),
     "vqa_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
-    "vqa_dropout_bits": (C.c_int, [C.c_float, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "vqa_pack_weights": (C.c_int, [C.POINTER(PackSegment), C.c_int, C.c_void_p]),
+    "vqa_dropout_bits": (C.c_int, [C.c_float, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p,
+                                   C.c_void_p]),
+    "vqa_seed_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vqa_linear_fwd": _OP(LinearFwd), "vqa_linear_bwd": _OP(LinearBwd),
     "vqa_linear_fwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),
     "vqa_linear_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),

@@ -100,6 +100,6 @@ class Model(CoreModel):
         self.alpha_dict = {
             'alpha1': torch.split(alpha1, 1, dim=2),
             'alpha2': torch.split(alpha2, 1, dim=2),
-            'feature': v2[:, [0, 1], :]
+            'feature': v2[:, 0:2, :]          # reference: v2_feature[:, [0, 1], :] (config/CoR2.py:224); a view, no kernel
         }
         return logits

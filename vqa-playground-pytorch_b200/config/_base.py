@@ -29,6 +29,7 @@ class CoreModel(nn.Module):
         self.alpha_dict = {}
         self.grad_sink = None          # set by parallel.DataParallelEngine
         self.fixed_seed = None         # tests: pin the Philox key of the next train-mode forward
+        self.seed_device = None        # int64[1] CUDA tensor: device-resident Philox key (engine.GraphedStep)
 
     def core_parameters(self):
         """Parameters in the reference's state_dict order, seq2vec.* excluded."""
@@ -44,7 +45,8 @@ class CoreModel(nn.Module):
         seed = 0
         if train:
             seed = self.fixed_seed if self.fixed_seed is not None else ops.next_seed()
-        return ops.ModelCoreFn.apply(self.MODEL, v, q, train, self.precision, seed, self.num_regions,
+        return ops.ModelCoreFn.apply(self.MODEL, v, q, train, self.precision, seed,
+                                     self.seed_device if train else None, self.num_regions,
                                      self.num_classes, self.grad_sink, *self.core_parameters())
 
     def __call__(self, *input, **kwargs):

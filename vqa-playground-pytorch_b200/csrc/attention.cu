@@ -146,7 +146,7 @@ extern "C" int vqa_region_softmax_pool_fwd(const vqa_region_softmax_pool_fwd_par
   VQA_REQUIRE(smem <= 200 * 1024, "vqa_region_softmax_pool_fwd: Ff=%lld too large for shared memory", (long long)p->Ff);
   if (p->B == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0)};
+  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev)};
   auto kern = att_logits_softmax_kernel<FuseGeneric>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<(unsigned)p->B, ATT_THREADS, smem, st>>>(fs, p->N, p->Ff, p->Wc, p->bc, p->alpha);
@@ -168,7 +168,7 @@ extern "C" int vqa_region_softmax_pool_bwd(const vqa_region_softmax_pool_bwd_par
     cudaMemsetAsync(p->dWc, 0, (size_t)G * p->Ff * sizeof(float), st);
     if (p->dbc) cudaMemsetAsync(p->dbc, 0, G * sizeof(float), st);
   }
-  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0)};
+  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev)};
   const int64_t groups = p->B < 2 * (int64_t)sm_count() ? p->B : 2 * (int64_t)sm_count();
   dim3 grid((unsigned)groups, (unsigned)cdiv(p->Ff, ATT_THREADS));
   const size_t smem = (size_t)2 * p->N * G * sizeof(float);

@@ -87,20 +87,22 @@ __device__ __forceinline__ uint32_t philox_bytes4(uint64_t seed, uint32_t layer,
 // Device-side view of one dropout call site.
 struct Drop {
   uint64_t seed;
+  const uint64_t* seed_ptr;   // when non-null the key is read from device memory (CUDA-graph replay, fresh mask per step)
   uint64_t base;      // added to the element index
   uint32_t layer;
   uint32_t thr;       // keep iff byte >= thr (0..255)
   float scale;        // 1/(1-p)
   int on;
+  __device__ __forceinline__ uint64_t key() const { return seed_ptr ? __ldg(seed_ptr) : seed; }
   // multiplier (0 or scale) for logical element idx
   __device__ __forceinline__ float mul(uint64_t idx) const {
     if (!on) return 1.0f;
-    return philox_byte(seed, layer, base + idx) >= thr ? scale : 0.0f;
+    return philox_byte(key(), layer, base + idx) >= thr ? scale : 0.0f;
   }
   // multipliers for 4 consecutive elements idx..idx+3
   __device__ __forceinline__ void mul4(uint64_t idx, float (&m)[4]) const {
     if (!on) { m[0] = m[1] = m[2] = m[3] = 1.0f; return; }
-    const uint32_t b = philox_bytes4(seed, layer, base + idx);
+    const uint32_t b = philox_bytes4(key(), layer, base + idx);
 #pragma unroll
     for (int e = 0; e < 4; ++e) m[e] = ((b >> (8 * e)) & 0xFFu) >= thr ? scale : 0.0f;
   }
@@ -113,9 +115,11 @@ static inline uint32_t drop_threshold(float p) {
   return (uint32_t)t;   // floor(p * 256)
 }
 
-static inline Drop make_drop(float p, uint64_t seed, uint32_t layer, uint64_t base, int train_on = 1) {
+static inline Drop make_drop(float p, uint64_t seed, uint32_t layer, uint64_t base, int train_on = 1,
+                             const uint64_t* seed_ptr = nullptr) {
   Drop d;
   d.seed = seed;
+  d.seed_ptr = seed_ptr;
   d.base = base;
   d.layer = layer;
   d.on = (train_on && p > 0.0f) ? 1 : 0;

@@ -179,7 +179,7 @@ struct EpiDgrad {
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = ((nb >> j) & 1u) ? o[j] * drop.scale : 0.0f;
     } else if (drop_on) {
-      const uint32_t bt = philox_bytes4(drop.seed, gd.layer[g], gd.base[g] + (uint64_t)(m * drop_ld + n));
+      const uint32_t bt = philox_bytes4(drop.key(), gd.layer[g], gd.base[g] + (uint64_t)(m * drop_ld + n));
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = ((bt >> (8 * e)) & 0xFFu) >= drop.thr ? o[e] * drop.scale : 0.0f;
     }
@@ -252,8 +252,8 @@ static int launch(Params<Epi> p, int groups, bool x3, cudaStream_t st, const cha
 }
 
 static void fill_drop(Drop& d, GroupDrop& gd, float pdrop, uint64_t seed, const uint32_t* layer, const uint64_t* base,
-                      int groups) {
-  d = make_drop(pdrop, seed, 0, 0);
+                      int groups, const uint64_t* seed_dev = nullptr) {
+  d = make_drop(pdrop, seed, 0, 0, 1, seed_dev);
   for (int g = 0; g < MAXG; ++g) {
     const int s = g < groups ? g : 0;
     gd.layer[g] = layer[s];
@@ -328,9 +328,22 @@ static int pack_weights(const float* const* W, int groups, int64_t rows, int64_t
   return check_launch("pack_rows");
 }
 
+// One launch for a list of weights (vqa_pack_weights). grid = (blocks, nsegs)
+struct PackSegs { vqa_pack_segment s[VQA_MAX_PACK_SEGMENTS]; };
+__global__ void pack_segments_kernel(PackSegs a) {
+  const vqa_pack_segment sg = a.s[blockIdx.y];
+  const int64_t Kp = (sg.K + 3) / 4 * 4;
+  const int64_t total = sg.rows_pad * Kp;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / Kp, k = t - r * Kp;
+    sg.dst[t] = (k < sg.K && r < sg.rows) ? sg.src[r * sg.K + k] : 0.0f;
+  }
+}
+
 // keep-bits: thread per group of 16 elements -> 2 bytes
-__global__ void dropout_bits_kernel(uint64_t seed, uint32_t layer, uint32_t thr, uint64_t ngroups,
-                                    uint16_t* __restrict__ out) {
+__global__ void dropout_bits_kernel(uint64_t seed, const uint64_t* seed_ptr, uint32_t layer, uint32_t thr,
+                                    uint64_t ngroups, uint16_t* __restrict__ out) {
+  if (seed_ptr) seed = __ldg(seed_ptr);
   for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 r = philox_group(seed, layer, g);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
@@ -472,7 +485,9 @@ int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
   }
   const int64_t Kp = roundup(p->K, 4);
   float* wpk = reinterpret_cast<float*>(p->workspace);
-  if (pack) {
+  bool prepacked = pack;
+  for (int g = 0; g < p->groups; ++g) prepacked &= p->Wp[g] != nullptr;
+  if (pack && !prepacked) {
     if (!wpk || p->workspace_bytes < (size_t)p->groups * p->N * Kp * sizeof(float) ||
         reinterpret_cast<uintptr_t>(wpk) % 16 != 0)
       return VQA_TC_UNSUPPORTED;
@@ -483,14 +498,15 @@ int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
   for (int g = 0; g < MAXG; ++g) {
     const int s = g < p->groups ? g : 0;
     VQA_TRY(operand_tmap(&q.tmA[g], p->X[s], false, p->M, p->K, p->ldx[s], BM));
-    if (pack) VQA_TRY(operand_tmap(&q.tmB[g], wpk + (size_t)s * p->N * Kp, false, p->N, p->K, Kp, bn));
+    if (prepacked) VQA_TRY(operand_tmap(&q.tmB[g], p->Wp[s], false, p->N, p->K, Kp, bn));
+    else if (pack) VQA_TRY(operand_tmap(&q.tmB[g], wpk + (size_t)s * p->N * Kp, false, p->N, p->K, Kp, bn));
     else VQA_TRY(operand_tmap(&q.tmB[g], p->W[s], false, p->N, p->K, p->K, bn));
     q.epi.Y[g] = p->Y[s]; q.epi.bias[g] = p->b[s]; q.epi.ld[g] = p->ldy[s];
   }
   q.M = (int)p->M; q.N = (int)p->N; q.K = (int)p->K; q.a_mn = 0; q.b_mn = 0;
   q.k_splits = pick_splits(cdiv(p->M, BM) * cdiv(p->N, bn) * p->groups, p->K);
   q.drop_on = p->p > 0.0f;
-  fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
+  fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
   q.drop_ld = p->K; q.drop_rows = p->M;
   for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
   q.epi.act = p->act;
@@ -532,7 +548,9 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
   float* dz = reinterpret_cast<float*>(p->workspace);
   float* wpk = reinterpret_cast<float*>(reinterpret_cast<char*>(p->workspace) + dz_bytes);
   if (reinterpret_cast<uintptr_t>(dz) % 16 != 0) return VQA_TC_UNSUPPORTED;
-  if (pack) VQA_TRY(pack_weights(p->W, p->groups, p->N, p->N, p->K, wpk, st));
+  bool prepacked = pack;
+  for (int g = 0; g < p->groups; ++g) prepacked &= p->Wp[g] != nullptr;
+  if (pack && !prepacked) VQA_TRY(pack_weights(p->W, p->groups, p->N, p->N, p->K, wpk, st));
 
   // 1. dZ (padded) + bias gradient
   {
@@ -563,7 +581,7 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
     q.epi.ldw = p->K;
     q.M = (int)p->K; q.N = (int)p->N; q.K = (int)p->M; q.a_mn = 1; q.b_mn = 1;
     q.drop_on = p->p > 0.0f;
-    fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
+    fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
     q.drop_ld = p->K; q.drop_rows = p->M;
     for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
     // split the reduction (over the M rows) so that the grid covers the chip
@@ -585,7 +603,8 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
     for (int g = 0; g < MAXG; ++g) {
       const int s = g < p->groups ? g : 0;
       VQA_TRY(operand_tmap(&q.tmA[g], dz + (size_t)s * p->M * ldz, false, p->M, p->N, ldz, BM));
-      if (pack) VQA_TRY(operand_tmap(&q.tmB[g], wpk + (size_t)s * p->N * Kp, true, p->K, p->N, Kp, bn));
+      if (prepacked) VQA_TRY(operand_tmap(&q.tmB[g], p->Wp[s], true, p->K, p->N, Kp, bn));
+      else if (pack) VQA_TRY(operand_tmap(&q.tmB[g], wpk + (size_t)s * p->N * Kp, true, p->K, p->N, Kp, bn));
       else VQA_TRY(operand_tmap(&q.tmB[g], p->W[s], true, p->K, p->N, p->K, bn));
       q.epi.dX[g] = p->dX[s]; q.epi.ld[g] = p->lddx[s];
     }
@@ -599,7 +618,7 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
       for (int g = 0; g < p->groups; ++g)
         if (p->dX[g]) zero_window(p->dX[g], p->lddx[g], p->M, p->K, st);
     q.epi.drop_on = p->p > 0.0f;
-    fill_drop(q.epi.drop, q.epi.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups);
+    fill_drop(q.epi.drop, q.epi.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
     q.epi.drop_ld = p->K;
     for (int g = 0; g < MAXG; ++g) q.epi.bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
     VQA_TRY(launch(q, p->groups, x3, st, "tc_linear_bwd.dgrad"));
@@ -642,8 +661,12 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
     return VQA_TC_UNSUPPORTED;
   const bool x3 = p->math == VQA_MATH_TF32X3;
   const int64_t Fp = roundup(p->F, 32), K1p = roundup(p->K1, 4), K2p = roundup(p->K2, 4);
-  VQA_TRY(pack_weights(p->W1, p->R, p->F, Fp, p->K1, w.w1pk, st));
-  VQA_TRY(pack_weights(p->W2, p->R, p->F, Fp, p->K2, w.w2pk, st));
+  if (p->W1p && p->W2p) {
+    w.w1pk = const_cast<float*>(p->W1p); w.w2pk = const_cast<float*>(p->W2p);
+  } else {
+    VQA_TRY(pack_weights(p->W1, p->R, p->F, Fp, p->K1, w.w1pk, st));
+    VQA_TRY(pack_weights(p->W2, p->R, p->F, Fp, p->K2, w.w2pk, st));
+  }
   const int bn = pick_bn(p->F);
   {  // H2_r = X2 . W2_r^T + b2_r  (grouped over r)
     Params<EpiBiasAct> q = {};
@@ -702,8 +725,12 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
   const bool x3 = p->math == VQA_MATH_TF32X3;
   const int R = p->R;
   const int64_t Fp = roundup(p->F, 32), K1p = roundup(p->K1, 4), K2p = roundup(p->K2, 4), RF = R * Fp;
-  VQA_TRY(pack_weights(p->W1, R, p->F, Fp, p->K1, w.w1pk, st));
-  VQA_TRY(pack_weights(p->W2, R, p->F, Fp, p->K2, w.w2pk, st));
+  if (p->W1p && p->W2p) {
+    w.w1pk = const_cast<float*>(p->W1p); w.w2pk = const_cast<float*>(p->W2p);
+  } else {
+    VQA_TRY(pack_weights(p->W1, R, p->F, Fp, p->K1, w.w1pk, st));
+    VQA_TRY(pack_weights(p->W2, R, p->F, Fp, p->K2, w.w2pk, st));
+  }
   if (!p->accumulate_w)
     for (int r = 0; r < R; ++r) {
       if (p->db1[r]) cudaMemsetAsync(p->db1[r], 0, (size_t)p->F * 4, st);
@@ -767,12 +794,34 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
   return VQA_OK;
 }
 
-int tc_dropout_bits(float pdrop, uint64_t seed, uint32_t layer, uint64_t n, uint8_t* out, cudaStream_t st) {
+int tc_pack_segments(const vqa_pack_segment* segs, int nsegs, cudaStream_t st) {
+  tc::PackSegs a = {};
+  int64_t biggest = 1;
+  for (int i = 0; i < nsegs; ++i) {
+    a.s[i] = segs[i];
+    const int64_t n = segs[i].rows_pad * ((segs[i].K + 3) / 4 * 4);
+    if (n > biggest) biggest = n;
+  }
+  int64_t blocks = cdiv(biggest, 256 * 4);
+  if (blocks > 1024) blocks = 1024;
+  tc::pack_segments_kernel<<<dim3((unsigned)blocks, (unsigned)nsegs), 256, 0, st>>>(a);
+  return check_launch("pack_segments");
+}
+
+// *seed += 1 (graph-captured at the head of every replayed step)
+__global__ void seed_advance_kernel(uint64_t* seed) { *seed += 1; }
+int tc_seed_advance(uint64_t* seed_dev, cudaStream_t st) {
+  seed_advance_kernel<<<1, 1, 0, st>>>(seed_dev);
+  return check_launch("seed_advance");
+}
+
+int tc_dropout_bits(float pdrop, uint64_t seed, const uint64_t* seed_dev, uint32_t layer, uint64_t n, uint8_t* out,
+                    cudaStream_t st) {
   const uint64_t ngroups = (n + 15) / 16;
   if (ngroups == 0) return VQA_OK;
   uint64_t blocks = (ngroups + 255) / 256;
   if (blocks > 65535) blocks = 65535;
-  tc::dropout_bits_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed, layer, drop_threshold(pdrop), ngroups,
+  tc::dropout_bits_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed, seed_dev, layer, drop_threshold(pdrop), ngroups,
                                                             reinterpret_cast<uint16_t*>(out));
   return check_launch("dropout_bits");
 }

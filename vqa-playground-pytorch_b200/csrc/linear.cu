@@ -114,10 +114,25 @@ struct DgradStore {
 
 using namespace vqa;
 
-extern "C" int vqa_dropout_bits(float p, uint64_t seed, uint32_t layer, uint64_t n, uint8_t* out, void* stream) {
+extern "C" int vqa_pack_weights(const vqa_pack_segment* segs, int nsegs, void* stream) {
+  VQA_REQUIRE(segs != nullptr && nsegs >= 0 && nsegs <= VQA_MAX_PACK_SEGMENTS, "vqa_pack_weights: bad segment list");
+  for (int i = 0; i < nsegs; ++i)
+    VQA_REQUIRE(segs[i].src && segs[i].dst && segs[i].rows >= 0 && segs[i].rows_pad >= segs[i].rows && segs[i].K > 0,
+                "vqa_pack_weights: bad segment %d", i);
+  if (nsegs == 0) return VQA_OK;
+  return tc_pack_segments(segs, nsegs, (cudaStream_t)stream);
+}
+
+extern "C" int vqa_dropout_bits(float p, uint64_t seed, const uint64_t* seed_dev, uint32_t layer, uint64_t n,
+                                uint8_t* out, void* stream) {
   VQA_REQUIRE(out != nullptr && p >= 0.0f && p < 1.0f, "vqa_dropout_bits: bad argument");
   VQA_REQUIRE(reinterpret_cast<uintptr_t>(out) % 2 == 0, "vqa_dropout_bits: out must be 2-byte aligned");
-  return tc_dropout_bits(p, seed, layer, n, out, (cudaStream_t)stream);
+  return tc_dropout_bits(p, seed, seed_dev, layer, n, out, (cudaStream_t)stream);
+}
+
+extern "C" int vqa_seed_advance(uint64_t* seed_dev, void* stream) {
+  VQA_REQUIRE(seed_dev != nullptr, "vqa_seed_advance: null pointer");
+  return tc_seed_advance(seed_dev, (cudaStream_t)stream);
 }
 
 extern "C" size_t vqa_linear_fwd_workspace_bytes(int math, int groups, int64_t M, int64_t K, int64_t N) {
@@ -144,7 +159,7 @@ extern "C" int vqa_linear_fwd(const vqa_linear_fwd_params* p, void* stream) {
   }
   XDropLoader a; WLoader b; BiasActStore e;
   a.K = p->K; b.K = p->K; e.act = p->act;
-  a.d = make_drop(p->p, p->seed, 0, 0);
+  a.d = make_drop(p->p, p->seed, 0, 0, 1, p->seed_dev);
   for (int g = 0; g < VQA_MAX_GROUPS; ++g) {
     const int s = g < p->groups ? g : 0;
     a.X.p[g] = p->X[s]; a.ld.v[g] = p->ldx[s]; a.dt.layer[g] = p->layer[s]; a.dt.base[g] = p->drop_index_base[s];
@@ -175,7 +190,7 @@ extern "C" int vqa_linear_bwd(const vqa_linear_bwd_params* p, void* stream) {
   if (any_w) {
     DzT_Loader a; XDropT_Loader b; WgradStore e;
     a.act = p->act; b.K = p->K; e.K = p->K; e.accumulate = p->accumulate_w;
-    b.d = make_drop(p->p, p->seed, 0, 0);
+    b.d = make_drop(p->p, p->seed, 0, 0, 1, p->seed_dev);
     for (int g = 0; g < VQA_MAX_GROUPS; ++g) {
       const int s = g < p->groups ? g : 0;
       a.dY.p[g] = p->dY[s]; a.Y.p[g] = p->Y[s]; a.lddy.v[g] = p->lddy[s]; a.ldy.v[g] = p->ldy[s];
@@ -188,7 +203,7 @@ extern "C" int vqa_linear_bwd(const vqa_linear_bwd_params* p, void* stream) {
   if (any_x) {
     Dz_Loader a; WT_Loader b; DgradStore e;
     a.act = p->act; b.K = p->K; e.K = p->K; e.accumulate = p->accumulate_x;
-    e.d = make_drop(p->p, p->seed, 0, 0);
+    e.d = make_drop(p->p, p->seed, 0, 0, 1, p->seed_dev);
     for (int g = 0; g < VQA_MAX_GROUPS; ++g) {
       const int s = g < p->groups ? g : 0;
       a.dY.p[g] = p->dY[s]; a.Y.p[g] = p->Y[s]; a.lddy.v[g] = p->lddy[s]; a.ldy.v[g] = p->ldy[s];

@@ -11,6 +11,7 @@ namespace vqa {
 constexpr int64_t H = 310, F = 510, A = 620, AG = 155, Q = 2400, D = 2048;
 // padded row strides of intermediates that are TMA operands of the tensor-core GEMMs (16-byte multiples)
 constexpr int64_t HP = 320, XP = 512;
+constexpr int64_t FPAD = 512;   // roundup(F, 32): row padding of stacked Mutan weights
 constexpr float P_DROP = 0.5f;
 
 // ---- state_dict indices -------------------------------------------------------------------------
@@ -50,6 +51,7 @@ struct Cor2Ws {
       *dhq2, *dalpha_ext, *dpooled1, *dalpha1, *dz1, *dfuse1, *dvl, *d_f1_H2;
   float* lin_ws; size_t lin_ws_bytes;
   uint8_t *bits_v, *bits_v2;   // packed dropout keep-bits of compress_v / compress_v2 inputs (train mode)
+  float *vq1_w1p, *vq1_w2p, *vq2_w1p, *vq2_w2p, *ff_w1p, *ff_w2p, *eq1p, *eq2p, *clsp;   // vqa_pack_weights copies
   size_t bytes;
 };
 
@@ -87,6 +89,10 @@ static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N, int64_t C) {
   w.dfuse1 = c.take(M * F); w.dvl = c.take(M * HP); w.d_f1_H2 = c.take(2 * B * F);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
   w.bits_v = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16)); w.bits_v2 = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16));
+  w.vq1_w1p = c.take(2 * FPAD * 312); w.vq1_w2p = c.take(2 * FPAD * 312);
+  w.vq2_w1p = c.take(2 * FPAD * 312); w.vq2_w2p = c.take(2 * FPAD * 312);
+  w.ff_w1p = c.take(2 * FPAD * 2 * A); w.ff_w2p = c.take(2 * FPAD * 312);
+  w.eq1p = c.take(D * 312); w.eq2p = c.take(D * 312); w.clsp = c.take(C * 512);
   w.bytes = c.off;
   return w;
 }
@@ -96,6 +102,7 @@ struct OdaWs {
   float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled, *dalpha, *dz, *dwsum, *dvl, *dql;
   float* lin_ws; size_t lin_ws_bytes;
   uint8_t* bits_v;
+  float *ff_w1p, *ff_w2p, *clsp;
   size_t bytes;
 };
 
@@ -111,6 +118,7 @@ static OdaWs carve_oda(void* base, int64_t B, int64_t N, int64_t C) {
   w.dvl = c.take(M * H); w.dql = c.take(B * H);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
   w.bits_v = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16));
+  w.ff_w1p = c.take(5 * FPAD * A); w.ff_w2p = c.take(5 * FPAD * 312); w.clsp = c.take(C * 512);
   w.bytes = c.off;
   return w;
 }
@@ -123,6 +131,7 @@ struct Ctx {
   float* const* dW;           // gradient table (backward) or nullptr
   int accumulate;
   void* lin_ws; size_t lin_ws_bytes;
+  int packed;                 // padded weight copies in the workspace are valid (tensor-core math)
   float pdrop() const { return p->train ? P_DROP : 0.0f; }
   float* grad(int idx) const { return dW ? dW[idx] : nullptr; }
 };
@@ -130,14 +139,15 @@ struct Ctx {
 // single or grouped linear forward; weight index widx[g] (bias = widx[g]+1)
 static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
                    const int64_t* ldx, const int* widx, float* const* Y, const int64_t* ldy, const uint32_t* layer,
-                   const uint8_t* bits = nullptr) {
+                   const uint8_t* bits = nullptr, const float* const* Wp = nullptr) {
   vqa_linear_fwd_params lp = {};
   lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
-  lp.p = c.pdrop(); lp.seed = c.p->seed;
+  lp.p = c.pdrop(); lp.seed = c.p->seed; lp.seed_dev = c.p->seed_dev;
   for (int g = 0; g < groups; ++g) {
     lp.X[g] = X[g]; lp.ldx[g] = ldx[g]; lp.W[g] = c.W[widx[g]]; lp.b[g] = c.W[widx[g] + 1];
     lp.Y[g] = Y[g]; lp.ldy[g] = ldy[g]; lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
     lp.drop_bits[g] = (c.p->train && groups == 1) ? bits : nullptr;
+    lp.Wp[g] = (Wp && c.packed) ? Wp[g] : nullptr;
   }
   lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
   return vqa_linear_fwd(&lp, c.stream);
@@ -146,10 +156,10 @@ static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
 static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
                    const int64_t* ldx, const int* widx, const float* const* Y, const int64_t* ldy,
                    const float* const* dY, const int64_t* lddy, float* const* dX, const int64_t* lddx, int accumulate_x,
-                   const uint32_t* layer, const uint8_t* bits = nullptr) {
+                   const uint32_t* layer, const uint8_t* bits = nullptr, const float* const* Wp = nullptr) {
   vqa_linear_bwd_params lp = {};
   lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
-  lp.p = c.pdrop(); lp.seed = c.p->seed; lp.accumulate_w = c.accumulate; lp.accumulate_x = accumulate_x;
+  lp.p = c.pdrop(); lp.seed = c.p->seed; lp.seed_dev = c.p->seed_dev; lp.accumulate_w = c.accumulate; lp.accumulate_x = accumulate_x;
   for (int g = 0; g < groups; ++g) {
     lp.X[g] = X[g]; lp.ldx[g] = ldx[g]; lp.W[g] = c.W[widx[g]];
     lp.Y[g] = Y[g]; lp.ldy[g] = ldy[g]; lp.dY[g] = dY[g]; lp.lddy[g] = lddy[g];
@@ -157,6 +167,7 @@ static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
     lp.dX[g] = dX ? dX[g] : nullptr; lp.lddx[g] = lddx ? lddx[g] : 0;
     lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
     lp.drop_bits[g] = (c.p->train && groups == 1) ? bits : nullptr;
+    lp.Wp[g] = (Wp && c.packed) ? Wp[g] : nullptr;
   }
   lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
   return vqa_linear_bwd(&lp, c.stream);
@@ -164,7 +175,7 @@ static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
 
 static int mutan_fwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int64_t rows_per, const float* X1,
                      int64_t ldx1, const float* X2, int64_t ldx2, int l1, int l2, float* H1, float* H2, float* Y,
-                     int64_t ldy) {
+                     int64_t ldy, const float* W1p = nullptr, const float* W2p = nullptr) {
   vqa_mutan_fwd_params mp = {};
   mp.R = R; mp.M = M; mp.K1 = K1; mp.K2 = K2; mp.F = F; mp.rows_per_h2 = rows_per; mp.math = c.p->math;
   mp.X1 = X1; mp.ldx1 = ldx1; mp.X2 = X2; mp.ldx2 = ldx2;
@@ -173,6 +184,7 @@ static int mutan_fwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int
     mp.W2[r] = c.W[l2 + 2 * r]; mp.b2[r] = c.W[l2 + 2 * r + 1];
   }
   mp.H1 = H1; mp.H2 = H2; mp.Y = Y; mp.ldy = ldy;
+  if (c.packed) { mp.W1p = W1p; mp.W2p = W2p; }
   mp.workspace = c.lin_ws; mp.workspace_bytes = c.lin_ws_bytes;
   return vqa_mutan_fwd(&mp, c.stream);
 }
@@ -180,7 +192,7 @@ static int mutan_fwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int
 static int mutan_bwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int64_t rows_per, const float* X1,
                      int64_t ldx1, const float* X2, int64_t ldx2, int l1, int l2, const float* H1, const float* H2,
                      const float* dY, int64_t lddy, float* dH2, float* dX1, int64_t lddx1, float* dX2, int64_t lddx2,
-                     int accumulate_x2) {
+                     int accumulate_x2, const float* W1p = nullptr, const float* W2p = nullptr) {
   vqa_mutan_bwd_params mp = {};
   mp.R = R; mp.M = M; mp.K1 = K1; mp.K2 = K2; mp.F = F; mp.rows_per_h2 = rows_per; mp.math = c.p->math;
   mp.accumulate_w = c.accumulate; mp.accumulate_x1 = 0; mp.accumulate_x2 = accumulate_x2;
@@ -192,9 +204,23 @@ static int mutan_bwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int
   }
   mp.H1 = H1; mp.H2 = H2; mp.dY = dY; mp.lddy = lddy; mp.dH2 = dH2;
   mp.dX1 = dX1; mp.lddx1 = lddx1; mp.dX2 = dX2; mp.lddx2 = lddx2;
+  if (c.packed) { mp.W1p = W1p; mp.W2p = W2p; }
   mp.workspace = c.lin_ws; mp.workspace_bytes = c.lin_ws_bytes;
   return vqa_mutan_bwd(&mp, c.stream);
 }
+
+struct PackList {
+  vqa_pack_segment s[VQA_MAX_PACK_SEGMENTS];
+  int n = 0;
+  void add(const float* src, float* dst, int64_t rows, int64_t rows_pad, int64_t K) {
+    s[n].src = src; s[n].dst = dst; s[n].rows = rows; s[n].rows_pad = rows_pad; s[n].K = K; ++n;
+  }
+  // the R matrices of one Mutan side, stacked with FPAD rows each
+  void add_mutan(const float* const* W, int l, int R, float* dst, int64_t K) {
+    const int64_t Kp = (K + 3) / 4 * 4;
+    for (int r = 0; r < R; ++r) add(W[l + 2 * r], dst + (int64_t)r * FPAD * Kp, F, FPAD, K);
+  }
+};
 
 // MyATT glimpse linears: pooled[B,G,D] -> vf[:, col0 + g*155 ...]
 static int glimpse_fwd(const Ctx& c, int64_t B, const float* pooled, int w0, float* vf, int64_t ldvf, int64_t col0,
@@ -278,11 +304,22 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   using namespace cor2;
   const int64_t B = p->B, N = p->N, M = B * N;
   Cor2Ws w = carve_cor2(p->workspace, B, N, p->C);
-  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes};
+  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  const float* eqp[2] = {w.eq1p, w.eq2p}; const float* clp[1] = {w.clsp}; (void)eqp; (void)clp;
+  if (c.packed) {  // every weight whose rows TMA cannot address, packed once for this step's forward AND backward
+    ProfScope ps_(stream, "pack_weights");
+    PackList pl;
+    pl.add_mutan(c.W, VQ1_L1, 2, w.vq1_w1p, H); pl.add_mutan(c.W, VQ1_L2, 2, w.vq1_w2p, H);
+    pl.add_mutan(c.W, VQ2_L1, 2, w.vq2_w1p, H); pl.add_mutan(c.W, VQ2_L2, 2, w.vq2_w2p, H);
+    pl.add_mutan(c.W, FF_L1, 2, w.ff_w1p, 2 * A); pl.add_mutan(c.W, FF_L2, 2, w.ff_w2p, H);
+    pl.add(c.W[EQ1], w.eq1p, D, D, H); pl.add(c.W[EQ2], w.eq2p, D, D, H);
+    pl.add(c.W[CLASSIF], w.clsp, p->C, p->C, F);
+    VQA_TRY(vqa_pack_weights(pl.s, pl.n, stream));
+  }
   if (p->train) {  // keep-bits of the two big dropout sites, shared by their fwd GEMM, wgrad GEMM and dgrad epilogue
     ProfScope ps_(stream, "dropout_bits");
-    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
-    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, L_COMPRESS_V2, (uint64_t)M * D, w.bits_v2, stream));
+    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
+    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V2, (uint64_t)M * D, w.bits_v2, stream));
   }
   {  // four 2400->310 question projections in one launch (config/CoR2.py:211,195,196,228)
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
@@ -293,18 +330,18 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // gates g1, g2 = sigmoid(310->2048) (config/CoR2.py:195-196)
     const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {HP, HP}; int widx[2] = {EQ1, EQ2};
     float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; uint32_t layer[2] = {L_EQ1, L_EQ2};
-    { ProfScope ps_(stream, "gates.fwd"); VQA_TRY(lin_fwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(stream, "gates.fwd"); VQA_TRY(lin_fwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer, nullptr, eqp)); }
   }
   {  // compress_v (config/CoR2.py:213)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
     { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, w.bits_v)); }
   }
-  { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1, F)); }   // fusion_vq1 :214
+  { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1, F, w.vq1_w1p, w.vq1_w2p)); }   // fusion_vq1 :214
   {  // att1 on raw v (:214)
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
-    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
     ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.bc = c.W[ATT1_CONV + 1]; ap.x = p->v;
     ap.alpha = p->alpha1; ap.pooled = w.pooled1;
     { ProfScope ps_(stream, "att1.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
@@ -321,21 +358,21 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V2};
     { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, w.bits_v2)); }
   }
-  { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2, F)); }  // fusion_vq2 :219
+  { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2, F, w.vq2_w1p, w.vq2_w2p)); }  // fusion_vq2 :219
   {  // att2 on v2 (:219)
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
-    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.bc = c.W[ATT2_CONV + 1]; ap.x = p->v2;
     ap.alpha = p->alpha2; ap.pooled = w.pooled2;
     { ProfScope ps_(stream, "att2.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
   }
   { ProfScope ps_(stream, "att2.glimpse.fwd"); VQA_TRY(glimpse_fwd(c, B, w.pooled2, ATT2_G, w.vf, 2 * A, A, L_ATT2_G)); }
-  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 2, B, 2 * A, H, 1, w.vf, 2 * A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf, XP)); }    // fusion_final :233
+  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 2, B, 2 * A, H, 1, w.vf, 2 * A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf, XP, w.ff_w1p, w.ff_w2p)); }    // fusion_final :233
   {  // linear_classif (:236)
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
-    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer, nullptr, clp)); }
   }
   return VQA_OK;
 }
@@ -348,27 +385,28 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
   using namespace cor2;
   const int64_t B = p->B, N = p->N, M = B * N;
   Cor2Ws w = carve_cor2(p->workspace, B, N, p->C);
-  Ctx c{p, stream, p->params, bp->grads, bp->accumulate, w.lin_ws, w.lin_ws_bytes};
+  Ctx c{p, stream, p->params, bp->grads, bp->accumulate, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  const float* eqp[2] = {w.eq1p, w.eq2p}; const float* clp[1] = {w.clsp}; (void)eqp; (void)clp;
   {  // linear_classif
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
     float* dX[1] = {w.dxf}; int64_t lddx[1] = {XP}; uint32_t layer[1] = {L_CLASSIF};
-    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer)); }
+    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, clp)); }
   }
-  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 2, B, 2 * A, H, 1, w.vf, 2 * A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, XP, w.d_ff_H2, w.dvf, 2 * A, w.dqf, HP, 0)); }
+  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 2, B, 2 * A, H, 1, w.vf, 2 * A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, XP, w.d_ff_H2, w.dvf, 2 * A, w.dqf, HP, 0, w.ff_w1p, w.ff_w2p)); }
   // ---- att2 branch
   { ProfScope ps_(stream, "att2.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled2, ATT2_G, w.vf, w.dvf, 2 * A, A, w.dpooled2, L_ATT2_G)); }
   {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
-    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
     ap.accumulate_w = bp->accumulate; ap.accumulate_x = 0;
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.x = p->v2; ap.alpha = p->alpha2; ap.dpooled = w.dpooled2;
     ap.dalpha0_ext = nullptr; ap.dalpha = w.dalpha2; ap.dz = w.dz2;
     ap.dWc = c.grad(ATT2_CONV); ap.dbc = c.grad(ATT2_CONV + 1); ap.dfuse = w.dfuse2; ap.dx = w.dv2;
     { ProfScope ps_(stream, "att2.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
-  { ProfScope ps_(stream, "fusion_vq2.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, F, w.d_f2_H2, w.dv2l, HP, w.dql, HP, 0)); }
+  { ProfScope ps_(stream, "fusion_vq2.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, F, w.d_f2_H2, w.dv2l, HP, w.dql, HP, 0, w.vq2_w1p, w.vq2_w2p)); }
   {  // compress_v2: dgrad accumulates into dv2 (v2 feeds both compress_v2 and att2's pooling)
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; const float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {HP};
@@ -388,19 +426,19 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     const float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; const float* dY[2] = {w.dg1, w.dg2};
     int64_t lddy[2] = {D, D}; float* dX[2] = {w.dhq1, w.dhq2}; int64_t lddx[2] = {HP, HP};
     uint32_t layer[2] = {L_EQ1, L_EQ2};
-    { ProfScope ps_(stream, "gates.bwd"); VQA_TRY(lin_bwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer)); }
+    { ProfScope ps_(stream, "gates.bwd"); VQA_TRY(lin_bwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, eqp)); }
   }
   {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
-    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
     ap.accumulate_w = bp->accumulate; ap.accumulate_x = 0;
     ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.dpooled = w.dpooled1;
     ap.dalpha0_ext = w.dalpha_ext; ap.dalpha = w.dalpha1; ap.dz = w.dz1;
     ap.dWc = c.grad(ATT1_CONV); ap.dbc = c.grad(ATT1_CONV + 1); ap.dfuse = w.dfuse1; ap.dx = nullptr;
     { ProfScope ps_(stream, "att1.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
-  { ProfScope ps_(stream, "fusion_vq1.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, F, w.d_f1_H2, w.dvl, HP, w.dql, HP, 1)); }
+  { ProfScope ps_(stream, "fusion_vq1.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, F, w.d_f1_H2, w.dvl, HP, w.dql, HP, 1, w.vq1_w1p, w.vq1_w2p)); }
   {  // compress_v: v is a graph input, no dgrad
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
@@ -426,10 +464,18 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   using namespace oda;
   const int64_t B = p->B, N = p->N, M = B * N;
   OdaWs w = carve_oda(p->workspace, B, N, p->C);
-  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes};
+  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  const float* clp[1] = {w.clsp}; (void)clp;
+  if (c.packed) {
+    ProfScope ps_(stream, "pack_weights");
+    PackList pl;
+    pl.add_mutan(c.W, FF_L1, 5, w.ff_w1p, A); pl.add_mutan(c.W, FF_L2, 5, w.ff_w2p, H);
+    pl.add(c.W[CLASSIF], w.clsp, p->C, p->C, F);
+    VQA_TRY(vqa_pack_weights(pl.s, pl.n, stream));
+  }
   if (p->train) {
     ProfScope ps_(stream, "dropout_bits");
-    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
+    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
   }
   {  // compress_v (config/ODA.py:211)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
@@ -444,17 +490,17 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // pairwise differences + conv_att + softmax + pooling (:216-226)
     vqa_oda_pair_attn_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.H = H; ap.D = D; ap.train = p->train;
-    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT_CONV; ap.drop.seed = p->seed;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
     ap.vl = w.vl; ap.ql = w.ql; ap.W = c.W[ATT_CONV]; ap.bc = c.W[ATT_CONV + 1]; ap.x = p->v; ap.wsum = w.wsum;
     ap.alpha = p->alpha1; ap.pooled = w.pooled;
     { ProfScope ps_(stream, "oda_pair_attn.fwd"); VQA_TRY(vqa_oda_pair_attn_fwd(&ap, stream)); }
   }
   { ProfScope ps_(stream, "att.glimpse.fwd"); VQA_TRY(glimpse_fwd(c, B, w.pooled, ATT_G, w.vf, A, 0, L_ATT_G)); }
-  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 5, B, A, H, 1, w.vf, A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf, XP)); }       // fusion_final :236
+  { ProfScope ps_(stream, "fusion_final.fwd"); VQA_TRY(mutan_fwd(c, 5, B, A, H, 1, w.vf, A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.xf, XP, w.ff_w1p, w.ff_w2p)); }       // fusion_final :236
   {  // linear_classif (:239)
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
-    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer, nullptr, clp)); }
   }
   return VQA_OK;
 }
@@ -467,19 +513,20 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
   using namespace oda;
   const int64_t B = p->B, N = p->N, M = B * N;
   OdaWs w = carve_oda(p->workspace, B, N, p->C);
-  Ctx c{p, stream, p->params, bp->grads, bp->accumulate, w.lin_ws, w.lin_ws_bytes};
+  Ctx c{p, stream, p->params, bp->grads, bp->accumulate, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  const float* clp[1] = {w.clsp}; (void)clp;
   {
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
     float* dX[1] = {w.dxf}; int64_t lddx[1] = {XP}; uint32_t layer[1] = {L_CLASSIF};
-    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer)); }
+    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, clp)); }
   }
-  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 5, B, A, H, 1, w.vf, A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, XP, w.d_ff_H2, w.dvf, A, w.dqf, HP, 0)); }
+  { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 5, B, A, H, 1, w.vf, A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, XP, w.d_ff_H2, w.dvf, A, w.dqf, HP, 0, w.ff_w1p, w.ff_w2p)); }
   { ProfScope ps_(stream, "att.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled, ATT_G, w.vf, w.dvf, A, 0, w.dpooled, L_ATT_G)); }
   {
     vqa_oda_pair_attn_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.H = H; ap.D = D; ap.train = p->train;
-    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT_CONV; ap.drop.seed = p->seed;
+    ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
     ap.accumulate_w = bp->accumulate;
     ap.vl = w.vl; ap.ql = w.ql; ap.W = c.W[ATT_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.wsum = w.wsum;
     ap.dpooled = w.dpooled; ap.dalpha = w.dalpha; ap.dz = w.dz; ap.dwsum = w.dwsum;

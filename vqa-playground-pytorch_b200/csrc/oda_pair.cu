@@ -53,7 +53,7 @@ oda_pair_logits_train_kernel(int64_t N, int64_t H, Drop d, const float* __restri
   float acc[G] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t t = threadIdx.x; t < NH / 4; t += ODA_THREADS) {
     const int64_t e0 = t * 4;
-    const uint32_t bt = philox_bytes4(d.seed, d.layer, base + (uint64_t)e0);
+    const uint32_t bt = philox_bytes4(d.key(), d.layer, base + (uint64_t)e0);
     const uint32_t wd[4] = {bt & 0xFFu, (bt >> 8) & 0xFFu, (bt >> 16) & 0xFFu, bt >> 24};
     int64_t j = e0 / H, k = e0 - j * H;
 #pragma unroll
@@ -127,7 +127,7 @@ __global__ void oda_pair_bwd_train_dv_kernel(int64_t N, int64_t H, Drop d, const
       float colj = 0.0f;
       for (int64_t i = 0; i < N; ++i) {
         const uint64_t idx = (uint64_t)((b * N + i) * NH + j * H + k);
-        if (philox_byte(d.seed, d.layer, d.base + idx) >= d.thr) {
+        if (philox_byte(d.key(), d.layer, d.base + idx) >= d.thr) {
           const float* zz = dz_s + i * G;
           const float u = (zz[0] * w[0] + zz[1] * w[1] + zz[2] * w[2] + zz[3] * w[3]) * d.scale;
           colj -= u;
@@ -175,7 +175,7 @@ oda_pair_bwd_train_dw_kernel(int64_t B, int64_t N, int64_t H, Drop d, const floa
     for (int u = 0; u < 4; ++u) { qv[u] = ql[b * H + kk[u]]; vj[u] = vb[jj[u] * H + kk[u]]; }
     for (int64_t i = 0; i < N; ++i) {
       const uint64_t idx = d.base + (uint64_t)((b * N + i) * NH + e0);
-      const uint32_t bt = philox_bytes4(d.seed, d.layer, idx);
+      const uint32_t bt = philox_bytes4(d.key(), d.layer, idx);
       const uint32_t wd[4] = {bt & 0xFFu, (bt >> 8) & 0xFFu, (bt >> 16) & 0xFFu, bt >> 24};
       const float4 z4 = *reinterpret_cast<const float4*>(&dz[(b * N + i) * G]);
 #pragma unroll
@@ -224,7 +224,7 @@ extern "C" int vqa_oda_pair_attn_fwd(const vqa_oda_pair_attn_fwd_params* p, void
                                                                                      p->alpha);
     VQA_TRY(check_launch("oda_logits_eval"));
   } else {
-    Drop d = make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0);
+    Drop d = make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev);
     dim3 grid((unsigned)p->N, (unsigned)p->B);
     oda_pair_logits_train_kernel<<<grid, ODA_THREADS, (size_t)2 * p->H * sizeof(float), st>>>(
         p->N, p->H, d, p->vl, p->ql, p->W, p->bc, p->alpha);
@@ -259,7 +259,7 @@ extern "C" int vqa_oda_pair_attn_bwd(const vqa_oda_pair_attn_bwd_params* p, void
     oda_dw_broadcast_kernel<<<(unsigned)cdiv(G * NH, 256), 256, 0, st>>>(p->N, p->H, p->dwsum, p->dW, p->accumulate_w);
     return check_launch("oda_dw_broadcast");
   }
-  Drop d = make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0);
+  Drop d = make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev);
   softmax_regions_bwd_kernel<<<(unsigned)p->B, 128, 0, st>>>(p->N, p->alpha, p->dalpha, p->dz, p->dbc);
   VQA_TRY(check_launch("softmax_regions_bwd"));
   if (!p->accumulate_w) cudaMemsetAsync(p->dW, 0, (size_t)G * NH * sizeof(float), st);

@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
     const int t = threadIdx.x - 64;
     if (need_xform) {
       Drop d = p.drop;
+      d.seed = d.key();
       d.layer = p.gd.layer[g];
       d.base = p.gd.base[g];
       const uint8_t* __restrict__ bits = p.drop_bits[g];

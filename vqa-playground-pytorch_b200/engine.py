@@ -1,0 +1,138 @@
+"""Step-level host logic around the core: the reference's train step (train.py:41-107) restated for the
+one-process-per-GPU engine, and a pinned-memory input prefetcher that overlaps host->device copies of the
+next batch with the current step (at >1e5 samples/s the reference's per-item Python loader and
+synchronous `.cuda()` copies would starve the GPU).
+"""
+import torch
+
+from . import ops
+
+
+def kld_loss(logits, target):
+    """KLDivLoss(size_average=False)(log_softmax(x), a) — train.py:536-544 — through the fused kernel."""
+    return ops.kld_loss_rows(logits, target).sum()
+
+
+def train_step(model, sample, optimizer=None, scheduler=None, engine=None, clip_grad=None):
+    """One iteration of train.py:63-86: forward, KLD loss, (scheduler.step — the reference steps it BEFORE the
+    optimizer, :75-76), backward, gradient all-reduce, optional clip_grad_norm_(0.25) (:82), optimizer step."""
+    output = model(sample)
+    loss = kld_loss(output, sample['a'])
+    if scheduler is not None:
+        scheduler.step()
+    if optimizer is not None and (engine is None):
+        optimizer.zero_grad()
+    loss.backward()
+    if engine is not None:
+        engine.wait()
+    if clip_grad:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), clip_grad)
+    if optimizer is not None:
+        optimizer.step()
+    return output, loss
+
+
+class HostPrefetcher:
+    """Iterates over host batches (dicts of PINNED tensors) yielding device dicts; the copy of batch i+1 runs
+    on a side stream while batch i is being computed.  Two device staging slots, reused."""
+
+    def __init__(self, host_batches, device, keys=("v", "q_idxes", "a")):
+        self.batches = host_batches
+        self.device = torch.device(device)
+        self.keys = keys
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.bytes_per_batch = 0
+
+    def _issue(self, i, slot):
+        host = self.batches[i]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])        # previous user of the slot has finished
+            if self.slots[slot] is None:
+                self.slots[slot] = {k: torch.empty_like(host[k], device=self.device) for k in self.keys}
+            nbytes = 0
+            for k in self.keys:
+                self.slots[slot][k].copy_(host[k], non_blocking=True)
+                nbytes += host[k].numel() * host[k].element_size()
+            self.bytes_per_batch = nbytes
+            self.ready[slot].record(self.copy_stream)
+
+    def __iter__(self):
+        n = len(self.batches)
+        if n == 0:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        for s in (0, 1):
+            self.consumed[s].record(cur)
+        self._issue(0, 0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                self._issue(i + 1, slot ^ 1)
+            cur.wait_event(self.ready[slot])
+            yield self.slots[slot]
+            self.consumed[slot].record(cur)
+
+
+class GraphedStep:
+    """fwd + KLD loss + bwd of one fixed-shape batch captured in a CUDA graph and replayed every step.
+
+    Everything the step launches (the forward plan, the loss kernel, the backward plan — ~90 kernels and memsets)
+    becomes one graph launch, which removes the per-launch CPU cost and most of the inter-kernel gaps.  The Philox
+    dropout key lives in device memory (`model.seed_device`) and is advanced by a kernel captured at the head of
+    the graph, so every replay draws a fresh mask.  With a data-parallel engine the gradient all-reduce runs
+    after the replay (engine.after_backward / wait), outside the graph.
+
+        step = GraphedStep(model, example_sample, engine)     # warms up, then captures
+        loss = step(sample)                                   # copies the sample into the static buffers, replays
+    """
+
+    def __init__(self, model, example, engine=None, warmup=3, seed=0x5EED0000):
+        dev = example["v"].device
+        self.model, self.engine = model, engine
+        self.static = {k: torch.empty_like(t) for k, t in example.items() if torch.is_tensor(t)}
+        for k, t in self.static.items():
+            t.copy_(example[k])
+        model.seed_device = torch.tensor([seed], dtype=torch.int64, device=dev)
+        if engine is not None:
+            engine.defer = True                 # no collectives inside the captured region
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.lib().vqa_launch_count()
+        # capture on the SAME side stream the warm-up ran on: autograd caches each parameter's gradient-accumulator
+        # stream at first use, and a capture that has to wait on another (uncaptured) stream is invalid
+        with torch.cuda.graph(self.graph, stream=side):
+            self.loss = self._body()
+        self.launches_per_replay = int(_lib.lib().vqa_launch_count() - n0)    # libvqacore kernels inside the graph
+
+    def _body(self):
+        if self.model.training:
+            ops.seed_advance(self.model.seed_device)
+        out = self.model(self.static)
+        loss = kld_loss(out, self.static["a"])
+        if self.engine is None:
+            for p in self.model.parameters():
+                p.grad = None
+        loss.backward()
+        self.logits = out
+        return loss
+
+    def __call__(self, sample=None):
+        if sample is not None:
+            for k, t in self.static.items():
+                if sample[k].data_ptr() != t.data_ptr():
+                    t.copy_(sample[k], non_blocking=True)
+        self.graph.replay()
+        if self.engine is not None:
+            self.engine.reduce_all()
+            self.engine.wait()
+        return self.loss

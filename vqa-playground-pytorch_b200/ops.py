@@ -112,10 +112,15 @@ def linear_backward(xs, ws, ys, dys, act, p, seed, layers, need_dx, math=0, dws=
     return dws, dbs, dxs
 
 
+def seed_advance(seed_dev):
+    """*seed_dev += 1 on the current stream (captured at the head of a graphed step)."""
+    _lib.check(_lib.lib().vqa_seed_advance(seed_dev.data_ptr(), _stream()), "vqa_seed_advance")
+
+
 def dropout_bits(p, seed, layer, n, device):
     """Packed keep-bits of n elements (vqa_dropout_bits)."""
     out = torch.empty(((n + 15) // 16 * 2,), device=device, dtype=torch.uint8)
-    _lib.check(_lib.lib().vqa_dropout_bits(float(p), int(seed), int(layer), int(n), out.data_ptr(), _stream()),
+    _lib.check(_lib.lib().vqa_dropout_bits(float(p), int(seed), None, int(layer), int(n), out.data_ptr(), _stream()),
                "vqa_dropout_bits")
     return out
 
@@ -312,8 +317,9 @@ def stash_tensor(name):
     return flat.view(rows.value, ld.value)[:, :cols.value]
 
 
-def _fill_model_params(pr, B, N, Cc, train, math, seed, v, q, ptab, logits, alpha1, alpha2, v2, ws):
+def _fill_model_params(pr, B, N, Cc, train, math, seed, v, q, ptab, logits, alpha1, alpha2, v2, ws, seed_dev=None):
     pr.B, pr.N, pr.C, pr.train, pr.math, pr.seed = B, N, Cc, int(train), _math(math), int(seed)
+    pr.seed_dev = _p(seed_dev)
     pr.v, pr.q, pr.params = v.data_ptr(), q.data_ptr(), ptab
     pr.logits, pr.alpha1, pr.alpha2, pr.v2 = logits.data_ptr(), alpha1.data_ptr(), _p(alpha2), _p(v2)
     pr.workspace, pr.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -326,7 +332,7 @@ class ModelCoreFn(torch.autograd.Function):
     last_workspace = None
 
     @staticmethod
-    def forward(ctx, model, v, q, train, math, seed, num_regions, num_ans, grad_sink, *params):
+    def forward(ctx, model, v, q, train, math, seed, seed_dev, num_regions, num_ans, grad_sink, *params):
         wsb, fwd, _ = _MODEL[model]
         L = _lib.lib()
         vc = _chk(v, "sample['v']").reshape(-1, num_regions, D_DIM)
@@ -345,9 +351,9 @@ class ModelCoreFn(torch.autograd.Function):
         v2 = torch.empty((B, N, D_DIM), device=dev, dtype=torch.float32) if cor2 else None
         ptab = _ptr_table(params, len(params))
         pr = _lib.ModelFwd()
-        _fill_model_params(pr, B, N, Cc, train, math, seed, vc, qc, ptab, logits, alpha1, alpha2, v2, ws)
+        _fill_model_params(pr, B, N, Cc, train, math, seed, vc, qc, ptab, logits, alpha1, alpha2, v2, ws, seed_dev)
         _lib.check(getattr(L, fwd)(C.byref(pr), _stream()), fwd)
-        ctx.model, ctx.meta, ctx.grad_sink = model, (B, N, Cc, train, math, seed), grad_sink
+        ctx.model, ctx.meta, ctx.grad_sink = model, (B, N, Cc, train, math, seed, seed_dev), grad_sink
         ModelCoreFn.last_workspace = (model, B, N, Cc, ws)      # test introspection (vqa_stash_info)
         ctx.keep = (vc, qc, params, ws, logits, alpha1, alpha2, v2)
         if cor2:
@@ -360,7 +366,7 @@ class ModelCoreFn(torch.autograd.Function):
     def backward(ctx, dlogits, *_unused):
         _, _, bwd = _MODEL[ctx.model]
         L = _lib.lib()
-        B, N, Cc, train, math, seed = ctx.meta
+        B, N, Cc, train, math, seed, seed_dev = ctx.meta
         vc, qc, params, ws, logits, alpha1, alpha2, v2 = ctx.keep
         dlogits = dlogits.contiguous()
         sink = ctx.grad_sink
@@ -377,10 +383,10 @@ class ModelCoreFn(torch.autograd.Function):
         ptab = _ptr_table(params, len(params))
         gtab = _ptr_table(grads, len(grads))
         pr = _lib.ModelBwd()
-        _fill_model_params(pr.fwd, B, N, Cc, train, math, seed, vc, qc, ptab, logits, alpha1, alpha2, v2, ws)
+        _fill_model_params(pr.fwd, B, N, Cc, train, math, seed, vc, qc, ptab, logits, alpha1, alpha2, v2, ws, seed_dev)
         pr.dlogits, pr.grads, pr.accumulate = dlogits.data_ptr(), gtab, accumulate
         _lib.check(getattr(L, bwd)(C.byref(pr), _stream()), bwd)
         if sink is not None:
             sink.after_backward()
         ctx.keep = None
-        return (None, None, None, None, None, None, None, None, None, *ret)
+        return (None, None, None, None, None, None, None, None, None, None, *ret)

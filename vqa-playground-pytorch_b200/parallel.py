@@ -92,6 +92,7 @@ class DataParallelEngine(GradSink):
         self.is_cuda = self.flat.is_cuda
         self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.is_cuda else None
         self._pending = []
+        self.defer = False          # True: the caller triggers the reduction itself (engine.GraphedStep)
         model.grad_sink = self
 
     def broadcast_parameters(self, src=0):
@@ -113,10 +114,14 @@ class DataParallelEngine(GradSink):
         else:
             self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    def after_backward(self):
-        # called by ops.ModelCoreFn.backward right after the backward plan has been enqueued
+    def reduce_all(self):
         for k in range(len(self.bucket_ranges)):
             self.reduce_bucket(k)
+
+    def after_backward(self):
+        # called by ops.ModelCoreFn.backward right after the backward plan has been enqueued
+        if not self.defer:
+            self.reduce_all()
 
     def wait(self):
         for w in self._pending:

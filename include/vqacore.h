@@ -392,6 +392,10 @@ typedef struct {
   const float* dlogits;      /* [B,C] */
   float* const* grads;       /* table of gradient pointers, state_dict order */
   int accumulate;            /* 1: grads += , 0: grads = */
+  float* grads_flat;         /* optional: one buffer that contains every gradient tensor (e.g. the data-parallel
+                                flat buffer); with accumulate == 0 the plan zero-fills it ONCE and lets every
+                                kernel accumulate, instead of one memset per tensor */
+  size_t grads_flat_bytes;
 } vqa_model_bwd_params;
 
 size_t vqa_cor2_workspace_bytes(int64_t B, int64_t N, int64_t C);

@@ -114,7 +114,8 @@ class ModelFwd(C.Structure):
 
 
 class ModelBwd(C.Structure):
-    _fields_ = [("fwd", ModelFwd), ("dlogits", fp), ("grads", C.POINTER(fp)), ("accumulate", C.c_int)]
+    _fields_ = [("fwd", ModelFwd), ("dlogits", fp), ("grads", C.POINTER(fp)), ("accumulate", C.c_int),
+                ("grads_flat", fp), ("grads_flat_bytes", C.c_size_t)]
 
 
 STRUCTS = {

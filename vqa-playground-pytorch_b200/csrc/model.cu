@@ -44,12 +44,44 @@ struct Carver {
   }
 };
 
+// ---- internal fork/join lanes -----------------------------------------------------------------------
+// A plan may run branches that do not depend on each other (the question-side projections vs the region-side
+// GEMMs; in the backward the att1 glimpse linears, the gates and the question projections vs the critical dgrad
+// chain) on a library-owned side stream.  Every branch forks from and joins back into the CALLER's stream with
+// events before the plan returns, so the external contract (all work ordered on the caller's stream, capturable
+// in a CUDA graph — the side stream simply becomes a parallel branch of the graph) is unchanged.
+struct Lanes {
+  int dev = -1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev[32];
+  int next = 0;
+  cudaEvent_t record(cudaStream_t s) {
+    cudaEvent_t e = ev[next++ & 31];
+    cudaEventRecord(e, s);
+    return e;
+  }
+  static void wait(cudaStream_t s, cudaEvent_t e) { cudaStreamWaitEvent(s, e, 0); }
+};
+static Lanes* get_lanes() {
+  static thread_local Lanes L;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (L.dev != dev) {
+    if (cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 32; ++i)
+      if (cudaEventCreateWithFlags(&L.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    L.dev = dev;
+  }
+  return &L;
+}
+
 struct Cor2Ws {
   float *ql, *hq1, *hq2, *qf, *g1, *g2, *vl, *f1_H1, *f1_H2, *fuse1, *pooled1, *vf, *v2l, *f2_H1, *f2_H2, *fuse2,
       *pooled2, *ff_H1, *ff_H2, *xf;
   float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled2, *dalpha2, *dz2, *dfuse2, *dv2, *dv2l, *d_f2_H2, *dql, *dg1, *dg2, *dhq1,
       *dhq2, *dalpha_ext, *dpooled1, *dalpha1, *dz1, *dfuse1, *dvl, *d_f1_H2;
   float* lin_ws; size_t lin_ws_bytes;
+  float* side_ws; size_t side_ws_bytes;   // scratch of the ops that run on the side lane
   uint8_t *bits_v, *bits_v2;   // packed dropout keep-bits of compress_v / compress_v2 inputs (train mode)
   float *vq1_w1p, *vq1_w2p, *vq2_w1p, *vq2_w2p, *ff_w1p, *ff_w2p, *eq1p, *eq2p, *clsp;   // vqa_pack_weights copies
   size_t bytes;
@@ -88,6 +120,7 @@ static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N, int64_t C) {
   w.dpooled1 = c.take(B * G * D); w.dalpha1 = c.take(M * G); w.dz1 = c.take(M * G);
   w.dfuse1 = c.take(M * F); w.dvl = c.take(M * HP); w.d_f1_H2 = c.take(2 * B * F);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
+  w.side_ws_bytes = (size_t)(8 * B * 2048 + 65536) * sizeof(float); w.side_ws = c.take(8 * B * 2048 + 65536);
   w.bits_v = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16)); w.bits_v2 = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16));
   w.vq1_w1p = c.take(2 * FPAD * 312); w.vq1_w2p = c.take(2 * FPAD * 312);
   w.vq2_w1p = c.take(2 * FPAD * 312); w.vq2_w2p = c.take(2 * FPAD * 312);
@@ -101,6 +134,7 @@ struct OdaWs {
   float *vl, *ql, *qf, *wsum, *pooled, *vf, *ff_H1, *ff_H2, *xf;
   float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled, *dalpha, *dz, *dwsum, *dvl, *dql;
   float* lin_ws; size_t lin_ws_bytes;
+  float* side_ws; size_t side_ws_bytes;
   uint8_t* bits_v;
   float *ff_w1p, *ff_w2p, *clsp;
   size_t bytes;
@@ -117,6 +151,7 @@ static OdaWs carve_oda(void* base, int64_t B, int64_t N, int64_t C) {
   w.dpooled = c.take(B * G * D); w.dalpha = c.take(M * G); w.dz = c.take(M * G); w.dwsum = c.take(G * H);
   w.dvl = c.take(M * H); w.dql = c.take(B * H);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
+  w.side_ws_bytes = (size_t)(8 * B * 2048 + 65536) * sizeof(float); w.side_ws = c.take(8 * B * 2048 + 65536);
   w.bits_v = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16));
   w.ff_w1p = c.take(5 * FPAD * A); w.ff_w2p = c.take(5 * FPAD * 312); w.clsp = c.take(C * 512);
   w.bytes = c.off;
@@ -316,6 +351,13 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     pl.add(c.W[CLASSIF], w.clsp, p->C, p->C, F);
     VQA_TRY(vqa_pack_weights(pl.s, pl.n, stream));
   }
+  // fork: the question-side chain (four projections -> gates) runs on the side lane while the region side starts
+  Lanes* L = get_lanes();
+  VQA_REQUIRE(L != nullptr, "vqa_cor2_fwd: cannot create the internal side stream");
+  cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
+  Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
+  Lanes::wait(ss, L->record(ms));
+  cudaEvent_t e_ql, e_gates;
   if (p->train) {  // keep-bits of the two big dropout sites, shared by their fwd GEMM, wgrad GEMM and dgrad epilogue
     ProfScope ps_(stream, "dropout_bits");
     VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
@@ -325,18 +367,21 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
     int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
     int64_t ldy[4] = {HP, HP, HP, HP}; uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
-    { ProfScope ps_(stream, "q_proj4.fwd"); VQA_TRY(lin_fwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(ss, "q_proj4.fwd"); VQA_TRY(lin_fwd(cs, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    e_ql = L->record(ss);
   }
   {  // gates g1, g2 = sigmoid(310->2048) (config/CoR2.py:195-196)
     const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {HP, HP}; int widx[2] = {EQ1, EQ2};
     float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; uint32_t layer[2] = {L_EQ1, L_EQ2};
-    { ProfScope ps_(stream, "gates.fwd"); VQA_TRY(lin_fwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer, nullptr, eqp)); }
+    { ProfScope ps_(ss, "gates.fwd"); VQA_TRY(lin_fwd(cs, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer, nullptr, eqp)); }
+    e_gates = L->record(ss);
   }
   {  // compress_v (config/CoR2.py:213)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
     { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, w.bits_v)); }
   }
+  Lanes::wait(ms, e_ql);      // ql / qf ready
   { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1, F, w.vq1_w1p, w.vq1_w2p)); }   // fusion_vq1 :214
   {  // att1 on raw v (:214)
     vqa_region_softmax_pool_fwd_params ap = {};
@@ -347,6 +392,7 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     { ProfScope ps_(stream, "att1.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
   }
   { ProfScope ps_(stream, "att1.glimpse.fwd"); VQA_TRY(glimpse_fwd(c, B, w.pooled1, ATT1_G, w.vf, 2 * A, 0, L_ATT1_G)); }
+  Lanes::wait(ms, e_gates);   // join: g1, g2 ready (last work of the side lane)
   {  // compound objects (:215-216)
     vqa_cor_compound_fwd_params cp = {};
     cp.B = B; cp.N = N; cp.D = D; cp.x = p->v; cp.pooled = w.pooled1; cp.alpha = p->alpha1; cp.g1 = w.g1; cp.g2 = w.g2;
@@ -385,8 +431,19 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
   using namespace cor2;
   const int64_t B = p->B, N = p->N, M = B * N;
   Cor2Ws w = carve_cor2(p->workspace, B, N, p->C);
-  Ctx c{p, stream, p->params, bp->grads, bp->accumulate, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  int acc = bp->accumulate;
+  if (!acc && bp->grads_flat && bp->grads_flat_bytes) {   // one zero-fill for every gradient tensor, then everything accumulates
+    cudaMemsetAsync(bp->grads_flat, 0, bp->grads_flat_bytes, (cudaStream_t)stream);
+    acc = 1;
+  }
+  Ctx c{p, stream, p->params, bp->grads, acc, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
   const float* eqp[2] = {w.eq1p, w.eq2p}; const float* clp[1] = {w.clsp}; (void)eqp; (void)clp;
+  // Side lane: att1's glimpse linears, the gates and the question projections are off the critical dgrad chain
+  // (classif -> fusion_final -> att2 -> fusion_vq2 -> compress_v2 -> compound -> att1 -> fusion_vq1 -> compress_v).
+  Lanes* L = get_lanes();
+  VQA_REQUIRE(L != nullptr, "vqa_cor2_bwd: cannot create the internal side stream");
+  cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
+  Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
   {  // linear_classif
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
@@ -394,13 +451,17 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, clp)); }
   }
   { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 2, B, 2 * A, H, 1, w.vf, 2 * A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, XP, w.d_ff_H2, w.dvf, 2 * A, w.dqf, HP, 0, w.ff_w1p, w.ff_w2p)); }
+  const cudaEvent_t e_ff = L->record(ms);          // dvf, dqf ready
+  Lanes::wait(ss, e_ff);
+  { ProfScope ps_(ss, "att1.glimpse.bwd"); VQA_TRY(glimpse_bwd(cs, B, w.pooled1, ATT1_G, w.vf, w.dvf, 2 * A, 0, w.dpooled1, L_ATT1_G)); }
+  const cudaEvent_t e_g1 = L->record(ss);          // dpooled1 initialised
   // ---- att2 branch
   { ProfScope ps_(stream, "att2.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled2, ATT2_G, w.vf, w.dvf, 2 * A, A, w.dpooled2, L_ATT2_G)); }
   {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
-    ap.accumulate_w = bp->accumulate; ap.accumulate_x = 0;
+    ap.accumulate_w = acc; ap.accumulate_x = 0;
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.x = p->v2; ap.alpha = p->alpha2; ap.dpooled = w.dpooled2;
     ap.dalpha0_ext = nullptr; ap.dalpha = w.dalpha2; ap.dz = w.dz2;
     ap.dWc = c.grad(ATT2_CONV); ap.dbc = c.grad(ATT2_CONV + 1); ap.dfuse = w.dfuse2; ap.dx = w.dv2;
@@ -413,8 +474,8 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     float* dX[1] = {w.dv2}; int64_t lddx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V2};
     { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 1, layer, w.bits_v2)); }
   }
-  // ---- att1 branch: glimpse linears first (they initialise dpooled1), then the compound objects add to it
-  { ProfScope ps_(stream, "att1.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled1, ATT1_G, w.vf, w.dvf, 2 * A, 0, w.dpooled1, L_ATT1_G)); }
+  // ---- att1 branch: the glimpse linears (side lane) initialise dpooled1, then the compound objects add to it
+  Lanes::wait(ms, e_g1);
   {
     vqa_cor_compound_bwd_params cp = {};
     cp.B = B; cp.N = N; cp.D = D; cp.x = p->v; cp.pooled = w.pooled1; cp.alpha = p->alpha1; cp.g1 = w.g1; cp.g2 = w.g2;
@@ -426,19 +487,21 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     const float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; const float* dY[2] = {w.dg1, w.dg2};
     int64_t lddy[2] = {D, D}; float* dX[2] = {w.dhq1, w.dhq2}; int64_t lddx[2] = {HP, HP};
     uint32_t layer[2] = {L_EQ1, L_EQ2};
-    { ProfScope ps_(stream, "gates.bwd"); VQA_TRY(lin_bwd(c, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, eqp)); }
+    Lanes::wait(ss, L->record(ms));                // dg1, dg2 ready
+    { ProfScope ps_(ss, "gates.bwd"); VQA_TRY(lin_bwd(cs, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, eqp)); }
   }
   {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
-    ap.accumulate_w = bp->accumulate; ap.accumulate_x = 0;
+    ap.accumulate_w = acc; ap.accumulate_x = 0;
     ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.dpooled = w.dpooled1;
     ap.dalpha0_ext = w.dalpha_ext; ap.dalpha = w.dalpha1; ap.dz = w.dz1;
     ap.dWc = c.grad(ATT1_CONV); ap.dbc = c.grad(ATT1_CONV + 1); ap.dfuse = w.dfuse1; ap.dx = nullptr;
     { ProfScope ps_(stream, "att1.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
   { ProfScope ps_(stream, "fusion_vq1.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, F, w.d_f1_H2, w.dvl, HP, w.dql, HP, 1, w.vq1_w1p, w.vq1_w2p)); }
+  Lanes::wait(ss, L->record(ms));                  // dql complete (fusion_vq2 + fusion_vq1)
   {  // compress_v: v is a graph input, no dgrad
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
@@ -449,8 +512,9 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; const float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
     int64_t ldy[4] = {HP, HP, HP, HP}; const float* dY[4] = {w.dql, w.dhq1, w.dhq2, w.dqf}; int64_t lddy[4] = {HP, HP, HP, HP};
     uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
-    { ProfScope ps_(stream, "q_proj4.bwd"); VQA_TRY(lin_bwd(c, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
+    { ProfScope ps_(ss, "q_proj4.bwd"); VQA_TRY(lin_bwd(cs, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
+  Lanes::wait(ms, L->record(ss));                  // join
   return VQA_OK;
 }
 
@@ -473,6 +537,11 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
     pl.add(c.W[CLASSIF], w.clsp, p->C, p->C, F);
     VQA_TRY(vqa_pack_weights(pl.s, pl.n, stream));
   }
+  Lanes* L = get_lanes();
+  VQA_REQUIRE(L != nullptr, "vqa_oda_fwd: cannot create the internal side stream");
+  cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
+  Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
+  Lanes::wait(ss, L->record(ms));               // fork: question projections on the side lane
   if (p->train) {
     ProfScope ps_(stream, "dropout_bits");
     VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
@@ -485,7 +554,8 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // compress_q + linear_q (:214, :233)
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
     float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, HP}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
-    { ProfScope ps_(stream, "q_proj2.fwd"); VQA_TRY(lin_fwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(ss, "q_proj2.fwd"); VQA_TRY(lin_fwd(cs, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    Lanes::wait(ms, L->record(ss));             // join
   }
   {  // pairwise differences + conv_att + softmax + pooling (:216-226)
     vqa_oda_pair_attn_fwd_params ap = {};
@@ -513,7 +583,12 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
   using namespace oda;
   const int64_t B = p->B, N = p->N, M = B * N;
   OdaWs w = carve_oda(p->workspace, B, N, p->C);
-  Ctx c{p, stream, p->params, bp->grads, bp->accumulate, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  int acc = bp->accumulate;
+  if (!acc && bp->grads_flat && bp->grads_flat_bytes) {   // one zero-fill for every gradient tensor, then everything accumulates
+    cudaMemsetAsync(bp->grads_flat, 0, bp->grads_flat_bytes, (cudaStream_t)stream);
+    acc = 1;
+  }
+  Ctx c{p, stream, p->params, bp->grads, acc, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
   const float* clp[1] = {w.clsp}; (void)clp;
   {
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
@@ -527,7 +602,7 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
     vqa_oda_pair_attn_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.H = H; ap.D = D; ap.train = p->train;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
-    ap.accumulate_w = bp->accumulate;
+    ap.accumulate_w = acc;
     ap.vl = w.vl; ap.ql = w.ql; ap.W = c.W[ATT_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.wsum = w.wsum;
     ap.dpooled = w.dpooled; ap.dalpha = w.dalpha; ap.dz = w.dz; ap.dwsum = w.dwsum;
     ap.dW = c.grad(ATT_CONV); ap.dbc = c.grad(ATT_CONV + 1); ap.dvl = w.dvl; ap.dql = w.dql;

@@ -372,7 +372,7 @@ class ModelCoreFn(torch.autograd.Function):
         sink = ctx.grad_sink
         if sink is not None:
             # data-parallel engine: gradients land directly in its flat buffer (no autograd copies)
-            grads, accumulate, ret = sink.slices, int(sink.accumulate), [None] * len(params)
+            grads, accumulate, ret, flat = sink.slices, int(sink.accumulate), [None] * len(params), sink.flat
         else:
             flat = torch.empty((sum(t.numel() for t in params),), device=dlogits.device, dtype=torch.float32)
             grads, off = [], 0
@@ -385,6 +385,7 @@ class ModelCoreFn(torch.autograd.Function):
         pr = _lib.ModelBwd()
         _fill_model_params(pr.fwd, B, N, Cc, train, math, seed, vc, qc, ptab, logits, alpha1, alpha2, v2, ws, seed_dev)
         pr.dlogits, pr.grads, pr.accumulate = dlogits.data_ptr(), gtab, accumulate
+        pr.grads_flat, pr.grads_flat_bytes = flat.data_ptr(), flat.numel() * 4
         _lib.check(getattr(L, bwd)(C.byref(pr), _stream()), bwd)
         if sink is not None:
             sink.after_backward()

@@ -7,6 +7,7 @@
 
 #include <mutex>
 
+
 #include "tc_gemm.cuh"
 
 namespace vqa {
@@ -58,10 +59,21 @@ static inline bool tma_ok(const void* ptr, int64_t ld) {
   return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (ld % 4 == 0);
 }
 
+// Thread-block clusters with TMA multicast are implemented (tc_gemm.cuh) but OFF by default: on this path they
+// measured slower (the tiles must then be fetched as 4 KB boxes and the kernel is bound by DRAM row locality of the
+// strided A tiles rather than by L2 bandwidth).  VQA_TC_CM / VQA_TC_CN >= 2 enable them for experiments.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int max_cm() { static int v = env_int("VQA_TC_CM", 1); return v; }
+static int max_cn() { static int v = env_int("VQA_TC_CN", 1); return v; }
+static bool cluster_enabled() { return max_cm() > 1 || max_cn() > 1; }
+
 // K-major operand: source is [rows(M or N), K]; MN-major operand: source is [K, rows(M or N)].
 static int operand_tmap(CUtensorMap* out, const float* ptr, bool mn_major, int64_t mn_extent, int64_t k_extent,
                         int64_t ld, int tile_mn) {
-  if (!mn_major) return make_tmap(out, ptr, mn_extent, k_extent, ld, BK, tile_mn, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!mn_major) return make_tmap(out, ptr, mn_extent, k_extent, ld, BK, cluster_enabled() ? 32 : tile_mn, CU_TENSOR_MAP_SWIZZLE_128B);
   return make_tmap(out, ptr, k_extent, mn_extent, ld, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
@@ -207,7 +219,17 @@ static int launch_cfg(const Params<Epi>& p, int groups, cudaStream_t st, const c
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
     return check_launch(what);
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(groups * p.k_splits));
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  // cluster = CM adjacent m-tiles x CN adjacent n-tiles sharing operand tiles by TMA multicast
+  unsigned cm = 1, cn = 1;
+  for (unsigned c = 4; c >= 2; c >>= 1) if ((int)c <= max_cm() && grid.x % c == 0) { cm = c; break; }
+  if (max_cn() >= 2 && grid.y % 2 == 0) cn = 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cm; attr[0].val.clusterDim.y = cn; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return check_launch(what);
   return check_launch(what);
 }
 
@@ -230,11 +252,22 @@ static int rewrite_hi_flag() {
   return v;
 }
 
-// k-splits for problems whose output tiles alone cannot fill the chip
+// k-splits for problems whose output tiles alone cannot fill the chip.  One CTA per SM is resident (shared
+// memory), so the CTA count should not spill into a mostly empty second wave: tiles * splits <= #SMs.
 static int pick_splits(int64_t tiles, int64_t K) {
   const int64_t kb = cdiv(K, BK);
-  if (tiles * 2 > (int64_t)sm_count()) return 1;
-  int64_t s = cdiv((int64_t)sm_count(), tiles);
+  const int64_t sms = sm_count();
+  if (tiles * 2 > sms) return 1;
+  int64_t s = sms / tiles;
+  if (s > kb / 4) s = kb / 4;
+  return (int)(s < 1 ? 1 : s);
+}
+
+// wgrad always reduces over the (long) row dimension: fill one wave exactly, never a partial second one
+static int pick_splits_wgrad(int64_t tiles, int64_t K) {
+  const int64_t kb = cdiv(K, BK);
+  const int64_t sms = sm_count();
+  int64_t s = tiles >= sms ? 1 : sms / tiles;
   if (s > kb / 4) s = kb / 4;
   return (int)(s < 1 ? 1 : s);
 }
@@ -242,6 +275,7 @@ static int pick_splits(int64_t tiles, int64_t K) {
 template <class Epi>
 static int launch(Params<Epi> p, int groups, bool x3, cudaStream_t st, const char* what) {
   p.rewrite_hi = rewrite_hi_flag();
+  p.box_split = cluster_enabled() ? 1 : 0;
   {
     const char* e = getenv("VQA_TC_DEBUG");
     p.debug = e ? atoi(e) : 0;
@@ -585,12 +619,7 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
     q.drop_ld = p->K; q.drop_rows = p->M;
     for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
     // split the reduction (over the M rows) so that the grid covers the chip
-    const int64_t tiles = cdiv(p->K, BM) * cdiv(p->N, bn) * p->groups;
-    const int64_t kb = cdiv(p->M, BK);
-    int64_t splits = cdiv((int64_t)sm_count(), tiles);
-    if (splits > kb / 4) splits = kb / 4;
-    if (splits < 1) splits = 1;
-    q.k_splits = (int)splits;
+    q.k_splits = pick_splits_wgrad(cdiv(p->K, BM) * cdiv(p->N, bn) * p->groups, p->M);
     if (!p->accumulate_w)
       for (int g = 0; g < p->groups; ++g)
         if (p->dW[g]) cudaMemsetAsync(p->dW[g], 0, (size_t)p->N * p->K * sizeof(float), st);
@@ -763,12 +792,7 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
     }
     q.epi.ldw = Kin;
     q.M = (int)Kin; q.N = (int)p->F; q.K = (int)Krows; q.a_mn = 1; q.b_mn = 1;
-    const int64_t tiles = cdiv(Kin, BM) * cdiv(p->F, bn) * R;
-    const int64_t kb = cdiv(Krows, BK);
-    int64_t splits = cdiv((int64_t)sm_count(), tiles);
-    if (splits > kb / 4) splits = kb / 4;
-    if (splits < 1) splits = 1;
-    q.k_splits = (int)splits;
+    q.k_splits = pick_splits_wgrad(cdiv(Kin, BM) * cdiv(p->F, bn) * R, Krows);
     return launch(q, R, x3, st, what);
   };
   auto dgrad = [&](const float* dHcat, int64_t rows, const float* Wpk, int64_t Kin, int64_t Kinp, float* dX,

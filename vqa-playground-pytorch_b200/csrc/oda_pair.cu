@@ -30,54 +30,98 @@ __global__ void oda_dw_broadcast_kernel(int64_t N, int64_t H, const float* __res
 }
 
 // ---- train mode ------------------------------------------------------------------------------
-// z[b,i,g] = bc[g] + scale * sum_{e=(j,k)} keep(b,i,e) W[g,e] (vl[b,i,k]-vl[b,j,k]) ql[b,k].
-// grid = (N, B); each thread walks aligned quads of the flat (j,k) row so one Philox call
-// yields four keep-bits.  Requires (N*H) % 4 == 0.
+// The [B,N,N*H] tensor of the reference (config/ODA.py:222) is indexed by (b, i, e) with e = j*H + k.
+// z[b,i,g] = bc[g] + scale * sum_e keep(b,i,e) W[g,e] (vl[b,i,k]-vl[b,j,k]) ql[b,k].
+//
+// "e-mapping" kernels: a thread owns EPT = 8 consecutive e of one sample — their W[g,e], vl[b,j,k], ql[b,k] stay
+// in registers — and loops over all regions i, drawing the 8 keep-bytes of (b,i,e..e+7) with one Philox call
+// (N*H is a multiple of 8, so the 8 elements never straddle a 16-element Philox group).  W is read once per
+// (sample, e) instead of once per (sample, i, e): 100x less L2 traffic at N = 100.
+constexpr int ODA_EPT = 8;
 constexpr int ODA_THREADS = 256;
+
+// keep flags (1.0 / 0.0) of 8 consecutive indices starting at idx.  Fast path idx % 8 == 0: one Philox call.
+__device__ __forceinline__ void keep8(const Drop& d, uint64_t seed, uint64_t idx, float (&keep)[8]) {
+  const uint4 r = philox_group(seed, d.layer, idx >> 4);
+  if ((idx & 7) == 0) {
+    const uint32_t lo = (idx & 8) ? r.z : r.x, hi = (idx & 8) ? r.w : r.y;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      keep[e] = ((lo >> (8 * e)) & 0xFFu) >= d.thr ? 1.0f : 0.0f;
+      keep[4 + e] = ((hi >> (8 * e)) & 0xFFu) >= d.thr ? 1.0f : 0.0f;
+    }
+    return;
+  }
+  const uint4 r1 = philox_group(seed, d.layer, (idx >> 4) + 1);     // unaligned rows (N*H not a multiple of 8)
+  const uint32_t wd[8] = {r.x, r.y, r.z, r.w, r1.x, r1.y, r1.z, r1.w};
+  const uint32_t off = (uint32_t)idx & 15u;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const uint32_t pos = off + e;
+    keep[e] = ((wd[pos >> 2] >> (8u * (pos & 3u))) & 0xFFu) >= d.thr ? 1.0f : 0.0f;
+  }
+}
+
+// grid = (cdiv(NH/8, 256), B).  z must hold bc[g] on entry (oda_init_logits_kernel); partial sums are added.
 __global__ void __launch_bounds__(ODA_THREADS)
 oda_pair_logits_train_kernel(int64_t N, int64_t H, Drop d, const float* __restrict__ vl, const float* __restrict__ ql,
-                             const float* __restrict__ W, const float* __restrict__ bc, float* __restrict__ z) {
-  extern __shared__ float sm[];
-  float* vi_s = sm;          // vl[b,i,:]
-  float* ql_s = sm + H;      // ql[b,:]
-  __shared__ float red[G][ODA_THREADS / 32];
-  const int64_t i = blockIdx.x, b = blockIdx.y;
+                             const float* __restrict__ W, float* __restrict__ z) {
+  extern __shared__ float part[];                       // [warps][N][G]
+  const int64_t b = blockIdx.y;
   const int64_t NH = N * H;
-  for (int64_t k = threadIdx.x; k < H; k += ODA_THREADS) {
-    vi_s[k] = vl[(b * N + i) * H + k];
-    ql_s[k] = ql[b * H + k];
-  }
-  __syncthreads();
-  const float* vb = vl + b * N * H;
-  const uint64_t base = d.base + (uint64_t)((b * N + i) * NH);
-  float acc[G] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t t = threadIdx.x; t < NH / 4; t += ODA_THREADS) {
-    const int64_t e0 = t * 4;
-    const uint32_t bt = philox_bytes4(d.key(), d.layer, base + (uint64_t)e0);
-    const uint32_t wd[4] = {bt & 0xFFu, (bt >> 8) & 0xFFu, (bt >> 16) & 0xFFu, bt >> 24};
+  const int64_t e0 = ((int64_t)blockIdx.x * ODA_THREADS + threadIdx.x) * ODA_EPT;
+  const bool active = e0 < NH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t seed = d.key();
+  const float* vb = vl + b * NH;
+  float w[G][ODA_EPT], vj[ODA_EPT], qk[ODA_EPT];
+  int kk[ODA_EPT];
+  if (active) {
     int64_t j = e0 / H, k = e0 - j * H;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (wd[u] >= d.thr) {
-        const float delta = (vi_s[k] - vb[j * H + k]) * ql_s[k];
+    for (int e = 0; e < ODA_EPT; ++e) {
+      const bool in = e0 + e < NH;                      // ragged tail when N*H is not a multiple of 8
+      kk[e] = in ? (int)k : 0;
+      vj[e] = in ? vb[j * H + k] : 0.0f;
+      qk[e] = in ? ql[b * H + k] * d.scale : 0.0f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] = fmaf(W[g * NH + e0 + u], delta, acc[g]);
-      }
+      for (int g = 0; g < G; ++g) w[g][e] = in ? W[g * NH + e0 + e] : 0.0f;
       if (++k == H) { k = 0; ++j; }
     }
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t i = 0; i < N; ++i) {
+    float acc[G] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      float keep[ODA_EPT];
+      keep8(d, seed, d.base + (uint64_t)((b * N + i) * NH + e0), keep);
+      const float* vi = vb + i * H;
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
-    const float v = warp_sum(acc[g]);
-    if (lane == 0) red[g][warp] = v;
+      for (int e = 0; e < ODA_EPT; ++e) {          // branch-free: a 50 % mask would diverge on every element
+        const float delta = (__ldg(vi + kk[e]) - vj[e]) * (qk[e] * keep[e]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = fmaf(w[g][e], delta, acc[g]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = warp_sum(acc[g]);
+    if (lane == 0) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) part[(warp * N + i) * G + g] = acc[g];
+    }
   }
   __syncthreads();
-  if (threadIdx.x < G) {
+  for (int64_t t = threadIdx.x; t < N * G; t += ODA_THREADS) {
     float s = 0.0f;
-    for (int w = 0; w < ODA_THREADS / 32; ++w) s += red[threadIdx.x][w];
-    z[(b * N + i) * G + threadIdx.x] = fmaf(s, d.scale, bc[threadIdx.x]);
+#pragma unroll
+    for (int wv = 0; wv < ODA_THREADS / 32; ++wv) s += part[wv * N * G + t];
+    atomicAdd(&z[b * N * G + t], s);
   }
+}
+
+// z[b,i,g] = bc[g]
+__global__ void oda_init_logits_kernel(int64_t total, const float* __restrict__ bc, float* __restrict__ z) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total) z[t] = bc[t % G];
 }
 
 // dz = alpha (.) (dalpha - <alpha, dalpha>), dbc += sum dz.  grid = B
@@ -100,100 +144,151 @@ __global__ void softmax_regions_bwd_kernel(int64_t N, const float* __restrict__ 
   if (lane == 0 && dbc) atomicAdd(&dbc[warp], tot);
 }
 
-// dvl / dql in train mode.  grid = B; thread k owns column k of dvl[b] (held in shared memory), so
-// the +(i,k) / -(j,k) scatter needs no atomics and the result is deterministic.
-//   u(i,j,k) = scale*keep*sum_g dz[i,g] W[g,j,k];  dvl[i,k] += u*ql[k];  dvl[j,k] -= u*ql[k];
-//   dql[k] += u*(vl[i,k]-vl[j,k]).
-__global__ void oda_pair_bwd_train_dv_kernel(int64_t N, int64_t H, Drop d, const float* __restrict__ vl,
-                                             const float* __restrict__ ql, const float* __restrict__ W,
-                                             const float* __restrict__ dz, float* __restrict__ dvl,
-                                             float* __restrict__ dql) {
-  extern __shared__ float sm[];
-  float* dz_s = sm;              // [N*G]
-  float* col_s = sm + N * G;     // [N*H]
-  const int64_t b = blockIdx.x;
-  const int64_t NH = N * H;
-  for (int64_t t = threadIdx.x; t < N * G; t += blockDim.x) dz_s[t] = dz[b * N * G + t];
-  for (int64_t t = threadIdx.x; t < NH; t += blockDim.x) col_s[t] = 0.0f;
-  __syncthreads();
-  const float* vb = vl + b * N * H;
-  for (int64_t k = threadIdx.x; k < H; k += blockDim.x) {
-    float dq = 0.0f;
-    for (int64_t j = 0; j < N; ++j) {
-      const float vj = vb[j * H + k];
-      float w[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) w[g] = W[g * NH + j * H + k];
-      float colj = 0.0f;
-      for (int64_t i = 0; i < N; ++i) {
-        const uint64_t idx = (uint64_t)((b * N + i) * NH + j * H + k);
-        if (philox_byte(d.key(), d.layer, d.base + idx) >= d.thr) {
-          const float* zz = dz_s + i * G;
-          const float u = (zz[0] * w[0] + zz[1] * w[1] + zz[2] * w[2] + zz[3] * w[3]) * d.scale;
-          colj -= u;
-          dq = fmaf(u, vb[i * H + k] - vj, dq);
-          col_s[i * H + k] += u;
-        }
-      }
-      col_s[j * H + k] += colj;
-    }
-    const float qk = ql[b * H + k];
-    for (int64_t i = 0; i < N; ++i) dvl[(b * N + i) * H + k] = col_s[i * H + k] * qk;
-    dql[b * H + k] = dq;
-  }
-}
-
-// dW[g,e] += scale * sum_{b,i} dz[b,i,g] keep(b,i,e) (vl[b,i,k]-vl[b,j,k]) ql[b,k].
-// grid = (cdiv(NH/4,128), b-chunks); a thread owns one aligned quad of e for its chunk of samples.
-constexpr int ODA_BCHUNK = 4;
+// Backward, e-mapping (thread owns 8 consecutive e = fixed (j,k) pairs, loops over the samples of its chunk and
+// over i).  With u(b,i,e) = scale * keep * sum_g dz[b,i,g] W[g,e]:
+//   dvl[b,j,k]  = -ql[b,k] * sum_i u              (this thread is the only writer of (b,j,k): plain store)
+//   dql[b,k]   += sum_i u * (vl[b,i,k]-vl[b,j,k])  (atomic: other j share k)
+//   dW[g,e]    += scale * sum_{b,i} dz[b,i,g] keep (vl[b,i,k]-vl[b,j,k]) ql[b,k]   (registers over the chunk, then atomic)
+// grid = (cdiv(NH/8, 128), cdiv(B, ODA_BCHUNK))
+constexpr int ODA_BCHUNK = 8;
 __global__ void __launch_bounds__(128)
-oda_pair_bwd_train_dw_kernel(int64_t B, int64_t N, int64_t H, Drop d, const float* __restrict__ vl,
-                             const float* __restrict__ ql, const float* __restrict__ dz, float* __restrict__ dW) {
+oda_pair_bwd_train_e_kernel(int64_t B, int64_t N, int64_t H, Drop d, const float* __restrict__ vl,
+                            const float* __restrict__ ql, const float* __restrict__ W, const float* __restrict__ dz,
+                            float* __restrict__ dW, float* __restrict__ dvl, float* __restrict__ dql) {
   const int64_t NH = N * H;
-  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (t >= NH / 4) return;
-  const int64_t e0 = t * 4;
-  int64_t jj[4], kk[4];
+  const int64_t e0 = ((int64_t)blockIdx.x * 128 + threadIdx.x) * ODA_EPT;
+  if (e0 >= NH) return;
+  const uint64_t seed = d.key();
+  float w[G][ODA_EPT], dwacc[G][ODA_EPT];
+  int jj[ODA_EPT], kk[ODA_EPT];
   {
     int64_t j = e0 / H, k = e0 - j * H;
-    for (int u = 0; u < 4; ++u) {
-      jj[u] = j; kk[u] = k;
+#pragma unroll
+    for (int e = 0; e < ODA_EPT; ++e) {
+      const bool in = e0 + e < NH;
+      jj[e] = in ? (int)j : 0; kk[e] = in ? (int)k : 0;
+#pragma unroll
+      for (int g = 0; g < G; ++g) { w[g][e] = in ? W[g * NH + e0 + e] : 0.0f; dwacc[g][e] = 0.0f; }
       if (++k == H) { k = 0; ++j; }
     }
   }
-  float acc[4][G];
-#pragma unroll
-  for (int u = 0; u < 4; ++u)
-#pragma unroll
-    for (int g = 0; g < G; ++g) acc[u][g] = 0.0f;
   const int64_t b0 = (int64_t)blockIdx.y * ODA_BCHUNK;
   const int64_t b1 = b0 + ODA_BCHUNK < B ? b0 + ODA_BCHUNK : B;
   for (int64_t b = b0; b < b1; ++b) {
-    const float* vb = vl + b * N * H;
-    float qv[4], vj[4];
+    const float* vb = vl + b * NH;
+    float vj[ODA_EPT], qk[ODA_EPT], minus[ODA_EPT], dq[ODA_EPT];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { qv[u] = ql[b * H + kk[u]]; vj[u] = vb[jj[u] * H + kk[u]]; }
+    for (int e = 0; e < ODA_EPT; ++e) {
+      vj[e] = vb[(int64_t)jj[e] * H + kk[e]];
+      qk[e] = ql[b * H + kk[e]];
+      minus[e] = 0.0f; dq[e] = 0.0f;
+    }
     for (int64_t i = 0; i < N; ++i) {
-      const uint64_t idx = d.base + (uint64_t)((b * N + i) * NH + e0);
-      const uint32_t bt = philox_bytes4(d.key(), d.layer, idx);
-      const uint32_t wd[4] = {bt & 0xFFu, (bt >> 8) & 0xFFu, (bt >> 16) & 0xFFu, bt >> 24};
-      const float4 z4 = *reinterpret_cast<const float4*>(&dz[(b * N + i) * G]);
+      float keep[ODA_EPT];
+      keep8(d, seed, d.base + (uint64_t)((b * N + i) * NH + e0), keep);
+      const float4 z4 = __ldg(reinterpret_cast<const float4*>(dz + (b * N + i) * G));
+      const float zg[G] = {z4.x * d.scale, z4.y * d.scale, z4.z * d.scale, z4.w * d.scale};
+      const float* vi = vb + i * H;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (wd[u] >= d.thr) {
-          const float delta = (vb[i * H + kk[u]] - vj[u]) * qv[u];
-          acc[u][0] = fmaf(z4.x, delta, acc[u][0]);
-          acc[u][1] = fmaf(z4.y, delta, acc[u][1]);
-          acc[u][2] = fmaf(z4.z, delta, acc[u][2]);
-          acc[u][3] = fmaf(z4.w, delta, acc[u][3]);
-        }
+      for (int e = 0; e < ODA_EPT; ++e) {          // branch-free
+        const float diff = (__ldg(vi + kk[e]) - vj[e]) * keep[e];
+        const float u = (zg[0] * w[0][e] + zg[1] * w[1][e] + zg[2] * w[2][e] + zg[3] * w[3][e]) * keep[e];
+        minus[e] += u;
+        dq[e] = fmaf(u, diff, dq[e]);
+        const float dl = diff * qk[e];
+#pragma unroll
+        for (int g = 0; g < G; ++g) dwacc[g][e] = fmaf(zg[g], dl, dwacc[g][e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < ODA_EPT; ++e) {
+      if (e0 + e < NH) {
+        dvl[b * NH + e0 + e] = -minus[e] * qk[e];
+        atomicAdd(&dql[b * H + kk[e]], dq[e]);
       }
     }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int e = 0; e < ODA_EPT; ++e)
 #pragma unroll
-    for (int g = 0; g < G; ++g) atomicAdd(&dW[g * NH + e0 + u], acc[u][g] * d.scale);
+    for (int g = 0; g < G; ++g)
+      if (e0 + e < NH) atomicAdd(&dW[g * NH + e0 + e], dwacc[g][e]);
+}
+
+// Backward, (i,k)-mapping: thread (i, 16-column slot) loops over j and adds the "+" term
+//   dvl[b,i,k] += ql[b,k] * sum_j u(b,i,(j,k))
+// to the value the e-kernel stored (it is the only "+" writer of (b,i,k)).  W rows of a block of ODA_JB regions j
+// are staged in shared memory (row stride padded to a multiple of 4 floats) and shared by the ODA_IC rows i of the
+// CTA.  grid = (cdiv(N, ODA_IC), B); threads = ODA_IC * cdiv(H,16) rounded up to a warp.
+constexpr int ODA_IC = 16, ODA_JB = 8;
+__global__ void __launch_bounds__(320, 2)
+oda_pair_bwd_train_plus_kernel(int64_t N, int64_t H, Drop d, const float* __restrict__ ql,
+                                               const float* __restrict__ W, const float* __restrict__ dz,
+                                               float* __restrict__ dvl) {
+  extern __shared__ float w_s[];                        // [G][ODA_JB][Hp]
+  const int64_t NH = N * H;
+  const int64_t Hp = (H + 3) / 4 * 4;
+  const int KS = (int)((H + 15) / 16);
+  const int64_t b = blockIdx.y;
+  const int ii = threadIdx.x / KS, ks = threadIdx.x % KS;
+  const int64_t i = (int64_t)blockIdx.x * ODA_IC + ii;
+  const bool active = ii < ODA_IC && i < N;
+  const int k0 = ks * 16;
+  const int nk = (int)(H - k0 < 16 ? H - k0 : 16);
+  const uint64_t seed = d.key();
+  float zg[G] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const float4 z4 = __ldg(reinterpret_cast<const float4*>(dz + (b * N + i) * G));
+    zg[0] = z4.x * d.scale; zg[1] = z4.y * d.scale; zg[2] = z4.z * d.scale; zg[3] = z4.w * d.scale;
+  }
+  float plus[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) plus[e] = 0.0f;
+  for (int64_t jb = 0; jb < N; jb += ODA_JB) {
+    const int64_t nj = N - jb < ODA_JB ? N - jb : ODA_JB;
+    __syncthreads();
+    for (int64_t t = threadIdx.x; t < (int64_t)G * nj * H; t += blockDim.x) {
+      const int64_t g = t / (nj * H), r = t - g * nj * H, jl = r / H, k = r - jl * H;
+      w_s[(g * ODA_JB + jl) * Hp + k] = W[g * NH + (jb + jl) * H + k];
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int64_t jl = 0; jl < nj; ++jl) {
+      const uint64_t idx0 = d.base + (uint64_t)((b * N + i) * NH + (jb + jl) * H + k0);
+      const uint4 r0 = philox_group(seed, d.layer, idx0 >> 4);
+      const uint32_t off = (uint32_t)idx0 & 15u;
+      uint4 r1 = r0;
+      if (off) r1 = philox_group(seed, d.layer, (idx0 >> 4) + 1);
+      // the 16 keep-bytes start at byte `off` of the 32-byte pair (r0, r1): rotate by whole words with predicated
+      // moves (static register indexing), then funnel-shift the remaining 0..3 bytes
+      uint32_t a[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      if (off & 4u) {
+#pragma unroll
+        for (int t = 0; t < 7; ++t) a[t] = a[t + 1];
+      }
+      if (off & 8u) {
+#pragma unroll
+        for (int t = 0; t < 6; ++t) a[t] = a[t + 2];
+      }
+      const uint32_t sh = 8u * (off & 3u);
+      uint32_t by[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) by[t] = __funnelshift_r(a[t], a[t + 1], sh);
+      const float* wrow = w_s + jl * Hp + k0;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float m = (e < nk && ((by[e >> 2] >> (8 * (e & 3))) & 0xFFu) >= d.thr) ? 1.0f : 0.0f;
+        const float u = zg[0] * wrow[e] + zg[1] * wrow[ODA_JB * Hp + e] + zg[2] * wrow[2 * ODA_JB * Hp + e] +
+                        zg[3] * wrow[3 * ODA_JB * Hp + e];
+        plus[e] = fmaf(m, u, plus[e]);
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (e < nk) dvl[(b * N + i) * H + k0 + e] += plus[e] * ql[b * H + k0 + e];
+  }
 }
 
 }  // namespace vqa
@@ -203,7 +298,6 @@ using namespace vqa;
 static int oda_check(int64_t B, int64_t N, int64_t H, int64_t D, const char* who) {
   VQA_REQUIRE(B >= 0 && N >= 1 && H >= 1 && D >= 4 && D % 4 == 0, "%s: bad shape B=%lld N=%lld H=%lld D=%lld", who,
               (long long)B, (long long)N, (long long)H, (long long)D);
-  VQA_REQUIRE((N * H) % 4 == 0, "%s: N*H=%lld must be a multiple of 4", who, (long long)(N * H));
   return VQA_OK;
 }
 
@@ -225,9 +319,13 @@ extern "C" int vqa_oda_pair_attn_fwd(const vqa_oda_pair_attn_fwd_params* p, void
     VQA_TRY(check_launch("oda_logits_eval"));
   } else {
     Drop d = make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev);
-    dim3 grid((unsigned)p->N, (unsigned)p->B);
-    oda_pair_logits_train_kernel<<<grid, ODA_THREADS, (size_t)2 * p->H * sizeof(float), st>>>(
-        p->N, p->H, d, p->vl, p->ql, p->W, p->bc, p->alpha);
+    const int64_t NH = p->N * p->H;
+    oda_init_logits_kernel<<<(unsigned)cdiv(p->B * p->N * G, 256), 256, 0, st>>>(p->B * p->N * G, p->bc, p->alpha);
+    VQA_TRY(check_launch("oda_init_logits"));
+    dim3 grid((unsigned)cdiv(cdiv(NH, ODA_EPT), ODA_THREADS), (unsigned)p->B);
+    const size_t smem = (size_t)(ODA_THREADS / 32) * p->N * G * sizeof(float);
+    VQA_REQUIRE(smem <= 48 * 1024, "vqa_oda_pair_attn_fwd: N=%lld too large", (long long)p->N);
+    oda_pair_logits_train_kernel<<<grid, ODA_THREADS, smem, st>>>(p->N, p->H, d, p->vl, p->ql, p->W, p->alpha);
     VQA_TRY(check_launch("oda_pair_logits_train"));
     softmax_regions_kernel<<<(unsigned)p->B, 128, (size_t)p->N * G * sizeof(float), st>>>(p->N, p->alpha);
     VQA_TRY(check_launch("softmax_regions"));
@@ -263,20 +361,23 @@ extern "C" int vqa_oda_pair_attn_bwd(const vqa_oda_pair_attn_bwd_params* p, void
   softmax_regions_bwd_kernel<<<(unsigned)p->B, 128, 0, st>>>(p->N, p->alpha, p->dalpha, p->dz, p->dbc);
   VQA_TRY(check_launch("softmax_regions_bwd"));
   if (!p->accumulate_w) cudaMemsetAsync(p->dW, 0, (size_t)G * NH * sizeof(float), st);
+  cudaMemsetAsync(p->dql, 0, (size_t)p->B * p->H * sizeof(float), st);
   {
-    const int threads = (int)(p->H >= 512 ? 512 : ((p->H + 31) / 32) * 32);
-    const size_t smem = (size_t)(p->N * G + NH) * sizeof(float);
-    VQA_REQUIRE(smem <= 220 * 1024, "vqa_oda_pair_attn_bwd: N*H=%lld too large for shared memory", (long long)NH);
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(oda_pair_bwd_train_dv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    oda_pair_bwd_train_dv_kernel<<<(unsigned)p->B, threads, smem, st>>>(p->N, p->H, d, p->vl, p->ql, p->W, p->dz,
-                                                                       p->dvl, p->dql);
-    VQA_TRY(check_launch("oda_pair_bwd_train_dv"));
+    dim3 grid((unsigned)cdiv(cdiv(NH, ODA_EPT), 128), (unsigned)cdiv(p->B, ODA_BCHUNK));
+    oda_pair_bwd_train_e_kernel<<<grid, 128, 0, st>>>(p->B, p->N, p->H, d, p->vl, p->ql, p->W, p->dz, p->dW, p->dvl,
+                                                      p->dql);
+    VQA_TRY(check_launch("oda_pair_bwd_train_e"));
   }
   {
-    dim3 grid((unsigned)cdiv(NH / 4, 128), (unsigned)cdiv(p->B, ODA_BCHUNK));
-    oda_pair_bwd_train_dw_kernel<<<grid, 128, 0, st>>>(p->B, p->N, p->H, d, p->vl, p->ql, p->dz, p->dW);
-    VQA_TRY(check_launch("oda_pair_bwd_train_dw"));
+    const int KS = (int)((p->H + 15) / 16);
+    const int threads = ((ODA_IC * KS + 31) / 32) * 32;
+    VQA_REQUIRE(threads <= 1024, "vqa_oda_pair_attn_bwd: H=%lld too large", (long long)p->H);
+    const size_t smem = ((size_t)G * ODA_JB * ((p->H + 3) / 4 * 4) + 16) * sizeof(float);   // +16: masked tail reads
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(oda_pair_bwd_train_plus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((unsigned)cdiv(p->N, ODA_IC), (unsigned)p->B);
+    oda_pair_bwd_train_plus_kernel<<<grid, threads, smem, st>>>(p->N, p->H, d, p->ql, p->W, p->dz, p->dvl);
+    VQA_TRY(check_launch("oda_pair_bwd_train_plus"));
   }
   return VQA_OK;
 }

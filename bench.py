@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--model", default="CoR2", choices=["CoR2", "ODA"])
     ap.add_argument("--batch", type=int, default=256, help="per GPU")
     ap.add_argument("--regions", type=int, default=36)
-    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--precision", default="tf32x3", help="tf32x3 = fp32-parity mode (3xTF32 tensor cores); fp32 = CUDA cores; tf32")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the CPU oracle sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (default: train mode)")
@@ -219,7 +219,7 @@ def run_ours(args):
 
     def eager_step(v, q, a):
         logits = model({"v": v, "q_idxes": q})
-        loss = ops.kld_loss_rows(logits, a).sum()
+        loss = ops.kld_loss(logits, a)
         loss.backward()
         engine.wait()
         return loss

@@ -361,6 +361,10 @@ typedef struct {
   float* dlogits;        /* [B,C] or NULL */
 } vqa_kld_logsoftmax_params;
 int vqa_kld_logsoftmax_fwd_bwd(const vqa_kld_logsoftmax_params* p, void* stream);
+/* out[0] = sum(rows[0..n)) with a fixed reduction order; y = x * scale[0] with the scalar read on the device
+ * (the incoming autograd gradient of the scalar loss) — the two pieces that keep the loss off ATen. */
+int vqa_sum_rows(int64_t n, const float* rows, float* out, void* stream);
+int vqa_scale_by_device_scalar(int64_t n, const float* x, const float* scale, float* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole-model plans: one call enqueues every kernel of Model.forward / its backward

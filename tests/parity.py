@@ -118,8 +118,7 @@ def run_cuda_model(model, sd, v, q, a, N=36, train_seed=None, precision="fp32", 
     m.fixed_seed = train_seed
     sample = {"v": v.to(device), "q_idxes": q.to(device)}
     logits = m(sample)
-    rows = ops.kld_loss_rows(logits, a.to(device))
-    loss = rows.sum()
+    loss = ops.kld_loss(logits, a.to(device))
     loss.backward()
     torch.cuda.synchronize()
     grads = {n: p.grad.detach().cpu() for n, p in m.named_parameters()}

@@ -11,7 +11,8 @@ class CoreModel(nn.Module):
 
     Extra constructor arguments, all defaulting to the reference's behaviour:
       num_regions  N (reference hard-codes 36: config/CoR2.py:203, config/ODA.py:202,222)
-      precision    GEMM arithmetic: 'fp32' (CUDA-core FMA), 'tf32x3', 'tf32', 'bf16' (tcgen05)
+      precision    GEMM arithmetic: 'tf32x3' (default: tcgen05 tensor cores, error-compensated 3xTF32, meets the
+                   1e-4 fp32-parity bound), 'fp32' (CUDA-core FMA, bitwise reproducible), 'tf32' (single pass)
       seq2vec      question encoder module; default passes sample['q_idxes'] through as the
                    2400-d embedding (blocks.QuestionPassThrough)
     """

@@ -46,6 +46,21 @@ kld_logsoftmax_kernel(int64_t C, float grad_scale, const float* __restrict__ log
   if (threadIdx.x == 0) loss_rows[b] = l;
 }
 
+// loss = sum_b loss_rows[b] (deterministic single-CTA tree);  dlogits *= *scale (device scalar, no host sync)
+__global__ void __launch_bounds__(LOSS_THREADS) sum_rows_kernel(int64_t B, const float* __restrict__ rows, float* __restrict__ out) {
+  __shared__ float red[LOSS_THREADS / 32];
+  float s = 0.0f;
+  for (int64_t b = threadIdx.x; b < B; b += LOSS_THREADS) s += rows[b];
+  s = block_reduce(s, red, false);
+  if (threadIdx.x == 0) *out = s;
+}
+__global__ void scale_by_device_scalar_kernel(int64_t n, const float* __restrict__ x, const float* __restrict__ scale,
+                                              float* __restrict__ y) {
+  const float sc = __ldg(scale);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    y[t] = x[t] * sc;
+}
+
 }  // namespace vqa
 
 using namespace vqa;
@@ -58,4 +73,19 @@ extern "C" int vqa_kld_logsoftmax_fwd_bwd(const vqa_kld_logsoftmax_params* p, vo
   kld_logsoftmax_kernel<<<(unsigned)p->B, LOSS_THREADS, 0, (cudaStream_t)stream>>>(p->C, p->grad_scale, p->logits,
                                                                                   p->target, p->loss_rows, p->dlogits);
   return check_launch("kld_logsoftmax");
+}
+
+extern "C" int vqa_sum_rows(int64_t n, const float* rows, float* out, void* stream) {
+  VQA_REQUIRE(n >= 0 && rows && out, "vqa_sum_rows: bad argument");
+  sum_rows_kernel<<<1, LOSS_THREADS, 0, (cudaStream_t)stream>>>(n, rows, out);
+  return check_launch("sum_rows");
+}
+
+extern "C" int vqa_scale_by_device_scalar(int64_t n, const float* x, const float* scale, float* y, void* stream) {
+  VQA_REQUIRE(n >= 0 && x && scale && y, "vqa_scale_by_device_scalar: bad argument");
+  if (n == 0) return VQA_OK;
+  int64_t blocks = (n + 1023) / 1024;
+  if (blocks > 2048) blocks = 2048;
+  scale_by_device_scalar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, x, scale, y);
+  return check_launch("scale_by_device_scalar");
 }

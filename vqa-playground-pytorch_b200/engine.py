@@ -10,7 +10,7 @@ from . import ops
 
 def kld_loss(logits, target):
     """KLDivLoss(size_average=False)(log_softmax(x), a) — train.py:536-544 — through the fused kernel."""
-    return ops.kld_loss_rows(logits, target).sum()
+    return ops.kld_loss(logits, target)
 
 
 def train_step(model, sample, optimizer=None, scheduler=None, engine=None, clip_grad=None):

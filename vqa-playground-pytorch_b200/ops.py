@@ -300,6 +300,41 @@ def kld_loss_rows(logits, target):
     return KldLogSoftmaxFn.apply(logits, target)
 
 
+class KldLossFn(torch.autograd.Function):
+    """Scalar KLDivLoss(size_average=False)(log_softmax(x,1), a) (train.py:536-544): per-row loss + gradient in one
+    kernel, a fixed-order row sum, and the backward scaling by the incoming gradient read on the device."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        x, a = _chk(logits, "logits", 2), _chk(target, "target", 2)
+        B, Cc = x.shape
+        rows = torch.empty((B,), device=x.device, dtype=torch.float32)
+        dlogits = torch.empty_like(x)
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        pr = _lib.KldParams()
+        pr.B, pr.C, pr.grad_scale = B, Cc, 1.0
+        pr.logits, pr.target, pr.loss_rows, pr.dlogits = x.data_ptr(), a.data_ptr(), rows.data_ptr(), dlogits.data_ptr()
+        L = _lib.lib()
+        _lib.check(L.vqa_kld_logsoftmax_fwd_bwd(C.byref(pr), _stream()), "vqa_kld_logsoftmax_fwd_bwd")
+        _lib.check(L.vqa_sum_rows(B, rows.data_ptr(), loss.data_ptr(), _stream()), "vqa_sum_rows")
+        ctx.save_for_backward(dlogits)
+        ctx.rows = rows
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        out = torch.empty_like(dlogits)
+        gg = g.contiguous().to(torch.float32)
+        _lib.check(_lib.lib().vqa_scale_by_device_scalar(dlogits.numel(), dlogits.data_ptr(), gg.data_ptr(),
+                                                         out.data_ptr(), _stream()), "vqa_scale_by_device_scalar")
+        return out, None
+
+
+def kld_loss(logits, target):
+    return KldLossFn.apply(logits, target)
+
+
 # =========================================================================== whole-model plans
 _MODEL = {
     "CoR2": ("vqa_cor2_workspace_bytes", "vqa_cor2_fwd", "vqa_cor2_bwd"),

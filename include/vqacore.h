@@ -167,6 +167,13 @@ typedef struct {
   const float* Wp[VQA_MAX_GROUPS];           /* optional, as in the forward */
   void* workspace;          /* >= vqa_linear_bwd_workspace_bytes() */
   size_t workspace_bytes;
+  /* Optional addend fused into the dX_0 store (groups == 1, K % 4 == 0): the gradient of a 4-glimpse attention
+   * pooling over the same X (MyATT's bmatmul, config/CoR2.py:118-121):
+   *   dX_0[m, :] += sum_g pool_alpha[m*4 + g] * pool_dpooled[(m / pool_regions)*4*K + g*K + :]
+   * pool_alpha NULL: none. */
+  const float* pool_alpha;
+  const float* pool_dpooled;
+  int64_t pool_regions;
 } vqa_linear_bwd_params;
 int vqa_linear_bwd(const vqa_linear_bwd_params* p, void* stream);
 

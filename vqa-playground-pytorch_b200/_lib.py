@@ -44,7 +44,8 @@ class LinearBwd(C.Structure):
                 ("accumulate_x", C.c_int),
                 ("X", PA), ("ldx", IA), ("W", PA), ("Y", PA), ("ldy", IA), ("dY", PA), ("lddy", IA),
                 ("dW", PA), ("db", PA), ("dX", PA), ("lddx", IA), ("layer", U32A), ("drop_index_base", U64A),
-                ("drop_bits", PA), ("Wp", PA), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
+                ("drop_bits", PA), ("Wp", PA), ("workspace", fp), ("workspace_bytes", C.c_size_t),
+                ("pool_alpha", fp), ("pool_dpooled", fp), ("pool_regions", i64)]
 
 
 class MutanFwd(C.Structure):

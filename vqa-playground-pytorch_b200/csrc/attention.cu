@@ -72,61 +72,87 @@ int launch_pool_fwd(int64_t B, int64_t N, int64_t D, const float* x, const float
 }
 
 // dalpha[b,i,g] = <dpooled[b,g,:], x[b,i,:]> (+ ext for g=0);  dx[b,i,:] (+)= sum_g alpha[b,i,g] dpooled[b,g,:].
-// One warp per region: the second (and last) pass over x in the backward.  grid = (cdiv(N,8), B).
+// The second (and last) pass over x in the backward.  One warp owns RW consecutive regions of one sample and walks the
+// feature axis once: every dpooled vector it fetches (L1/L2-resident, 4*D floats per sample) is used for RW rows, so the
+// streaming read of x, not the re-read of dpooled, sets the pace.  grid = (cdiv(N, 8*RW), B), 8 warps.
+constexpr int POOL_BWD_RW = 4;
 __global__ void __launch_bounds__(256)
 pool_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* __restrict__ alpha,
                 const float* __restrict__ dpooled, const float* __restrict__ dalpha0_ext, float* __restrict__ dalpha,
                 float* __restrict__ dx, int accumulate_x) {
+  constexpr int RW = POOL_BWD_RW;
   const int64_t b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
-  if (i >= N) return;
-  float a[G];
+  const int64_t i0 = ((int64_t)blockIdx.x * 8 + warp) * RW;
+  if (i0 >= N) return;
+  const int nr = N - i0 < RW ? (int)(N - i0) : RW;
+  float a[RW][G];
+  float dot[RW][G];
 #pragma unroll
-  for (int g = 0; g < G; ++g) a[g] = alpha[(b * N + i) * G + g];
-  float dot[G] = {0.f, 0.f, 0.f, 0.f};
-  const float* xr = x + (b * N + i) * D;
+  for (int r = 0; r < RW; ++r)
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      a[r][g] = r < nr ? alpha[(b * N + i0 + r) * G + g] : 0.0f;
+      dot[r][g] = 0.0f;
+    }
+  const float* xr = x + (b * N + i0) * D;
   const float* dp = dpooled + b * G * D;
-  float* dxr = dx ? dx + (b * N + i) * D : nullptr;
-  constexpr int U = 4;
-  for (int64_t c0 = lane * 4; c0 < D; c0 += 128 * U) {
-    float4 xv[U];
+  constexpr int CU = 2;                              // column chunks in flight per lane
+  for (int64_t c0 = lane * 4; c0 < D; c0 += 128 * CU) {
+    float4 xv[CU][RW];
+    float4 d[CU][G];
 #pragma unroll
-    for (int u = 0; u < U; ++u) xv[u] = (c0 + u * 128 < D) ? ld_stream4(xr + c0 + u * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < CU; ++u) {
       const int64_t c = c0 + u * 128;
-      if (c >= D) break;
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float4 d = __ldg(reinterpret_cast<const float4*>(dp + g * D + c));
-        dot[g] = fmaf(xv[u].x, d.x, fmaf(xv[u].y, d.y, fmaf(xv[u].z, d.z, fmaf(xv[u].w, d.w, dot[g]))));
-        o.x = fmaf(a[g], d.x, o.x); o.y = fmaf(a[g], d.y, o.y);
-        o.z = fmaf(a[g], d.z, o.z); o.w = fmaf(a[g], d.w, o.w);
-      }
-      if (dxr) {
-        float4* dst = reinterpret_cast<float4*>(dxr + c);
-        if (accumulate_x) {
-          const float4 old = *dst;
-          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      for (int r = 0; r < RW; ++r)
+        xv[u][r] = (r < nr && c < D) ? ld_stream4(xr + r * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        d[u][g] = c < D ? __ldg(reinterpret_cast<const float4*>(dp + g * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < CU; ++u) {
+      const int64_t c = c0 + u * 128;
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float4 dg = d[u][g], xr4 = xv[u][r];
+          dot[r][g] = fmaf(xr4.x, dg.x, fmaf(xr4.y, dg.y, fmaf(xr4.z, dg.z, fmaf(xr4.w, dg.w, dot[r][g]))));
+          o.x = fmaf(a[r][g], dg.x, o.x); o.y = fmaf(a[r][g], dg.y, o.y);
+          o.z = fmaf(a[r][g], dg.z, o.z); o.w = fmaf(a[r][g], dg.w, o.w);
         }
-        *dst = o;
+        if (dx && r < nr && c < D) {
+          float4* dst = reinterpret_cast<float4*>(dx + (b * N + i0 + r) * D + c);
+          if (accumulate_x) {
+            const float4 old = *dst;
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *dst = o;
+        }
       }
     }
   }
 #pragma unroll
-  for (int g = 0; g < G; ++g) dot[g] = warp_sum(dot[g]);
-  if (lane == 0) {
-    if (dalpha0_ext) dot[0] += dalpha0_ext[b];
+  for (int r = 0; r < RW; ++r)
 #pragma unroll
-    for (int g = 0; g < G; ++g) dalpha[(b * N + i) * G + g] = dot[g];
+    for (int g = 0; g < G; ++g) dot[r][g] = warp_sum(dot[r][g]);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      if (r >= nr) break;
+      if (dalpha0_ext) dot[r][0] += dalpha0_ext[b];
+#pragma unroll
+      for (int g = 0; g < G; ++g) dalpha[(b * N + i0 + r) * G + g] = dot[r][g];
+    }
   }
 }
 
 int launch_pool_bwd(int64_t B, int64_t N, int64_t D, const float* x, const float* alpha, const float* dpooled,
                     const float* dalpha0_ext, float* dalpha, float* dx, int accumulate_x, cudaStream_t st) {
-  dim3 grid((unsigned)cdiv(N, 8), (unsigned)B);
+  dim3 grid((unsigned)cdiv(N, 8 * POOL_BWD_RW), (unsigned)B);
   pool_bwd_kernel<<<grid, 256, 0, st>>>(N, D, x, alpha, dpooled, dalpha0_ext, dalpha, dx, accumulate_x);
   return check_launch("pool_bwd");
 }

@@ -94,11 +94,25 @@ __device__ __forceinline__ void store4(float* dst, const float (&o)[4], int nv) 
       if (e < nv) dst[e] = o[e];
   }
 }
+// o[0..nv) added to dst[0..nv) with reductions that return nothing: one 16-byte red when the quad is whole and aligned
+__device__ __forceinline__ void red_add4(float* dst, const float (&o)[4], int nv) {
+  if (nv == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3])
+                 : "memory");
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (e < nv) atomicAdd(dst + e, o[e]);
+  }
+}
 __device__ __forceinline__ void load4(const float* src, float (&o)[4], int nv) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(src);
   if (nv == 4 && (a & 15) == 0) {
     const float4 t = *reinterpret_cast<const float4*>(src);
     o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  } else if (nv == 4 && (a & 7) == 0) {
+    const float2 t0 = *reinterpret_cast<const float2*>(src), t1 = *reinterpret_cast<const float2*>(src + 2);
+    o[0] = t0.x; o[1] = t0.y; o[2] = t1.x; o[3] = t1.y;
   } else {
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[e] = e < nv ? src[e] : 0.0f;
@@ -110,30 +124,31 @@ __device__ __forceinline__ void load4(const float* src, float (&o)[4], int nv) {
 // act_inplace_kernel.
 struct EpiBiasAct {
   static constexpr bool kStaged = true;
+  static constexpr int kBatch = 8;
   float* Y[MAXG];
   const float* bias[MAXG];
   int64_t ld[MAXG];
   int act;
   int atomic;
-  __device__ __forceinline__ void row4(int g, int split, int64_t m, int n, int N, const float4 v) const {
-    float* y = Y[g] + m * ld[g] + n;
-    const float* b = bias[g];
-    const int nv = N - n < 4 ? N - n : 4;
-    float o[4] = {v.x, v.y, v.z, v.w};
-    if (b && (!atomic || split == 0)) {
+  struct Col { float* y; int64_t ld; float b[4]; int nv; };
+  struct Pre {};
+  __device__ __forceinline__ void column(Col& c, int g, int split, int n, int N) const {
+    c.y = Y[g] + n; c.ld = ld[g]; c.nv = N - n < 4 ? N - n : 4;
+    const float* bp = bias[g];
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (e < nv) o[e] += __ldg(b + n + e);
-    }
+    for (int e = 0; e < 4; ++e) c.b[e] = (bp && e < c.nv && (!atomic || split == 0)) ? __ldg(bp + n + e) : 0.0f;
+  }
+  __device__ __forceinline__ void preload(Pre&, const Col&, int) const {}
+  __device__ __forceinline__ void row4(const Col& c, int m, const float4 v, const Pre&) const {
+    float* y = c.y + (int64_t)m * c.ld;
+    float o[4] = {v.x + c.b[0], v.y + c.b[1], v.z + c.b[2], v.w + c.b[3]};
     if (atomic) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (e < nv) atomicAdd(y + e, o[e]);
+      red_add4(y, o, c.nv);
       return;
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[e] = act_apply(act, o[e]);
-    store4(y, o, nv);
+    store4(y, o, c.nv);
   }
 };
 
@@ -153,6 +168,7 @@ __global__ void act_inplace_kernel(ActArgs a, int64_t M, int64_t N, int act) {
 // red.global.add (split-K partials and the "+=" of a flat gradient buffer are the same operation).
 struct EpiWgradT {
   static constexpr bool kStaged = false;
+  static constexpr int kBatch = 8;
   float* dW[MAXG];
   int64_t ldw;
   __device__ __forceinline__ void operator()(int g, int, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
@@ -168,8 +184,13 @@ struct EpiWgradT {
 };
 
 // dgrad: dX[m, n] (=|+=) acc * mask(m*drop_ld + n) / (1-p)
-struct EpiDgrad {
+// POOL: additionally dX[m, n] += sum_g alpha[m, g] * dpooled[m / regions, g, n] — the gradient of an attention pooling
+// over the same X (MyATT's bmatmul over v2, config/CoR2.py), which would otherwise cost a full write of dX by the
+// pooling backward and a read-modify-write here.
+template <bool POOL>
+struct EpiDgradT {
   static constexpr bool kStaged = true;
+  static constexpr int kBatch = POOL ? 4 : 8;
   float* dX[MAXG];
   int64_t ld[MAXG];
   int accumulate;
@@ -179,37 +200,65 @@ struct EpiDgrad {
   GroupDrop gd;
   int64_t drop_ld;
   const uint8_t* bits[MAXG];
-  __device__ __forceinline__ void row4(int g, int, int64_t m, int n, int N, const float4 v) const {
-    float* x = dX[g];
-    if (!x) return;
-    x += m * ld[g] + n;
-    const int nv = N - n < 4 ? N - n : 4;
+  const float* pool_alpha;      // [M, 4]
+  const float* pool_dp;         // [M / pool_regions, 4, pool_ld]
+  int64_t pool_regions, pool_ld;
+  struct Col { float* x; int64_t ld; int n, nv, first; const uint8_t* bits; const float* dp; uint32_t layer; uint64_t base; };
+  struct PreBase { float old[4]; uint32_t byte; };
+  struct PrePool : PreBase { float4 al; float4 dp[4]; };
+  using Pre = typename std::conditional<POOL, PrePool, PreBase>::type;
+  __device__ __forceinline__ void column(Col& c, int g, int split, int n, int N) const {
+    c.first = split == 0;
+    c.x = dX[g] ? dX[g] + n : nullptr; c.ld = ld[g]; c.n = n; c.nv = N - n < 4 ? N - n : 4;
+    c.bits = drop_on ? bits[g] : nullptr; c.layer = gd.layer[g]; c.base = gd.base[g];
+    c.dp = POOL ? pool_dp + n : nullptr;
+  }
+  __device__ __forceinline__ void preload(Pre& r, const Col& c, int m) const {
+    if (!c.x) return;
+    if (c.bits) r.byte = __ldg(c.bits + (((uint64_t)m * (uint64_t)drop_ld + (uint64_t)c.n) >> 3));
+    if (accumulate && !atomic) load4(c.x + (int64_t)m * c.ld, r.old, c.nv);
+    if constexpr (POOL) {
+      r.al = __ldg(reinterpret_cast<const float4*>(pool_alpha) + m);
+      const float* dp = c.dp + (int64_t)((uint32_t)m / (uint32_t)pool_regions) * 4 * pool_ld;   // N % 4 == 0 (host check)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r.dp[j] = __ldg(reinterpret_cast<const float4*>(dp + j * pool_ld));
+    }
+  }
+  __device__ __forceinline__ void row4(const Col& c, int m, const float4 v, const Pre& pre) const {
+    if (!c.x) return;
+    float* x = c.x + (int64_t)m * c.ld;
     float o[4] = {v.x, v.y, v.z, v.w};
-    if (drop_on && bits[g]) {
-      const uint64_t e = (uint64_t)(m * drop_ld + n);
-      const uint32_t nb = ((uint32_t)__ldg(bits[g] + (e >> 3)) >> (uint32_t)(e & 4)) & 0xFu;
+    if (c.bits) {
+      const uint32_t nb = pre.byte >> (((uint32_t)m * (uint32_t)drop_ld + (uint32_t)c.n) & 4u);
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = ((nb >> j) & 1u) ? o[j] * drop.scale : 0.0f;
     } else if (drop_on) {
-      const uint32_t bt = philox_bytes4(drop.key(), gd.layer[g], gd.base[g] + (uint64_t)(m * drop_ld + n));
+      const uint32_t bt = philox_bytes4(drop.key(), c.layer, c.base + ((uint64_t)m * (uint64_t)drop_ld + (uint64_t)c.n));
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = ((bt >> (8 * e)) & 0xFFu) >= drop.thr ? o[e] * drop.scale : 0.0f;
     }
-    if (atomic) {
+    if constexpr (POOL) {
+      if (c.first) {
+        const float al[4] = {pre.al.x, pre.al.y, pre.al.z, pre.al.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (e < nv) atomicAdd(x + e, o[e]);
+        for (int j = 0; j < 4; ++j) {
+          o[0] = fmaf(al[j], pre.dp[j].x, o[0]); o[1] = fmaf(al[j], pre.dp[j].y, o[1]);
+          o[2] = fmaf(al[j], pre.dp[j].z, o[2]); o[3] = fmaf(al[j], pre.dp[j].w, o[3]);
+        }
+      }
+    }
+    if (atomic) {
+      red_add4(x, o, c.nv);
       return;
     }
     if (accumulate) {
-      float old[4];
-      load4(x, old, nv);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] += old[e];
+      for (int e = 0; e < 4; ++e) o[e] += pre.old[e];
     }
-    store4(x, o, nv);
+    store4(x, o, c.nv);
   }
 };
+using EpiDgrad = EpiDgradT<false>;
 
 // ------------------------------------------------------------------------------------------ launch
 template <int BN, bool X3, class Epi>
@@ -394,41 +443,39 @@ __global__ void dropout_bits_kernel(uint64_t seed, const uint64_t* seed_ptr, uin
 // atomic mode (k-splits, small M) accumulates every partial into zeroed Y / H1 with red.global.add.
 struct EpiMutan {
   static constexpr bool kStaged = true;
+  static constexpr int kBatch = 8;
   const float* bias[MAXG]; const float* H2[MAXG]; float* H1[MAXG]; float* Y;
   int64_t ldh, ldy, rows_per; int accumulate; int atomic;
-  __device__ __forceinline__ void row4(int g, int split, int64_t m, int n, int N, const float4 v) const {
-    const int nv = N - n < 4 ? N - n : 4;
-    const float* h2 = H2[g] + (m / rows_per) * ldh + n;
-    const float* b = bias[g];
-    float* y = Y + m * ldy + n;
-    float h[4] = {v.x, v.y, v.z, v.w}, o[4];
+  struct Col { const float* h2; float* h1; float* y; float b[4]; int nv; };
+  struct Pre { float h2[4]; float old[4]; };
+  __device__ __forceinline__ void column(Col& c, int g, int split, int n, int N) const {
+    c.nv = N - n < 4 ? N - n : 4;
+    c.h2 = H2[g] + n; c.h1 = H1[g] ? H1[g] + n : nullptr; c.y = Y + n;
+    const float* bp = bias[g];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (e < nv) {
-        if (b && split == 0) h[e] += __ldg(b + n + e);
-        o[e] = h[e] * __ldg(h2 + e);
-      } else {
-        o[e] = 0.0f;
-      }
-    }
-    float* h1 = H1[g] ? H1[g] + m * ldh + n : nullptr;
+    for (int e = 0; e < 4; ++e) c.b[e] = (bp && e < c.nv && split == 0) ? __ldg(bp + n + e) : 0.0f;
+  }
+  __device__ __forceinline__ void preload(Pre& r, const Col& c, int m) const {
+    load4(c.h2 + (int64_t)((uint32_t)m / (uint32_t)rows_per) * ldh, r.h2, c.nv);
+    if (accumulate && !atomic) load4(c.y + (int64_t)m * ldy, r.old, c.nv);
+  }
+  __device__ __forceinline__ void row4(const Col& c, int m, const float4 v, const Pre& pre) const {
+    float h[4] = {v.x + c.b[0], v.y + c.b[1], v.z + c.b[2], v.w + c.b[3]}, o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = e < c.nv ? h[e] * pre.h2[e] : 0.0f;
+    float* y = c.y + (int64_t)m * ldy;
+    float* h1 = c.h1 ? c.h1 + (int64_t)m * ldh : nullptr;
     if (atomic) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (e < nv) {
-          if (h1) atomicAdd(h1 + e, h[e]);
-          atomicAdd(y + e, o[e]);
-        }
+      if (h1) red_add4(h1, h, c.nv);
+      red_add4(y, o, c.nv);
       return;
     }
-    if (h1) store4(h1, h, nv);
+    if (h1) store4(h1, h, c.nv);
     if (accumulate) {
-      float old[4];
-      load4(y, old, nv);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] += old[e];
+      for (int e = 0; e < 4; ++e) o[e] += pre.old[e];
     }
-    store4(y, o, nv);
+    store4(y, o, c.nv);
   }
 };
 
@@ -560,6 +607,40 @@ int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
 }
 
 // ============================================================================================ linear bwd
+template <bool POOL>
+static int dgrad_launch(const vqa_linear_bwd_params* p, float* dz, float* wpk, int64_t ldz, int64_t Kp, bool pack,
+                        bool prepacked, bool x3, cudaStream_t st) {
+  using namespace tc;
+  Params<EpiDgradT<POOL>> q = {};
+  const int bn = pick_bn(p->K);
+  for (int g = 0; g < MAXG; ++g) {
+    const int s = g < p->groups ? g : 0;
+    VQA_TRY(operand_tmap(&q.tmA[g], dz + (size_t)s * p->M * ldz, false, p->M, p->N, ldz, BM));
+    if (prepacked) VQA_TRY(operand_tmap(&q.tmB[g], p->Wp[s], true, p->K, p->N, Kp, bn));
+    else if (pack) VQA_TRY(operand_tmap(&q.tmB[g], wpk + (size_t)s * p->N * Kp, true, p->K, p->N, Kp, bn));
+    else VQA_TRY(operand_tmap(&q.tmB[g], p->W[s], true, p->K, p->N, p->K, bn));
+    q.epi.dX[g] = p->dX[s]; q.epi.ld[g] = p->lddx[s];
+  }
+  q.M = (int)p->M; q.N = (int)p->K; q.K = (int)p->N; q.a_mn = 0; q.b_mn = 1;
+  q.k_splits = pick_splits(cdiv(p->M, BM) * cdiv(p->K, bn) * p->groups, p->N);
+  q.drop_on = 0;
+  fill_drop(q.drop, q.gd, 0.0f, p->seed, p->layer, p->drop_index_base, p->groups);
+  q.epi.accumulate = p->accumulate_x;
+  q.epi.atomic = q.k_splits > 1;
+  if (q.epi.atomic && !p->accumulate_x)
+    for (int g = 0; g < p->groups; ++g)
+      if (p->dX[g]) zero_window(p->dX[g], p->lddx[g], p->M, p->K, st);
+  q.epi.drop_on = p->p > 0.0f;
+  fill_drop(q.epi.drop, q.epi.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
+  q.epi.drop_ld = p->K;
+  for (int g = 0; g < MAXG; ++g) q.epi.bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
+  if constexpr (POOL) {
+    q.epi.pool_alpha = p->pool_alpha; q.epi.pool_dp = p->pool_dpooled;
+    q.epi.pool_regions = p->pool_regions; q.epi.pool_ld = p->K;
+  }
+  return launch(q, p->groups, x3, st, "tc_linear_bwd.dgrad");
+}
+
 int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
   using namespace tc;
   if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return VQA_TC_UNSUPPORTED;
@@ -626,32 +707,8 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
     VQA_TRY(launch(q, p->groups, x3, st, "tc_linear_bwd.wgrad"));
   }
   // 3. dgrad: dX[M, K_in] = dZ[M, N_out] . W[N_out, K_in]   (W is the MN-major B operand as stored)
-  if (any_x) {
-    Params<EpiDgrad> q = {};
-    const int bn = pick_bn(p->K);
-    for (int g = 0; g < MAXG; ++g) {
-      const int s = g < p->groups ? g : 0;
-      VQA_TRY(operand_tmap(&q.tmA[g], dz + (size_t)s * p->M * ldz, false, p->M, p->N, ldz, BM));
-      if (prepacked) VQA_TRY(operand_tmap(&q.tmB[g], p->Wp[s], true, p->K, p->N, Kp, bn));
-      else if (pack) VQA_TRY(operand_tmap(&q.tmB[g], wpk + (size_t)s * p->N * Kp, true, p->K, p->N, Kp, bn));
-      else VQA_TRY(operand_tmap(&q.tmB[g], p->W[s], true, p->K, p->N, p->K, bn));
-      q.epi.dX[g] = p->dX[s]; q.epi.ld[g] = p->lddx[s];
-    }
-    q.M = (int)p->M; q.N = (int)p->K; q.K = (int)p->N; q.a_mn = 0; q.b_mn = 1;
-    q.k_splits = pick_splits(cdiv(p->M, BM) * cdiv(p->K, bn) * p->groups, p->N);
-    q.drop_on = 0;
-    fill_drop(q.drop, q.gd, 0.0f, p->seed, p->layer, p->drop_index_base, p->groups);
-    q.epi.accumulate = p->accumulate_x;
-    q.epi.atomic = q.k_splits > 1;
-    if (q.epi.atomic && !p->accumulate_x)
-      for (int g = 0; g < p->groups; ++g)
-        if (p->dX[g]) zero_window(p->dX[g], p->lddx[g], p->M, p->K, st);
-    q.epi.drop_on = p->p > 0.0f;
-    fill_drop(q.epi.drop, q.epi.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
-    q.epi.drop_ld = p->K;
-    for (int g = 0; g < MAXG; ++g) q.epi.bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
-    VQA_TRY(launch(q, p->groups, x3, st, "tc_linear_bwd.dgrad"));
-  }
+  if (any_x) return p->pool_alpha ? dgrad_launch<true>(p, dz, wpk, ldz, Kp, pack, prepacked, x3, st)
+                                  : dgrad_launch<false>(p, dz, wpk, ldz, Kp, pack, prepacked, x3, st);
   return VQA_OK;
 }
 

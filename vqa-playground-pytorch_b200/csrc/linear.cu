@@ -100,11 +100,17 @@ struct WT_Loader {          // dgrad B'(n'=k, k'=n) = W[n,k]: contiguous along n
 };
 struct DgradStore {
   MutPtrTable dX; I64Table ld; DropTable dt; Drop d; int64_t K; int accumulate;
+  const float* pool_alpha; const float* pool_dp; int64_t pool_regions;     // optional pooling-gradient addend
   float* dx; int64_t l;
   __device__ void select(int z) { dx = dX.p[z]; l = ld.v[z]; d.layer = dt.layer[z]; d.base = dt.base[z]; }
   __device__ void operator()(int64_t m, int64_t k, float acc) const {
     if (!dx) return;
-    const float v = d.on ? acc * d.mul((uint64_t)(m * K + k)) : acc;
+    float v = d.on ? acc * d.mul((uint64_t)(m * K + k)) : acc;
+    if (pool_alpha) {
+      const float* dp = pool_dp + (m / pool_regions) * 4 * K + k;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) v = fmaf(pool_alpha[m * 4 + g], dp[g * K], v);
+    }
     float* dst = dx + m * l + k;
     *dst = accumulate ? *dst + v : v;
   }
@@ -181,6 +187,10 @@ extern "C" int vqa_linear_bwd(const vqa_linear_bwd_params* p, void* stream) {
     any_w |= (p->dW[g] != nullptr) || (p->db[g] != nullptr);
     any_x |= (p->dX[g] != nullptr);
   }
+  if (p->pool_alpha)
+    VQA_REQUIRE(p->groups == 1 && p->dX[0] && p->pool_dpooled && p->pool_regions >= 1 && p->M % p->pool_regions == 0 &&
+                    p->K % 4 == 0,
+                "vqa_linear_bwd: the pooling addend needs one group, dX, K %% 4 == 0 and M a multiple of pool_regions");
   if (p->M == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->math != VQA_MATH_FP32_SIMT) {
@@ -203,6 +213,7 @@ extern "C" int vqa_linear_bwd(const vqa_linear_bwd_params* p, void* stream) {
   if (any_x) {
     Dz_Loader a; WT_Loader b; DgradStore e;
     a.act = p->act; b.K = p->K; e.K = p->K; e.accumulate = p->accumulate_x;
+    e.pool_alpha = p->pool_alpha; e.pool_dp = p->pool_dpooled; e.pool_regions = p->pool_regions;
     e.d = make_drop(p->p, p->seed, 0, 0, 1, p->seed_dev);
     for (int g = 0; g < VQA_MAX_GROUPS; ++g) {
       const int s = g < p->groups ? g : 0;

@@ -191,7 +191,8 @@ static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
 static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
                    const int64_t* ldx, const int* widx, const float* const* Y, const int64_t* ldy,
                    const float* const* dY, const int64_t* lddy, float* const* dX, const int64_t* lddx, int accumulate_x,
-                   const uint32_t* layer, const uint8_t* bits = nullptr, const float* const* Wp = nullptr) {
+                   const uint32_t* layer, const uint8_t* bits = nullptr, const float* const* Wp = nullptr,
+                   const float* pool_alpha = nullptr, const float* pool_dpooled = nullptr, int64_t pool_regions = 0) {
   vqa_linear_bwd_params lp = {};
   lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
   lp.p = c.pdrop(); lp.seed = c.p->seed; lp.seed_dev = c.p->seed_dev; lp.accumulate_w = c.accumulate; lp.accumulate_x = accumulate_x;
@@ -205,6 +206,7 @@ static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
     lp.Wp[g] = (Wp && c.packed) ? Wp[g] : nullptr;
   }
   lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
+  lp.pool_alpha = pool_alpha; lp.pool_dpooled = pool_dpooled; lp.pool_regions = pool_regions;
   return vqa_linear_bwd(&lp, c.stream);
 }
 
@@ -464,15 +466,16 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     ap.accumulate_w = acc; ap.accumulate_x = 0;
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.x = p->v2; ap.alpha = p->alpha2; ap.dpooled = w.dpooled2;
     ap.dalpha0_ext = nullptr; ap.dalpha = w.dalpha2; ap.dz = w.dz2;
-    ap.dWc = c.grad(ATT2_CONV); ap.dbc = c.grad(ATT2_CONV + 1); ap.dfuse = w.dfuse2; ap.dx = w.dv2;
+    ap.dWc = c.grad(ATT2_CONV); ap.dbc = c.grad(ATT2_CONV + 1); ap.dfuse = w.dfuse2;
+    ap.dx = nullptr;             // the pooling's share of dv2 is added by compress_v2's dgrad epilogue below
     { ProfScope ps_(stream, "att2.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
   { ProfScope ps_(stream, "fusion_vq2.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, F, w.d_f2_H2, w.dv2l, HP, w.dql, HP, 0, w.vq2_w1p, w.vq2_w2p)); }
-  {  // compress_v2: dgrad accumulates into dv2 (v2 feeds both compress_v2 and att2's pooling)
+  {  // compress_v2: v2 feeds both compress_v2 and att2's pooling; the dgrad store adds sum_g alpha2 * dpooled2
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; const float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {HP};
     float* dX[1] = {w.dv2}; int64_t lddx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V2};
-    { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 1, layer, w.bits_v2)); }
+    { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, w.bits_v2, nullptr, p->alpha2, w.dpooled2, N)); }
   }
   // ---- att1 branch: the glimpse linears (side lane) initialise dpooled1, then the compound objects add to it
   Lanes::wait(ms, e_g1);

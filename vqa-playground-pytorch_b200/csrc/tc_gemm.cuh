@@ -369,33 +369,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       const uint8_t* __restrict__ bits = p.drop_bits[g];
       constexpr int A_CH = A_TILE_BYTES / 16 / XFORM_THREADS;                       // 4
       constexpr int B_CH = (C::B_TILE_BYTES / 16 + XFORM_THREADS - 1) / XFORM_THREADS;
+      // Packed keep-bits: the byte holding the 4 mask bits of chunk i at k-block kb sits at bit_ptr[i] + kb * bit_step
+      // (the element index is affine in the k coordinate and k-blocks start on multiples of 32 elements), so the
+      // index arithmetic is done once here.  The bytes of k-block it+1 are requested while k-block it is processed.
+      const uint8_t* bit_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+      uint32_t bit_sh[4] = {0, 0, 0, 0};
+      int bit_klim[4] = {0, 0, 0, 0};           // chunk i is inside the tensor while k0 < bit_klim[i]
+      int64_t bit_step = 0;
+      const bool use_bits = p.drop_on && bits != nullptr;
+      if (use_bits) {
+        bit_step = p.a_mn ? (int64_t)(BK / 8) * p.drop_ld : (int64_t)(BK / 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = t + i * XFORM_THREADS;
+          const int pc = ch & 7;
+          int64_t e;
+          bool ok;
+          if (!p.a_mn) {
+            const int r = ch >> 3, cc = (pc ^ (r & 7)) << 2;
+            e = (int64_t)(m0 + r) * p.drop_ld + cc;
+            ok = (m0 + r) < p.drop_rows;
+            bit_klim[i] = ok ? (int)min((int64_t)INT32_MAX, p.drop_ld - cc) : 0;
+          } else {
+            const int j = ch >> 8, r = (ch >> 3) & 31;
+            const int col = m0 + j * 32 + (((((pc >> 1) ^ (r & 3)) << 1) | (pc & 1)) << 2);
+            e = (int64_t)r * p.drop_ld + col;
+            ok = col < p.drop_ld;
+            bit_klim[i] = ok ? (int)min((int64_t)INT32_MAX, p.drop_rows - r) : 0;
+          }
+          bit_ptr[i] = bits + (e >> 3);
+          bit_sh[i] = (uint32_t)(e & 4);
+        }
+      }
+      uint32_t kbyte[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu}, kbyte_next[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu};
+      auto fetch_bits = [&](int it, uint32_t (&dst)[4]) {
+        const int kb = kb_begin + it;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = (kb * BK < bit_klim[i]) ? (uint32_t)__ldg(bit_ptr[i] + (int64_t)kb * bit_step) : 0xFFu;
+      };
+      if (use_bits && nkb > 0) fetch_bits(0, kbyte);
       for (int it = 0; it < nkb; ++it) {
         const int s = it % NR, l = it % NL;
         const uint32_t ph = (it / NR) & 1;
         const int k0 = (kb_begin + it) * BK;
-        // keep-bits of this thread's 4 chunks, fetched BEFORE waiting for the tile so the loads overlap the wait
-        uint32_t nib[4] = {0xFu, 0xFu, 0xFu, 0xFu};
-        if (p.drop_on && bits) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int ch = t + i * XFORM_THREADS;
-            const int pc = ch & 7;
-            int64_t row, col;
-            if (!p.a_mn) {
-              const int r = ch >> 3;
-              row = m0 + r;
-              col = k0 + ((pc ^ (r & 7)) << 2);
-            } else {
-              const int j = ch >> 8, r = (ch >> 3) & 31;
-              row = k0 + r;
-              col = m0 + j * 32 + (((((pc >> 1) ^ (r & 3)) << 1) | (pc & 1)) << 2);
-            }
-            if (row < p.drop_rows && col < p.drop_ld) {
-              const uint64_t e = (uint64_t)(row * p.drop_ld + col);
-              nib[i] = ((uint32_t)__ldg(bits + (e >> 3)) >> (uint32_t)(e & 4)) & 0xFu;
-            }
-          }
-        }
+        if (use_bits && it + 1 < nkb) fetch_bits(it + 1, kbyte_next);
         if (X3) mbar_wait(&lo_empty[l], ((it / NL) & 1) ^ 1);     // lo slot free (MMAs of k-block it-NL done)
         mbar_wait(&full[s], ph);
         if (!(p.debug & 1)) {
@@ -404,13 +422,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
           float4 v[A_CH];
 #pragma unroll
           for (int i = 0; i < A_CH; ++i) v[i] = lds128(a + (t + i * XFORM_THREADS) * 16);
-          if (p.drop_on && bits) {
+          if (use_bits) {
 #pragma unroll
             for (int i = 0; i < A_CH; ++i) {
-              v[i].x = (nib[i] & 1u) ? v[i].x * d.scale : 0.0f;
-              v[i].y = (nib[i] & 2u) ? v[i].y * d.scale : 0.0f;
-              v[i].z = (nib[i] & 4u) ? v[i].z * d.scale : 0.0f;
-              v[i].w = (nib[i] & 8u) ? v[i].w * d.scale : 0.0f;
+              const uint32_t nb = kbyte[i] >> bit_sh[i];
+              v[i].x = (nb & 1u) ? v[i].x * d.scale : 0.0f;
+              v[i].y = (nb & 2u) ? v[i].y * d.scale : 0.0f;
+              v[i].z = (nb & 4u) ? v[i].z * d.scale : 0.0f;
+              v[i].w = (nb & 8u) ? v[i].w * d.scale : 0.0f;
             }
           } else if (p.drop_on) {
             // The 4 lanes of a quartet hold the 4 chunks of one aligned 64-byte run (= 16 consecutive logical
@@ -495,6 +514,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         }
         fence_proxy_async();
         mbar_arrive(&ready[s]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kbyte[i] = kbyte_next[i];
       }
     }
     // ---- epilogue: two warps per TMEM lane quadrant (warp % 4), each takes half of the column blocks
@@ -520,13 +541,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             sts128(cs + (uint32_t)(row * LDC + cb * 32 + c) * 4u, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
         }
         named_bar_sync(1, XFORM_THREADS);
+        // A thread keeps ONE 4-column group of the tile and walks down its rows, U rows at a time in two phases:
+        // first every global read the functor needs for those rows (old values of a "+=", keep-bits, the
+        // multiplicand of the Mutan product) is issued, then the results are combined and stored.  A
+        // load->use->store chain per row keeps a single DRAM/L2 round trip in flight per thread and made these
+        // epilogues latency-bound.
         constexpr int V4 = BN / 4;
-#pragma unroll 2
-        for (int e = t; e < BM * V4; e += XFORM_THREADS) {
-          const int r = e / V4, c4 = e - r * V4;
-          const int64_t m = (int64_t)m0 + r;
-          const int n = n0 + c4 * 4;
-          if (m < p.M && n < p.N) p.epi.row4(g, split, m, n, p.N, lds128(cs + (uint32_t)(r * LDC + c4 * 4) * 4u));
+        constexpr int RS = XFORM_THREADS / V4;            // rows covered per pass (BN = 160: 16 threads sit out)
+        constexpr int U = Epi::kBatch;
+        const int c4 = t % V4, r0 = t / V4;
+        const int n = n0 + c4 * 4;
+        if (r0 < RS && n < p.N) {
+          typename Epi::Col col;
+          p.epi.column(col, g, split, n, p.N);
+          const int rows = min(BM, p.M - m0);
+#pragma unroll 1
+          for (int rb = r0; rb < rows; rb += RS * U) {
+            typename Epi::Pre pre[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int r = rb + u * RS;
+              if (r < rows) p.epi.preload(pre[u], col, m0 + r);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int r = rb + u * RS;
+              if (r < rows) p.epi.row4(col, m0 + r, lds128(cs + (uint32_t)(r * LDC + c4 * 4) * 4u), pre[u]);
+            }
+          }
         }
       } else {
 #pragma unroll 1

@@ -253,6 +253,8 @@ typedef struct {
   const float* x;        /* [B,N,D] */
   float* alpha;          /* [B,N,G] */
   float* pooled;         /* [B,G,D] */
+  const uint8_t* drop_bits;  /* optional: keep-bits of fuse from vqa_dropout_bits(p, seed, layer, B*N*Ff) — the same
+                                mask as the Philox contract, shared with the backward instead of being regenerated */
 } vqa_region_softmax_pool_fwd_params;
 int vqa_region_softmax_pool_fwd(const vqa_region_softmax_pool_fwd_params* p, void* stream);
 
@@ -278,6 +280,7 @@ typedef struct {
   float* dWc; float* dbc;
   float* dfuse;                /* [B,N,Ff] or NULL */
   float* dx;                   /* [B,N,D] or NULL */
+  const uint8_t* drop_bits;    /* optional, as in the forward */
 } vqa_region_softmax_pool_bwd_params;
 int vqa_region_softmax_pool_bwd(const vqa_region_softmax_pool_bwd_params* p, void* stream);
 

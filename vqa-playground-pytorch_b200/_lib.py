@@ -71,14 +71,16 @@ class PackSegment(C.Structure):
 
 class PoolFwd(C.Structure):
     _fields_ = [("B", i64), ("N", i64), ("Ff", i64), ("D", i64), ("drop", Dropout),
-                ("fuse", fp), ("Wc", fp), ("bc", fp), ("x", fp), ("alpha", fp), ("pooled", fp)]
+                ("fuse", fp), ("Wc", fp), ("bc", fp), ("x", fp), ("alpha", fp), ("pooled", fp),
+                ("drop_bits", fp)]
 
 
 class PoolBwd(C.Structure):
     _fields_ = [("B", i64), ("N", i64), ("Ff", i64), ("D", i64), ("drop", Dropout),
                 ("accumulate_w", C.c_int), ("accumulate_x", C.c_int),
                 ("fuse", fp), ("Wc", fp), ("x", fp), ("alpha", fp), ("dpooled", fp), ("dalpha0_ext", fp),
-                ("dalpha", fp), ("dz", fp), ("dWc", fp), ("dbc", fp), ("dfuse", fp), ("dx", fp)]
+                ("dalpha", fp), ("dz", fp), ("dWc", fp), ("dbc", fp), ("dfuse", fp), ("dx", fp),
+                ("drop_bits", fp)]
 
 
 class CompoundFwd(C.Structure):

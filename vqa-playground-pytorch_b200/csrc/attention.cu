@@ -74,16 +74,18 @@ int launch_pool_fwd(int64_t B, int64_t N, int64_t D, const float* x, const float
 // dalpha[b,i,g] = <dpooled[b,g,:], x[b,i,:]> (+ ext for g=0);  dx[b,i,:] (+)= sum_g alpha[b,i,g] dpooled[b,g,:].
 // The second (and last) pass over x in the backward.  One warp owns RW consecutive regions of one sample and walks the
 // feature axis once: every dpooled vector it fetches (L1/L2-resident, 4*D floats per sample) is used for RW rows, so the
-// streaming read of x, not the re-read of dpooled, sets the pace.  grid = (cdiv(N, 8*RW), B), 8 warps.
+// streaming read of x, not the re-read of dpooled, sets the pace.  grid = (cdiv(N, warps*RW), B); the launcher picks
+// the warp count so that one CTA covers a whole sample when N <= 48 (no nearly-empty tail CTA).
 constexpr int POOL_BWD_RW = 4;
-__global__ void __launch_bounds__(256)
+constexpr int POOL_BWD_MAX_WARPS = 12;
+__global__ void __launch_bounds__(POOL_BWD_MAX_WARPS * 32)
 pool_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* __restrict__ alpha,
                 const float* __restrict__ dpooled, const float* __restrict__ dalpha0_ext, float* __restrict__ dalpha,
                 float* __restrict__ dx, int accumulate_x) {
   constexpr int RW = POOL_BWD_RW;
   const int64_t b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i0 = ((int64_t)blockIdx.x * 8 + warp) * RW;
+  const int64_t i0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * RW;
   if (i0 >= N) return;
   const int nr = N - i0 < RW ? (int)(N - i0) : RW;
   float a[RW][G];
@@ -152,8 +154,10 @@ pool_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* 
 
 int launch_pool_bwd(int64_t B, int64_t N, int64_t D, const float* x, const float* alpha, const float* dpooled,
                     const float* dalpha0_ext, float* dalpha, float* dx, int accumulate_x, cudaStream_t st) {
-  dim3 grid((unsigned)cdiv(N, 8 * POOL_BWD_RW), (unsigned)B);
-  pool_bwd_kernel<<<grid, 256, 0, st>>>(N, D, x, alpha, dpooled, dalpha0_ext, dalpha, dx, accumulate_x);
+  int64_t warps = cdiv(N, POOL_BWD_RW);
+  if (warps > POOL_BWD_MAX_WARPS) warps = 8;
+  dim3 grid((unsigned)cdiv(N, warps * POOL_BWD_RW), (unsigned)B);
+  pool_bwd_kernel<<<grid, (unsigned)(warps * 32), 0, st>>>(N, D, x, alpha, dpooled, dalpha0_ext, dalpha, dx, accumulate_x);
   return check_launch("pool_bwd");
 }
 
@@ -172,7 +176,8 @@ extern "C" int vqa_region_softmax_pool_fwd(const vqa_region_softmax_pool_fwd_par
   VQA_REQUIRE(smem <= 200 * 1024, "vqa_region_softmax_pool_fwd: Ff=%lld too large for shared memory", (long long)p->Ff);
   if (p->B == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev)};
+  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev),
+                 p->drop.p > 0.0f ? p->drop_bits : nullptr};
   auto kern = att_logits_softmax_kernel<FuseGeneric>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<(unsigned)p->B, ATT_THREADS, smem, st>>>(fs, p->N, p->Ff, p->Wc, p->bc, p->alpha);
@@ -194,7 +199,8 @@ extern "C" int vqa_region_softmax_pool_bwd(const vqa_region_softmax_pool_bwd_par
     cudaMemsetAsync(p->dWc, 0, (size_t)G * p->Ff * sizeof(float), st);
     if (p->dbc) cudaMemsetAsync(p->dbc, 0, G * sizeof(float), st);
   }
-  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev)};
+  FuseGeneric fs{p->fuse, p->N, p->Ff, make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev),
+                 p->drop.p > 0.0f ? p->drop_bits : nullptr};
   const int64_t groups = p->B < 2 * (int64_t)sm_count() ? p->B : 2 * (int64_t)sm_count();
   dim3 grid((unsigned)groups, (unsigned)cdiv(p->Ff, ATT_THREADS));
   const size_t smem = (size_t)2 * p->N * G * sizeof(float);

@@ -11,13 +11,26 @@ constexpr int ATT_THREADS = 256;
 // Generic: a materialised [B,N,Ff] tensor with input dropout (MyATT.conv_att, config/CoR2.py:140).
 struct FuseGeneric {
   const float* fuse; int64_t N, Ff; Drop d;
+  const uint8_t* bits;        // optional packed keep-bits (vqa_dropout_bits) of the same mask
   __device__ __forceinline__ float mul(int64_t b, int64_t i, int64_t c) const {
-    return d.mul((uint64_t)((b * N + i) * Ff + c));
+    const uint64_t e = (uint64_t)((b * N + i) * Ff + c);
+    if (bits) return ((__ldg(bits + (e >> 3)) >> (e & 7)) & 1u) ? d.scale : 0.0f;
+    return d.mul(e);
   }
   __device__ __forceinline__ float raw(int64_t b, int64_t i, int64_t c) const { return fuse[(b * N + i) * Ff + c]; }
   // multipliers of 4 consecutive elements c..c+3 of row (b,i)
   __device__ __forceinline__ void mul4(int64_t b, int64_t i, int64_t c, float (&m)[4]) const {
-    d.mul4((uint64_t)((b * N + i) * Ff + c), m);
+    const uint64_t e = (uint64_t)((b * N + i) * Ff + c);
+    if (bits) {
+      const uint32_t sh = (uint32_t)(e & 7);
+      uint32_t w = __ldg(bits + (e >> 3));
+      if (sh > 4) w |= (uint32_t)__ldg(bits + (e >> 3) + 1) << 8;      // the 4 bits straddle two bytes
+      w >>= sh;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] = ((w >> j) & 1u) ? d.scale : 0.0f;
+      return;
+    }
+    d.mul4(e, m);
   }
 };
 // ODA, eval mode: fuse_eff[b,i,k] = vl[b,i,k]*ql[b,k] against Wsum[g,k] = sum_j W[g,j*H+k]

@@ -479,76 +479,72 @@ struct EpiMutan {
   }
 };
 
-// dH1cat[m, r*Fp + f] = dY[m,f] * H2[r, m/rows_per, f] (zero for f >= F), db1_r[f] += column sums.
-// grid = (cdiv(Fp,32), row chunks, R), 256 threads = 8 rows x 32 columns
 struct DbTable { float* p[MAXG]; };
-__global__ void __launch_bounds__(256)
-mutan_dh1_kernel(int64_t M, int64_t F, int64_t Fp, int64_t rows_per, int R, const float* __restrict__ dY, int64_t lddy,
-                 const float* __restrict__ H2, float* __restrict__ dH1cat, DbTable db, int rows_per_cta) {
-  __shared__ float red[8][33];
-  const int r = blockIdx.z;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t f = (int64_t)blockIdx.x * 32 + tx;
-  const int64_t Mh = M / rows_per;
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
-  const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
-  float s = 0.0f;
-  constexpr int U = 4;
-  for (int64_t mb = r0 + ty; mb < r1; mb += 8 * U) {
-    float dy[U], h2[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t m = mb + 8 * u;
-      const bool ok = m < r1 && f < F;
-      dy[u] = ok ? dY[m * lddy + f] : 0.0f;
-      h2[u] = ok ? H2[((int64_t)r * Mh + m / rows_per) * F + f] : 0.0f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t m = mb + 8 * u;
-      if (m < r1) {
-        const float v = dy[u] * h2[u];
-        if (f < Fp) dH1cat[m * (R * Fp) + r * Fp + f] = v;
-        s += v;
-      }
-    }
-  }
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && f < F && db.p[r]) {
-    float t = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][tx];
-    atomicAdd(db.p[r] + f, t);
-  }
-}
 
-// dH2cat[mh, r*Fp + f] = sum_{j<rows_per} dY[mh*rp+j, f] * H1[r, mh*rp+j, f];  db2_r[f] += over mh.
-// grid = (Mh, R)
-__global__ void mutan_dh2cat_kernel(int64_t M, int64_t F, int64_t Fp, int64_t rows_per, int R,
-                                    const float* __restrict__ dY, int64_t lddy, const float* __restrict__ H1,
-                                    float* __restrict__ dH2cat, DbTable db) {
+// Both Mutan gradient operands in one pass over dY (one CTA per (h2 row, rank)):
+//   dH1cat[m, r*Fp + f]  = dY[m,f] * H2[r, mh, f]                     (zero in the pad columns f >= F)
+//   dH2cat[mh, r*Fp + f] = sum_{j<rows_per} dY[mh*rp+j, f] * H1[r, mh*rp+j, f]
+//   db1_r[f] += sum_j dH1cat,  db2_r[f] += dH2cat
+// VEC = 2: columns handled in pairs (needs F, lddy even and 8-byte aligned bases), else one column per thread.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+mutan_dh_kernel(int64_t M, int64_t F, int64_t Fp, int64_t rows_per, int R, const float* __restrict__ dY, int64_t lddy,
+                const float* __restrict__ H1, const float* __restrict__ H2, float* __restrict__ dH1cat,
+                float* __restrict__ dH2cat, DbTable db1, DbTable db2) {
   const int64_t mh = blockIdx.x;
   const int r = blockIdx.y;
-  for (int64_t f = threadIdx.x; f < Fp; f += blockDim.x) {
-    float s = 0.0f;
-    if (f < F) {
-      constexpr int U = 6;
-      for (int64_t j0 = 0; j0 < rows_per; j0 += U) {
-        float dy[U], h1[U];
+  const int64_t Mh = M / rows_per, RF = (int64_t)R * Fp;
+  const float* h1r = H1 + (int64_t)r * M * F;
+  constexpr int U = 6;
+  for (int64_t f = (int64_t)threadIdx.x * VEC; f < Fp; f += 256 * VEC) {
+    const bool ok = f < F;
+    float h2[VEC], acc2[VEC], accb[VEC];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int64_t m = mh * rows_per + j0 + u;
-          const bool ok = j0 + u < rows_per;
-          dy[u] = ok ? dY[m * lddy + f] : 0.0f;
-          h1[u] = ok ? H1[((int64_t)r * M + m) * F + f] : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) s = fmaf(dy[u], h1[u], s);
-      }
-      if (db.p[r]) atomicAdd(db.p[r] + f, s);
+    for (int e = 0; e < VEC; ++e) {
+      h2[e] = ok ? H2[((int64_t)r * Mh + mh) * F + f + e] : 0.0f;
+      acc2[e] = 0.0f; accb[e] = 0.0f;
     }
-    dH2cat[mh * (R * Fp) + r * Fp + f] = s;
+    for (int64_t j0 = 0; j0 < rows_per; j0 += U) {
+      float dy[U][VEC], h1[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t m = mh * rows_per + j0 + u;
+        const bool live = ok && j0 + u < rows_per;
+        if (VEC == 2) {
+          const float2 a = live ? *reinterpret_cast<const float2*>(dY + m * lddy + f) : make_float2(0.f, 0.f);
+          const float2 b = live ? *reinterpret_cast<const float2*>(h1r + m * F + f) : make_float2(0.f, 0.f);
+          dy[u][0] = a.x; dy[u][VEC - 1] = a.y; h1[u][0] = b.x; h1[u][VEC - 1] = b.y;
+        } else {
+          dy[u][0] = live ? dY[m * lddy + f] : 0.0f;
+          h1[u][0] = live ? h1r[m * F + f] : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j0 + u >= rows_per) break;
+        const int64_t m = mh * rows_per + j0 + u;
+        float v[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          v[e] = dy[u][e] * h2[e];
+          accb[e] += v[e];
+          acc2[e] = fmaf(dy[u][e], h1[u][e], acc2[e]);
+        }
+        float* o = dH1cat + m * RF + (int64_t)r * Fp + f;
+        if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(v[0], v[VEC - 1]);
+        else o[0] = v[0];
+      }
+    }
+    float* o2 = dH2cat + mh * RF + (int64_t)r * Fp + f;
+    if (VEC == 2) *reinterpret_cast<float2*>(o2) = make_float2(acc2[0], acc2[VEC - 1]);
+    else o2[0] = acc2[0];
+    if (ok) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (db1.p[r]) atomicAdd(db1.p[r] + f + e, accb[e]);
+        if (db2.p[r]) atomicAdd(db2.p[r] + f + e, acc2[e]);
+      }
+    }
   }
 }
 
@@ -826,15 +822,17 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
     }
   DbTable db1 = {}, db2 = {};
   for (int r = 0; r < R; ++r) { db1.p[r] = p->db1[r]; db2.p[r] = p->db2[r]; }
-  mutan_dh2cat_kernel<<<dim3((unsigned)Mh, (unsigned)R), 256, 0, st>>>(p->M, p->F, Fp, p->rows_per_h2, R, p->dY,
-                                                                       p->lddy, p->H1, w.dh2, db2);
-  VQA_TRY(check_launch("tc_mutan_bwd.dh2"));
   {
-    const int rows_per_cta = 64;
-    dim3 grid((unsigned)cdiv(Fp, 32), (unsigned)cdiv(p->M, rows_per_cta), (unsigned)R);
-    mutan_dh1_kernel<<<grid, 256, 0, st>>>(p->M, p->F, Fp, p->rows_per_h2, R, p->dY, p->lddy, p->H2, w.dh1, db1,
-                                           rows_per_cta);
-    VQA_TRY(check_launch("tc_mutan_bwd.dh1"));
+    const bool vec2 = p->F % 2 == 0 && p->lddy % 2 == 0 && reinterpret_cast<uintptr_t>(p->dY) % 8 == 0 &&
+                      reinterpret_cast<uintptr_t>(p->H1) % 8 == 0;
+    const dim3 grid((unsigned)Mh, (unsigned)R);
+    if (vec2)
+      mutan_dh_kernel<2><<<grid, 256, 0, st>>>(p->M, p->F, Fp, p->rows_per_h2, R, p->dY, p->lddy, p->H1, p->H2, w.dh1,
+                                              w.dh2, db1, db2);
+    else
+      mutan_dh_kernel<1><<<grid, 256, 0, st>>>(p->M, p->F, Fp, p->rows_per_h2, R, p->dY, p->lddy, p->H1, p->H2, w.dh1,
+                                              w.dh2, db1, db2);
+    VQA_TRY(check_launch("tc_mutan_bwd.dh"));
   }
   auto wgrad = [&](const float* X, int64_t ldx, int64_t Krows, int64_t Kin, const float* dHcat, float* const* dW,
                    const char* what) -> int {

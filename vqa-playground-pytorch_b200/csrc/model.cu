@@ -83,6 +83,7 @@ struct Cor2Ws {
   float* lin_ws; size_t lin_ws_bytes;
   float* side_ws; size_t side_ws_bytes;   // scratch of the ops that run on the side lane
   uint8_t *bits_v, *bits_v2;   // packed dropout keep-bits of compress_v / compress_v2 inputs (train mode)
+  uint8_t *bits_f1, *bits_f2;  // ... and of the two conv_att inputs (fuse1 / fuse2)
   float *vq1_w1p, *vq1_w2p, *vq2_w1p, *vq2_w2p, *ff_w1p, *ff_w2p, *eq1p, *eq2p, *clsp;   // vqa_pack_weights copies
   size_t bytes;
 };
@@ -122,6 +123,7 @@ static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N, int64_t C) {
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
   w.side_ws_bytes = (size_t)(8 * B * 2048 + 65536) * sizeof(float); w.side_ws = c.take(8 * B * 2048 + 65536);
   w.bits_v = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16)); w.bits_v2 = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16));
+  w.bits_f1 = reinterpret_cast<uint8_t*>(c.take(M * F / 32 + 16)); w.bits_f2 = reinterpret_cast<uint8_t*>(c.take(M * F / 32 + 16));
   w.vq1_w1p = c.take(2 * FPAD * 312); w.vq1_w2p = c.take(2 * FPAD * 312);
   w.vq2_w1p = c.take(2 * FPAD * 312); w.vq2_w2p = c.take(2 * FPAD * 312);
   w.ff_w1p = c.take(2 * FPAD * 2 * A); w.ff_w2p = c.take(2 * FPAD * 312);
@@ -364,6 +366,8 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     ProfScope ps_(stream, "dropout_bits");
     VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
     VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V2, (uint64_t)M * D, w.bits_v2, stream));
+    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_ATT1_CONV, (uint64_t)M * F, w.bits_f1, stream));
+    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_ATT2_CONV, (uint64_t)M * F, w.bits_f2, stream));
   }
   {  // four 2400->310 question projections in one launch (config/CoR2.py:211,195,196,228)
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
@@ -389,6 +393,7 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
+    ap.drop_bits = p->train ? w.bits_f1 : nullptr;
     ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.bc = c.W[ATT1_CONV + 1]; ap.x = p->v;
     ap.alpha = p->alpha1; ap.pooled = w.pooled1;
     { ProfScope ps_(stream, "att1.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
@@ -411,6 +416,7 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
+    ap.drop_bits = p->train ? w.bits_f2 : nullptr;
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.bc = c.W[ATT2_CONV + 1]; ap.x = p->v2;
     ap.alpha = p->alpha2; ap.pooled = w.pooled2;
     { ProfScope ps_(stream, "att2.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
@@ -463,6 +469,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
+    ap.drop_bits = p->train ? w.bits_f2 : nullptr;
     ap.accumulate_w = acc; ap.accumulate_x = 0;
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.x = p->v2; ap.alpha = p->alpha2; ap.dpooled = w.dpooled2;
     ap.dalpha0_ext = nullptr; ap.dalpha = w.dalpha2; ap.dz = w.dz2;
@@ -497,6 +504,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
+    ap.drop_bits = p->train ? w.bits_f1 : nullptr;
     ap.accumulate_w = acc; ap.accumulate_x = 0;
     ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.dpooled = w.dpooled1;
     ap.dalpha0_ext = w.dalpha_ext; ap.dalpha = w.dalpha1; ap.dz = w.dz1;

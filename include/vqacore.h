@@ -102,6 +102,11 @@ int vqa_pack_weights(const vqa_pack_segment* segs, int nsegs, void* stream);
  * call per 16 elements in every one of them.  out must hold (n + 15) / 16 * 2 bytes. */
 int vqa_dropout_bits(float p, uint64_t seed, const uint64_t* seed_dev, uint32_t layer, uint64_t n, uint8_t* out,
                      void* stream);
+/* The same for several dropout sites of one step in ONE launch (a plan calls it once at its head). */
+typedef struct { uint32_t layer; uint64_t n; uint8_t* out; } vqa_bits_segment;
+#define VQA_MAX_BITS_SEGMENTS 32
+int vqa_dropout_bits_batch(float p, uint64_t seed, const uint64_t* seed_dev, const vqa_bits_segment* segs, int nsegs,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Grouped linear:  Y_g = act( dropout_g(X_g) . W_g^T + b_g ),  g < groups.

@@ -65,6 +65,10 @@ class MutanBwd(C.Structure):
                 ("W1p", fp), ("W2p", fp), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
+class BitsSegment(C.Structure):
+    _fields_ = [("layer", C.c_uint32), ("n", C.c_uint64), ("out", fp)]
+
+
 class PackSegment(C.Structure):
     _fields_ = [("src", fp), ("dst", fp), ("rows", i64), ("rows_pad", i64), ("K", i64)]
 
@@ -122,7 +126,7 @@ class ModelBwd(C.Structure):
 
 
 STRUCTS = {
-    "vqa_dropout": Dropout, "vqa_pack_segment": PackSegment, "vqa_linear_fwd_params": LinearFwd, "vqa_linear_bwd_params": LinearBwd,
+    "vqa_dropout": Dropout, "vqa_pack_segment": PackSegment, "vqa_bits_segment": BitsSegment, "vqa_linear_fwd_params": LinearFwd, "vqa_linear_bwd_params": LinearBwd,
     "vqa_mutan_fwd_params": MutanFwd, "vqa_mutan_bwd_params": MutanBwd,
     "vqa_region_softmax_pool_fwd_params": PoolFwd, "vqa_region_softmax_pool_bwd_params": PoolBwd,
     "vqa_cor_compound_fwd_params": CompoundFwd, "vqa_cor_compound_bwd_params": CompoundBwd,
@@ -143,6 +147,8 @@ SYMBOLS = {
     "vqa_pack_weights": (C.c_int, [C.POINTER(PackSegment), C.c_int, C.c_void_p]),
     "vqa_dropout_bits": (C.c_int, [C.c_float, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p,
                                    C.c_void_p]),
+    "vqa_dropout_bits_batch": (C.c_int, [C.c_float, C.c_uint64, C.c_void_p, C.POINTER(BitsSegment), C.c_int,
+                                         C.c_void_p]),
     "vqa_seed_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vqa_linear_fwd": _OP(LinearFwd), "vqa_linear_bwd": _OP(LinearBwd),
     "vqa_linear_fwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),

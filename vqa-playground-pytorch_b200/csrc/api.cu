@@ -132,6 +132,7 @@ extern "C" size_t vqa_sizeof(const char* name) {
 #define VQA_SZ(T) if (strcmp(name, #T) == 0) return sizeof(T)
   VQA_SZ(vqa_dropout);
   VQA_SZ(vqa_pack_segment);
+  VQA_SZ(vqa_bits_segment);
   VQA_SZ(vqa_linear_fwd_params);
   VQA_SZ(vqa_linear_bwd_params);
   VQA_SZ(vqa_mutan_fwd_params);

@@ -99,6 +99,9 @@ __device__ __forceinline__ void red_add4(float* dst, const float (&o)[4], int nv
   if (nv == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3])
                  : "memory");
+  } else if (nv == 4 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(dst), "f"(o[0]), "f"(o[1]) : "memory");
+    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(dst + 2), "f"(o[2]), "f"(o[3]) : "memory");
   } else {
 #pragma unroll
     for (int e = 0; e < 4; ++e)
@@ -171,15 +174,15 @@ struct EpiWgradT {
   static constexpr int kBatch = 8;
   float* dW[MAXG];
   int64_t ldw;
-  __device__ __forceinline__ void operator()(int g, int, int64_t m, int M, int n0, int N, const float (&v)[32]) const {
-    if (m >= M) return;
-    float* w = dW[g];
-    if (!w) return;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int n = n0 + c;
-      if (n < N) atomicAdd(w + (int64_t)n * ldw + m, v[c]);      // consecutive lanes -> consecutive m: coalesced
-    }
+  struct Row { float* w; int nv; };
+  __device__ __forceinline__ void rowquad(Row& r, int g, int m, int M) const {
+    r.w = dW[g] ? dW[g] + m : nullptr;             // consecutive tile rows m are consecutive addresses of dW[n, :]
+    r.nv = M - m < 4 ? M - m : 4;
+  }
+  __device__ __forceinline__ void col4(const Row& r, int n, const float4 v) const {
+    if (!r.w) return;
+    const float o[4] = {v.x, v.y, v.z, v.w};
+    red_add4(r.w + (int64_t)n * ldw, o, r.nv);
   }
 };
 
@@ -199,12 +202,13 @@ struct EpiDgradT {
   Drop drop;
   GroupDrop gd;
   int64_t drop_ld;
+  int wide_bits;               // drop_ld % 4 != 0: a quad's mask bits may run into the next byte
   const uint8_t* bits[MAXG];
   const float* pool_alpha;      // [M, 4]
   const float* pool_dp;         // [M / pool_regions, 4, pool_ld]
   int64_t pool_regions, pool_ld;
   struct Col { float* x; int64_t ld; int n, nv, first; const uint8_t* bits; const float* dp; uint32_t layer; uint64_t base; };
-  struct PreBase { float old[4]; uint32_t byte; };
+  struct PreBase { float old[4]; uint32_t byte, byte_hi; };
   struct PrePool : PreBase { float4 al; float4 dp[4]; };
   using Pre = typename std::conditional<POOL, PrePool, PreBase>::type;
   __device__ __forceinline__ void column(Col& c, int g, int split, int n, int N) const {
@@ -215,7 +219,11 @@ struct EpiDgradT {
   }
   __device__ __forceinline__ void preload(Pre& r, const Col& c, int m) const {
     if (!c.x) return;
-    if (c.bits) r.byte = __ldg(c.bits + (((uint64_t)m * (uint64_t)drop_ld + (uint64_t)c.n) >> 3));
+    if (c.bits) {            // the quad's 4 mask bits start at bit (e & 7) and may run into the next byte
+      const uint64_t e = (uint64_t)m * (uint64_t)drop_ld + (uint64_t)c.n;
+      r.byte = __ldg(c.bits + (e >> 3));
+      if (wide_bits) r.byte_hi = __ldg(c.bits + (e >> 3) + 1);      // combined at use: no load is waited for here
+    }
     if (accumulate && !atomic) load4(c.x + (int64_t)m * c.ld, r.old, c.nv);
     if constexpr (POOL) {
       r.al = __ldg(reinterpret_cast<const float4*>(pool_alpha) + m);
@@ -229,7 +237,8 @@ struct EpiDgradT {
     float* x = c.x + (int64_t)m * c.ld;
     float o[4] = {v.x, v.y, v.z, v.w};
     if (c.bits) {
-      const uint32_t nb = pre.byte >> (((uint32_t)m * (uint32_t)drop_ld + (uint32_t)c.n) & 4u);
+      const uint32_t nb = (wide_bits ? (pre.byte | (pre.byte_hi << 8)) : pre.byte) >>
+                          (((uint32_t)m * (uint32_t)drop_ld + (uint32_t)c.n) & 7u);
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = ((nb >> j) & 1u) ? o[j] * drop.scale : 0.0f;
     } else if (drop_on) {
@@ -423,17 +432,42 @@ __global__ void pack_segments_kernel(PackSegs a) {
   }
 }
 
+// bit j of the result = (byte j of w >= threshold): per-byte compare, then the four byte MSBs are gathered with one
+// multiply (bit 7 -> 28, 15 -> 29, 23 -> 30, 31 -> 31; the partial products never overlap)
+__device__ __forceinline__ uint32_t keep_nibble(uint32_t w, uint32_t thr4) {
+  return ((__vcmpgeu4(w, thr4) & 0x80808080u) * 0x00204081u) >> 28;
+}
+
 // keep-bits: thread per group of 16 elements -> 2 bytes
 __global__ void dropout_bits_kernel(uint64_t seed, const uint64_t* seed_ptr, uint32_t layer, uint32_t thr,
                                     uint64_t ngroups, uint16_t* __restrict__ out) {
   if (seed_ptr) seed = __ldg(seed_ptr);
+  const uint32_t thr4 = thr * 0x01010101u;
   for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 r = philox_group(seed, layer, g);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-    uint32_t bits = 0;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) bits |= (((w[e >> 2] >> (8 * (e & 3))) & 0xFFu) >= thr ? 1u : 0u) << e;
-    out[g] = (uint16_t)bits;
+    out[g] = (uint16_t)(keep_nibble(r.x, thr4) | (keep_nibble(r.y, thr4) << 4) | (keep_nibble(r.z, thr4) << 8) |
+                        (keep_nibble(r.w, thr4) << 12));
+  }
+}
+
+struct BitSegs {
+  vqa_bits_segment s[VQA_MAX_BITS_SEGMENTS];
+  uint64_t first[VQA_MAX_BITS_SEGMENTS + 1];     // running count of 16-element groups: segment i owns [first[i], first[i+1])
+  int n;
+};
+// one thread per 16-element group of the concatenated segments
+__global__ void dropout_bits_batch_kernel(uint64_t seed, const uint64_t* seed_ptr, uint32_t thr, BitSegs a) {
+  if (seed_ptr) seed = __ldg(seed_ptr);
+  const uint32_t thr4 = thr * 0x01010101u;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.first[a.n]; t += (uint64_t)gridDim.x * blockDim.x) {
+    int i = 0;
+    while (t >= a.first[i + 1]) ++i;
+    const vqa_bits_segment sg = a.s[i];
+    const uint64_t g = t - a.first[i];
+    uint16_t* out = reinterpret_cast<uint16_t*>(sg.out);
+    const uint4 r = philox_group(seed, sg.layer, g);
+    out[g] = (uint16_t)(keep_nibble(r.x, thr4) | (keep_nibble(r.y, thr4) << 4) | (keep_nibble(r.z, thr4) << 8) |
+                        (keep_nibble(r.w, thr4) << 12));
   }
 }
 
@@ -585,7 +619,7 @@ int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
   q.drop_on = p->p > 0.0f;
   fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
   q.drop_ld = p->K; q.drop_rows = p->M;
-  for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
+  for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = p->drop_bits[g < p->groups ? g : 0];
   q.epi.act = p->act;
   q.epi.atomic = q.k_splits > 1;
   if (q.epi.atomic)
@@ -628,8 +662,8 @@ static int dgrad_launch(const vqa_linear_bwd_params* p, float* dz, float* wpk, i
       if (p->dX[g]) zero_window(p->dX[g], p->lddx[g], p->M, p->K, st);
   q.epi.drop_on = p->p > 0.0f;
   fill_drop(q.epi.drop, q.epi.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
-  q.epi.drop_ld = p->K;
-  for (int g = 0; g < MAXG; ++g) q.epi.bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
+  q.epi.drop_ld = p->K; q.epi.wide_bits = (p->K & 3) != 0;
+  for (int g = 0; g < MAXG; ++g) q.epi.bits[g] = p->drop_bits[g < p->groups ? g : 0];
   if constexpr (POOL) {
     q.epi.pool_alpha = p->pool_alpha; q.epi.pool_dp = p->pool_dpooled;
     q.epi.pool_regions = p->pool_regions; q.epi.pool_ld = p->K;
@@ -694,7 +728,7 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
     q.drop_on = p->p > 0.0f;
     fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
     q.drop_ld = p->K; q.drop_rows = p->M;
-    for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = (p->K % 4 == 0) ? p->drop_bits[g < p->groups ? g : 0] : nullptr;
+    for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = p->drop_bits[g < p->groups ? g : 0];
     // split the reduction (over the M rows) so that the grid covers the chip
     q.k_splits = pick_splits_wgrad(cdiv(p->K, BM) * cdiv(p->N, bn) * p->groups, p->M);
     if (!p->accumulate_w)
@@ -903,6 +937,21 @@ int tc_dropout_bits(float pdrop, uint64_t seed, const uint64_t* seed_dev, uint32
   tc::dropout_bits_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed, seed_dev, layer, drop_threshold(pdrop), ngroups,
                                                             reinterpret_cast<uint16_t*>(out));
   return check_launch("dropout_bits");
+}
+
+int tc_dropout_bits_batch(float pdrop, uint64_t seed, const uint64_t* seed_dev, const vqa_bits_segment* segs, int nsegs,
+                          cudaStream_t st) {
+  tc::BitSegs a = {};
+  a.n = nsegs;
+  for (int i = 0; i < nsegs; ++i) {
+    a.s[i] = segs[i];
+    a.first[i + 1] = a.first[i] + (segs[i].n + 15) / 16;
+  }
+  if (a.first[nsegs] == 0) return VQA_OK;
+  uint64_t blocks = (a.first[nsegs] + 255) / 256;
+  if (blocks > 16384) blocks = 16384;
+  tc::dropout_bits_batch_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed, seed_dev, drop_threshold(pdrop), a);
+  return check_launch("dropout_bits_batch");
 }
 
 size_t tc_linear_fwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N) {

@@ -17,6 +17,8 @@ int tc_pack_segments(const vqa_pack_segment* segs, int nsegs, cudaStream_t st);
 int tc_dropout_bits(float pdrop, uint64_t seed, const uint64_t* seed_dev, uint32_t layer, uint64_t n, uint8_t* out,
                     cudaStream_t st);
 int tc_seed_advance(uint64_t* seed_dev, cudaStream_t st);
+int tc_dropout_bits_batch(float pdrop, uint64_t seed, const uint64_t* seed_dev, const vqa_bits_segment* segs, int nsegs,
+                          cudaStream_t st);
 size_t tc_linear_fwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N);
 size_t tc_linear_bwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N);
 

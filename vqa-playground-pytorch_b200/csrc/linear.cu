@@ -148,6 +148,17 @@ extern "C" size_t vqa_linear_bwd_workspace_bytes(int math, int groups, int64_t M
   return tc_linear_bwd_ws(math, groups, M, K, N);
 }
 
+extern "C" int vqa_dropout_bits_batch(float p, uint64_t seed, const uint64_t* seed_dev, const vqa_bits_segment* segs,
+                                      int nsegs, void* stream) {
+  VQA_REQUIRE(segs != nullptr && nsegs >= 0 && nsegs <= VQA_MAX_BITS_SEGMENTS && p >= 0.0f && p < 1.0f,
+              "vqa_dropout_bits_batch: bad argument");
+  for (int i = 0; i < nsegs; ++i)
+    VQA_REQUIRE(segs[i].out != nullptr && reinterpret_cast<uintptr_t>(segs[i].out) % 2 == 0,
+                "vqa_dropout_bits_batch: segment %d needs a 2-byte aligned output", i);
+  if (nsegs == 0) return VQA_OK;
+  return tc_dropout_bits_batch(p, seed, seed_dev, segs, nsegs, (cudaStream_t)stream);
+}
+
 extern "C" int vqa_linear_fwd(const vqa_linear_fwd_params* p, void* stream) {
   VQA_REQUIRE(p != nullptr, "vqa_linear_fwd: null params");
   VQA_REQUIRE(p->groups >= 1 && p->groups <= VQA_MAX_GROUPS, "vqa_linear_fwd: groups=%d out of range", p->groups);

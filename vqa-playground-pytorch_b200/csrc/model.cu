@@ -82,8 +82,8 @@ struct Cor2Ws {
       *dhq2, *dalpha_ext, *dpooled1, *dalpha1, *dz1, *dfuse1, *dvl, *d_f1_H2;
   float* lin_ws; size_t lin_ws_bytes;
   float* side_ws; size_t side_ws_bytes;   // scratch of the ops that run on the side lane
-  uint8_t *bits_v, *bits_v2;   // packed dropout keep-bits of compress_v / compress_v2 inputs (train mode)
-  uint8_t *bits_f1, *bits_f2;  // ... and of the two conv_att inputs (fuse1 / fuse2)
+  uint8_t* bits[32];           // packed dropout keep-bits of every dropout site, by layer id (train mode)
+  int64_t bits_n[32];          // element count of each site
   float *vq1_w1p, *vq1_w2p, *vq2_w1p, *vq2_w2p, *ff_w1p, *ff_w2p, *eq1p, *eq2p, *clsp;   // vqa_pack_weights copies
   size_t bytes;
 };
@@ -122,8 +122,16 @@ static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N, int64_t C) {
   w.dfuse1 = c.take(M * F); w.dvl = c.take(M * HP); w.d_f1_H2 = c.take(2 * B * F);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
   w.side_ws_bytes = (size_t)(8 * B * 2048 + 65536) * sizeof(float); w.side_ws = c.take(8 * B * 2048 + 65536);
-  w.bits_v = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16)); w.bits_v2 = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16));
-  w.bits_f1 = reinterpret_cast<uint8_t*>(c.take(M * F / 32 + 16)); w.bits_f2 = reinterpret_cast<uint8_t*>(c.take(M * F / 32 + 16));
+  {
+    using namespace cor2;
+    for (int i = 0; i < 32; ++i) { w.bits[i] = nullptr; w.bits_n[i] = 0; }
+    w.bits_n[L_COMPRESS_V] = M * D; w.bits_n[L_COMPRESS_V2] = M * D; w.bits_n[L_ATT1_CONV] = M * F; w.bits_n[L_ATT2_CONV] = M * F;
+    for (int l : {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q}) w.bits_n[l] = B * Q;
+    w.bits_n[L_EQ1] = B * H; w.bits_n[L_EQ2] = B * H; w.bits_n[L_CLASSIF] = B * F;
+    for (int g = 0; g < G; ++g) { w.bits_n[L_ATT1_G + g] = B * D; w.bits_n[L_ATT2_G + g] = B * D; }
+    for (int i = 0; i < 32; ++i)
+      if (w.bits_n[i]) w.bits[i] = reinterpret_cast<uint8_t*>(c.take(w.bits_n[i] / 32 + 16));
+  }
   w.vq1_w1p = c.take(2 * FPAD * 312); w.vq1_w2p = c.take(2 * FPAD * 312);
   w.vq2_w1p = c.take(2 * FPAD * 312); w.vq2_w2p = c.take(2 * FPAD * 312);
   w.ff_w1p = c.take(2 * FPAD * 2 * A); w.ff_w2p = c.take(2 * FPAD * 312);
@@ -137,7 +145,8 @@ struct OdaWs {
   float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled, *dalpha, *dz, *dwsum, *dvl, *dql;
   float* lin_ws; size_t lin_ws_bytes;
   float* side_ws; size_t side_ws_bytes;
-  uint8_t* bits_v;
+  uint8_t* bits[32];
+  int64_t bits_n[32];
   float *ff_w1p, *ff_w2p, *clsp;
   size_t bytes;
 };
@@ -154,7 +163,14 @@ static OdaWs carve_oda(void* base, int64_t B, int64_t N, int64_t C) {
   w.dvl = c.take(M * H); w.dql = c.take(B * H);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
   w.side_ws_bytes = (size_t)(8 * B * 2048 + 65536) * sizeof(float); w.side_ws = c.take(8 * B * 2048 + 65536);
-  w.bits_v = reinterpret_cast<uint8_t*>(c.take(M * D / 32 + 16));
+  {
+    using namespace oda;
+    for (int i = 0; i < 32; ++i) { w.bits[i] = nullptr; w.bits_n[i] = 0; }
+    w.bits_n[L_COMPRESS_V] = M * D; w.bits_n[L_COMPRESS_Q] = B * Q; w.bits_n[L_LINEAR_Q] = B * Q; w.bits_n[L_CLASSIF] = B * F;
+    for (int g = 0; g < G; ++g) w.bits_n[L_ATT_G + g] = B * D;
+    for (int i = 0; i < 32; ++i)
+      if (w.bits_n[i]) w.bits[i] = reinterpret_cast<uint8_t*>(c.take(w.bits_n[i] / 32 + 16));
+  }
   w.ff_w1p = c.take(5 * FPAD * A); w.ff_w2p = c.take(5 * FPAD * 312); w.clsp = c.take(C * 512);
   w.bytes = c.off;
   return w;
@@ -169,6 +185,7 @@ struct Ctx {
   int accumulate;
   void* lin_ws; size_t lin_ws_bytes;
   int packed;                 // padded weight copies in the workspace are valid (tensor-core math)
+  uint8_t* const* bits;       // keep-bits by dropout layer id (train mode), else nullptr
   float pdrop() const { return p->train ? P_DROP : 0.0f; }
   float* grad(int idx) const { return dW ? dW[idx] : nullptr; }
 };
@@ -176,14 +193,14 @@ struct Ctx {
 // single or grouped linear forward; weight index widx[g] (bias = widx[g]+1)
 static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
                    const int64_t* ldx, const int* widx, float* const* Y, const int64_t* ldy, const uint32_t* layer,
-                   const uint8_t* bits = nullptr, const float* const* Wp = nullptr) {
+                   const float* const* Wp = nullptr) {
   vqa_linear_fwd_params lp = {};
   lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
   lp.p = c.pdrop(); lp.seed = c.p->seed; lp.seed_dev = c.p->seed_dev;
   for (int g = 0; g < groups; ++g) {
     lp.X[g] = X[g]; lp.ldx[g] = ldx[g]; lp.W[g] = c.W[widx[g]]; lp.b[g] = c.W[widx[g] + 1];
     lp.Y[g] = Y[g]; lp.ldy[g] = ldy[g]; lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
-    lp.drop_bits[g] = (c.p->train && groups == 1) ? bits : nullptr;
+    lp.drop_bits[g] = c.bits ? c.bits[layer[g]] : nullptr;
     lp.Wp[g] = (Wp && c.packed) ? Wp[g] : nullptr;
   }
   lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
@@ -193,7 +210,7 @@ static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
 static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
                    const int64_t* ldx, const int* widx, const float* const* Y, const int64_t* ldy,
                    const float* const* dY, const int64_t* lddy, float* const* dX, const int64_t* lddx, int accumulate_x,
-                   const uint32_t* layer, const uint8_t* bits = nullptr, const float* const* Wp = nullptr,
+                   const uint32_t* layer, const float* const* Wp = nullptr,
                    const float* pool_alpha = nullptr, const float* pool_dpooled = nullptr, int64_t pool_regions = 0) {
   vqa_linear_bwd_params lp = {};
   lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
@@ -204,7 +221,7 @@ static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
     lp.dW[g] = c.grad(widx[g]); lp.db[g] = c.grad(widx[g] + 1);
     lp.dX[g] = dX ? dX[g] : nullptr; lp.lddx[g] = lddx ? lddx[g] : 0;
     lp.layer[g] = layer[g]; lp.drop_index_base[g] = 0;
-    lp.drop_bits[g] = (c.p->train && groups == 1) ? bits : nullptr;
+    lp.drop_bits[g] = c.bits ? c.bits[layer[g]] : nullptr;
     lp.Wp[g] = (Wp && c.packed) ? Wp[g] : nullptr;
   }
   lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
@@ -246,6 +263,15 @@ static int mutan_bwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int
   if (c.packed) { mp.W1p = W1p; mp.W2p = W2p; }
   mp.workspace = c.lin_ws; mp.workspace_bytes = c.lin_ws_bytes;
   return vqa_mutan_bwd(&mp, c.stream);
+}
+
+// one launch for the keep-bits of every dropout site of a plan
+static int make_bits(const vqa_model_fwd_params* p, uint8_t* const* bits, const int64_t* n, void* stream) {
+  vqa_bits_segment s[VQA_MAX_BITS_SEGMENTS];
+  int k = 0;
+  for (int i = 0; i < 32; ++i)
+    if (bits[i] && n[i] > 0) { s[k].layer = (uint32_t)i; s[k].n = (uint64_t)n[i]; s[k].out = bits[i]; ++k; }
+  return vqa_dropout_bits_batch(P_DROP, p->seed, p->seed_dev, s, k, stream);
 }
 
 struct PackList {
@@ -343,7 +369,7 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   using namespace cor2;
   const int64_t B = p->B, N = p->N, M = B * N;
   Cor2Ws w = carve_cor2(p->workspace, B, N, p->C);
-  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT, p->train ? w.bits : nullptr};
   const float* eqp[2] = {w.eq1p, w.eq2p}; const float* clp[1] = {w.clsp}; (void)eqp; (void)clp;
   if (c.packed) {  // every weight whose rows TMA cannot address, packed once for this step's forward AND backward
     ProfScope ps_(stream, "pack_weights");
@@ -362,12 +388,9 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
   Lanes::wait(ss, L->record(ms));
   cudaEvent_t e_ql, e_gates;
-  if (p->train) {  // keep-bits of the two big dropout sites, shared by their fwd GEMM, wgrad GEMM and dgrad epilogue
+  if (p->train) {  // keep-bits of every dropout site of the step, shared by its forward and backward kernels
     ProfScope ps_(stream, "dropout_bits");
-    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
-    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V2, (uint64_t)M * D, w.bits_v2, stream));
-    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_ATT1_CONV, (uint64_t)M * F, w.bits_f1, stream));
-    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_ATT2_CONV, (uint64_t)M * F, w.bits_f2, stream));
+    VQA_TRY(make_bits(p, w.bits, w.bits_n, stream));
   }
   {  // four 2400->310 question projections in one launch (config/CoR2.py:211,195,196,228)
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
@@ -379,13 +402,13 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // gates g1, g2 = sigmoid(310->2048) (config/CoR2.py:195-196)
     const float* X[2] = {w.hq1, w.hq2}; int64_t ldx[2] = {HP, HP}; int widx[2] = {EQ1, EQ2};
     float* Y[2] = {w.g1, w.g2}; int64_t ldy[2] = {D, D}; uint32_t layer[2] = {L_EQ1, L_EQ2};
-    { ProfScope ps_(ss, "gates.fwd"); VQA_TRY(lin_fwd(cs, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer, nullptr, eqp)); }
+    { ProfScope ps_(ss, "gates.fwd"); VQA_TRY(lin_fwd(cs, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, layer, eqp)); }
     e_gates = L->record(ss);
   }
   {  // compress_v (config/CoR2.py:213)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, w.bits_v)); }
+    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
   Lanes::wait(ms, e_ql);      // ql / qf ready
   { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1, F, w.vq1_w1p, w.vq1_w2p)); }   // fusion_vq1 :214
@@ -393,7 +416,7 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
-    ap.drop_bits = p->train ? w.bits_f1 : nullptr;
+    ap.drop_bits = p->train ? w.bits[L_ATT1_CONV] : nullptr;
     ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.bc = c.W[ATT1_CONV + 1]; ap.x = p->v;
     ap.alpha = p->alpha1; ap.pooled = w.pooled1;
     { ProfScope ps_(stream, "att1.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
@@ -409,14 +432,14 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // compress_v2 (:218)
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V2};
-    { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, w.bits_v2)); }
+    { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
   { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2, F, w.vq2_w1p, w.vq2_w2p)); }  // fusion_vq2 :219
   {  // att2 on v2 (:219)
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
-    ap.drop_bits = p->train ? w.bits_f2 : nullptr;
+    ap.drop_bits = p->train ? w.bits[L_ATT2_CONV] : nullptr;
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.bc = c.W[ATT2_CONV + 1]; ap.x = p->v2;
     ap.alpha = p->alpha2; ap.pooled = w.pooled2;
     { ProfScope ps_(stream, "att2.pool.fwd"); VQA_TRY(vqa_region_softmax_pool_fwd(&ap, stream)); }
@@ -426,7 +449,7 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // linear_classif (:236)
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
-    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer, nullptr, clp)); }
+    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer, clp)); }
   }
   return VQA_OK;
 }
@@ -444,7 +467,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     cudaMemsetAsync(bp->grads_flat, 0, bp->grads_flat_bytes, (cudaStream_t)stream);
     acc = 1;
   }
-  Ctx c{p, stream, p->params, bp->grads, acc, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  Ctx c{p, stream, p->params, bp->grads, acc, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT, p->train ? w.bits : nullptr};
   const float* eqp[2] = {w.eq1p, w.eq2p}; const float* clp[1] = {w.clsp}; (void)eqp; (void)clp;
   // Side lane: att1's glimpse linears, the gates and the question projections are off the critical dgrad chain
   // (classif -> fusion_final -> att2 -> fusion_vq2 -> compress_v2 -> compound -> att1 -> fusion_vq1 -> compress_v).
@@ -456,7 +479,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
     float* dX[1] = {w.dxf}; int64_t lddx[1] = {XP}; uint32_t layer[1] = {L_CLASSIF};
-    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, clp)); }
+    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, clp)); }
   }
   { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 2, B, 2 * A, H, 1, w.vf, 2 * A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, XP, w.d_ff_H2, w.dvf, 2 * A, w.dqf, HP, 0, w.ff_w1p, w.ff_w2p)); }
   const cudaEvent_t e_ff = L->record(ms);          // dvf, dqf ready
@@ -469,7 +492,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT2_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
-    ap.drop_bits = p->train ? w.bits_f2 : nullptr;
+    ap.drop_bits = p->train ? w.bits[L_ATT2_CONV] : nullptr;
     ap.accumulate_w = acc; ap.accumulate_x = 0;
     ap.fuse = w.fuse2; ap.Wc = c.W[ATT2_CONV]; ap.x = p->v2; ap.alpha = p->alpha2; ap.dpooled = w.dpooled2;
     ap.dalpha0_ext = nullptr; ap.dalpha = w.dalpha2; ap.dz = w.dz2;
@@ -482,7 +505,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; const float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {HP};
     float* dX[1] = {w.dv2}; int64_t lddx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V2};
-    { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, w.bits_v2, nullptr, p->alpha2, w.dpooled2, N)); }
+    { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, p->alpha2, w.dpooled2, N)); }
   }
   // ---- att1 branch: the glimpse linears (side lane) initialise dpooled1, then the compound objects add to it
   Lanes::wait(ms, e_g1);
@@ -498,13 +521,13 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     int64_t lddy[2] = {D, D}; float* dX[2] = {w.dhq1, w.dhq2}; int64_t lddx[2] = {HP, HP};
     uint32_t layer[2] = {L_EQ1, L_EQ2};
     Lanes::wait(ss, L->record(ms));                // dg1, dg2 ready
-    { ProfScope ps_(ss, "gates.bwd"); VQA_TRY(lin_bwd(cs, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, eqp)); }
+    { ProfScope ps_(ss, "gates.bwd"); VQA_TRY(lin_bwd(cs, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, eqp)); }
   }
   {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT1_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
-    ap.drop_bits = p->train ? w.bits_f1 : nullptr;
+    ap.drop_bits = p->train ? w.bits[L_ATT1_CONV] : nullptr;
     ap.accumulate_w = acc; ap.accumulate_x = 0;
     ap.fuse = w.fuse1; ap.Wc = c.W[ATT1_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.dpooled = w.dpooled1;
     ap.dalpha0_ext = w.dalpha_ext; ap.dalpha = w.dalpha1; ap.dz = w.dz1;
@@ -516,7 +539,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
   {  // compress_v: v is a graph input, no dgrad
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer, w.bits_v)); }
+    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
   {  // the four question projections
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
@@ -539,7 +562,7 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   using namespace oda;
   const int64_t B = p->B, N = p->N, M = B * N;
   OdaWs w = carve_oda(p->workspace, B, N, p->C);
-  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT, p->train ? w.bits : nullptr};
   const float* clp[1] = {w.clsp}; (void)clp;
   if (c.packed) {
     ProfScope ps_(stream, "pack_weights");
@@ -555,12 +578,12 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   Lanes::wait(ss, L->record(ms));               // fork: question projections on the side lane
   if (p->train) {
     ProfScope ps_(stream, "dropout_bits");
-    VQA_TRY(vqa_dropout_bits(P_DROP, p->seed, p->seed_dev, L_COMPRESS_V, (uint64_t)M * D, w.bits_v, stream));
+    VQA_TRY(make_bits(p, w.bits, w.bits_n, stream));
   }
   {  // compress_v (config/ODA.py:211)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, w.bits_v)); }
+    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
   }
   {  // compress_q + linear_q (:214, :233)
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
@@ -581,7 +604,7 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // linear_classif (:239)
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; uint32_t layer[1] = {L_CLASSIF};
-    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer, nullptr, clp)); }
+    { ProfScope ps_(stream, "classif.fwd"); VQA_TRY(lin_fwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, layer, clp)); }
   }
   return VQA_OK;
 }
@@ -599,13 +622,13 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
     cudaMemsetAsync(bp->grads_flat, 0, bp->grads_flat_bytes, (cudaStream_t)stream);
     acc = 1;
   }
-  Ctx c{p, stream, p->params, bp->grads, acc, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT};
+  Ctx c{p, stream, p->params, bp->grads, acc, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT, p->train ? w.bits : nullptr};
   const float* clp[1] = {w.clsp}; (void)clp;
   {
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
     float* dX[1] = {w.dxf}; int64_t lddx[1] = {XP}; uint32_t layer[1] = {L_CLASSIF};
-    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, clp)); }
+    { ProfScope ps_(stream, "classif.bwd"); VQA_TRY(lin_bwd(c, 1, B, F, p->C, VQA_ACT_NONE, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, clp)); }
   }
   { ProfScope ps_(stream, "fusion_final.bwd"); VQA_TRY(mutan_bwd(c, 5, B, A, H, 1, w.vf, A, w.qf, HP, FF_L1, FF_L2, w.ff_H1, w.ff_H2, w.dxf, XP, w.d_ff_H2, w.dvf, A, w.dqf, HP, 0, w.ff_w1p, w.ff_w2p)); }
   { ProfScope ps_(stream, "att.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled, ATT_G, w.vf, w.dvf, A, 0, w.dpooled, L_ATT_G)); }
@@ -622,7 +645,7 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
   {
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer, w.bits_v)); }
+    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
   }
   {
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};

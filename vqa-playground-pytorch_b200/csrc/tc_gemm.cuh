@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       // (the element index is affine in the k coordinate and k-blocks start on multiples of 32 elements), so the
       // index arithmetic is done once here.  The bytes of k-block it+1 are requested while k-block it is processed.
       const uint8_t* bit_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
-      uint32_t bit_sh[4] = {0, 0, 0, 0};
+      uint32_t bit_sh[4] = {0, 0, 0, 0};         // first mask bit of the chunk inside its byte; > 4: runs into the next
       int bit_klim[4] = {0, 0, 0, 0};           // chunk i is inside the tensor while k0 < bit_klim[i]
       int64_t bit_step = 0;
       const bool use_bits = p.drop_on && bits != nullptr;
@@ -398,22 +398,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             bit_klim[i] = ok ? (int)min((int64_t)INT32_MAX, p.drop_rows - r) : 0;
           }
           bit_ptr[i] = bits + (e >> 3);
-          bit_sh[i] = (uint32_t)(e & 4);
+          bit_sh[i] = (uint32_t)(e & 7);
         }
       }
+      // rows that are not a multiple of 4 elements long put some quads across a byte boundary: those launches fetch
+      // the following byte as well (kept apart until use so that no load is waited for inside the fetch)
+      const bool wide_bits = use_bits && (p.drop_ld & 3) != 0;
       uint32_t kbyte[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu}, kbyte_next[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu};
-      auto fetch_bits = [&](int it, uint32_t (&dst)[4]) {
+      uint32_t khigh[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu}, khigh_next[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu};
+      auto fetch_bits = [&](int it, uint32_t (&dst)[4], uint32_t (&dsth)[4]) {
         const int kb = kb_begin + it;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          dst[i] = (kb * BK < bit_klim[i]) ? (uint32_t)__ldg(bit_ptr[i] + (int64_t)kb * bit_step) : 0xFFu;
+        for (int i = 0; i < 4; ++i) {
+          const uint8_t* bp = bit_ptr[i] + (int64_t)kb * bit_step;
+          const bool in = kb * BK < bit_klim[i];
+          dst[i] = in ? (uint32_t)__ldg(bp) : 0xFFu;
+          if (wide_bits) dsth[i] = in ? (uint32_t)__ldg(bp + 1) : 0xFFu;
+        }
       };
-      if (use_bits && nkb > 0) fetch_bits(0, kbyte);
+      if (use_bits && nkb > 0) fetch_bits(0, kbyte, khigh);
       for (int it = 0; it < nkb; ++it) {
         const int s = it % NR, l = it % NL;
         const uint32_t ph = (it / NR) & 1;
         const int k0 = (kb_begin + it) * BK;
-        if (use_bits && it + 1 < nkb) fetch_bits(it + 1, kbyte_next);
+        if (use_bits && it + 1 < nkb) fetch_bits(it + 1, kbyte_next, khigh_next);
         if (X3) mbar_wait(&lo_empty[l], ((it / NL) & 1) ^ 1);     // lo slot free (MMAs of k-block it-NL done)
         mbar_wait(&full[s], ph);
         if (!(p.debug & 1)) {
@@ -425,7 +433,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
           if (use_bits) {
 #pragma unroll
             for (int i = 0; i < A_CH; ++i) {
-              const uint32_t nb = kbyte[i] >> bit_sh[i];
+              const uint32_t nb = (wide_bits ? (kbyte[i] | (khigh[i] << 8)) : kbyte[i]) >> bit_sh[i];
               v[i].x = (nb & 1u) ? v[i].x * d.scale : 0.0f;
               v[i].y = (nb & 2u) ? v[i].y * d.scale : 0.0f;
               v[i].z = (nb & 4u) ? v[i].z * d.scale : 0.0f;
@@ -515,7 +523,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         fence_proxy_async();
         mbar_arrive(&ready[s]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) kbyte[i] = kbyte_next[i];
+        for (int i = 0; i < 4; ++i) { kbyte[i] = kbyte_next[i]; khigh[i] = khigh_next[i]; }
       }
     }
     // ---- epilogue: two warps per TMEM lane quadrant (warp % 4), each takes half of the column blocks
@@ -571,11 +579,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
           }
         }
       } else {
+        // Transposed output (wgrad: the tile row index is the CONTIGUOUS index of the destination): the accumulator
+        // is staged column-major, then every thread adds 4 consecutive rows of one column with a single 16-byte
+        // reduction.  Scalar reds cost ~1.3 issue cycles per lane on the SM (20480 of them per tile was most of a
+        // small wgrad launch); the vector form moves 4 values per lane-op.
+        constexpr int LDT = BM + 4;
+        static_assert(BN * LDT * 4 <= C::TILE_BYTES, "transposed staging reuses the ring");
+        const uint32_t cs = smem_u32(smem);
 #pragma unroll 1
         for (int cb = cb0; cb < cb1; ++cb) {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
-          p.epi(g, split, (int64_t)m0 + row, p.M, n0 + cb * 32, p.N, v);
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(cs + (uint32_t)((cb * 32 + c) * LDT + row) * 4u), "f"(v[c]) : "memory");
+        }
+        named_bar_sync(1, XFORM_THREADS);
+        const int mq = t & 31;                             // 32 row-quads span the 128 tile rows
+        const int m = m0 + mq * 4;
+        if (m < p.M) {
+          typename Epi::Row rw;
+          p.epi.rowquad(rw, g, m, p.M);
+#pragma unroll 4
+          for (int cc = t >> 5; cc < BN; cc += XFORM_THREADS / 32) {
+            const int n = n0 + cc;
+            if (n < p.N) p.epi.col4(rw, n, lds128(cs + (uint32_t)(cc * LDT + mq * 4) * 4u));
+          }
         }
       }
     }

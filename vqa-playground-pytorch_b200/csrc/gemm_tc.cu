@@ -126,6 +126,7 @@ __device__ __forceinline__ void load4(const float* src, float (&o)[4], int nv) {
 // zeroed Y with red.global.add, split 0 contributes the bias, and the activation is applied afterwards by
 // act_inplace_kernel.
 struct EpiBiasAct {
+  static constexpr bool kOcc2 = false;
   static constexpr bool kStaged = true;
   static constexpr int kBatch = 8;
   float* Y[MAXG];
@@ -170,6 +171,7 @@ __global__ void act_inplace_kernel(ActArgs a, int64_t M, int64_t N, int act) {
 // wgrad: D'(m' = input feature k, n' = output feature n) accumulated into dW[n, k] (row stride ldw) with
 // red.global.add (split-K partials and the "+=" of a flat gradient buffer are the same operation).
 struct EpiWgradT {
+  static constexpr bool kOcc2 = false;
   static constexpr bool kStaged = false;
   static constexpr int kBatch = 8;
   float* dW[MAXG];
@@ -192,6 +194,7 @@ struct EpiWgradT {
 // pooling backward and a read-modify-write here.
 template <bool POOL>
 struct EpiDgradT {
+  static constexpr bool kOcc2 = false;
   static constexpr bool kStaged = true;
   static constexpr int kBatch = POOL ? 4 : 8;
   float* dX[MAXG];
@@ -270,12 +273,22 @@ struct EpiDgradT {
 using EpiDgrad = EpiDgradT<false>;
 
 // ------------------------------------------------------------------------------------------ launch
-template <int BN, bool X3, class Epi>
-static int launch_cfg(const Params<Epi>& p, int groups, cudaStream_t st, const char* what) {
-  using C = Cfg<BN, X3>;
-  auto kern = tc_gemm_kernel<BN, X3, Epi>;
+static int occ2_mode() {                 // VQA_TC_OCC2=0 disables the two-CTAs-per-SM variant (experiments)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VQA_TC_OCC2");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
+template <int BN, bool X3, class Epi, int OCC>
+static int launch_occ(const Params<Epi>& p, int groups, cudaStream_t st, const char* what) {
+  using C = Cfg<BN, X3, OCC>;
+  auto kern = tc_gemm_kernel<BN, X3, Epi, OCC>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
     return check_launch(what);
+  if (OCC == 2) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.N, BN), (unsigned)(groups * p.k_splits));
   // cluster = CM adjacent m-tiles x CN adjacent n-tiles sharing operand tiles by TMA multicast
   unsigned cm = 1, cn = 1;
@@ -289,6 +302,19 @@ static int launch_cfg(const Params<Epi>& p, int groups, cudaStream_t st, const c
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return check_launch(what);
   return check_launch(what);
+}
+
+template <int BN, bool X3, class Epi>
+static int launch_cfg(const Params<Epi>& p, int groups, cudaStream_t st, const char* what) {
+  // more than one wave of CTAs: two smaller CTAs per SM overlap each other's prologue / epilogue
+  // (measured: Mutan forward -8 us per launch; the dgrad epilogues spill at 102 registers and lose 50 us, so the
+  // variant is only built for the epilogues that declare kOcc2)
+  if constexpr (Epi::kOcc2) {
+    const int64_t ctas = cdiv(p.M, BM) * cdiv(p.N, BN) * groups * p.k_splits;
+    if (ctas > sm_count() && occ2_mode() && max_cm() <= 1 && max_cn() <= 1)
+      return launch_occ<BN, X3, Epi, 2>(p, groups, st, what);
+  }
+  return launch_occ<BN, X3, Epi, 1>(p, groups, st, what);
 }
 
 static inline int pick_bn(int64_t N) {
@@ -476,6 +502,7 @@ __global__ void dropout_bits_batch_kernel(uint64_t seed, const uint64_t* seed_pt
 // Non-atomic mode runs rank by rank in stream order (r == 0 stores, r > 0 read-modify-writes Y);
 // atomic mode (k-splits, small M) accumulates every partial into zeroed Y / H1 with red.global.add.
 struct EpiMutan {
+  static constexpr bool kOcc2 = true;
   static constexpr bool kStaged = true;
   static constexpr int kBatch = 8;
   const float* bias[MAXG]; const float* H2[MAXG]; float* H1[MAXG]; float* Y;

@@ -204,13 +204,16 @@ struct Params {
 // Shared-memory rings.  The TMA-landed ("raw") tiles are prefetched NS_RAW deep to cover the L2/HBM latency;
 // the 3xTF32 residual ("lo") tiles are produced by the transform warps just ahead of the MMA and only need
 // NS_LO = 2 slots, which is what lets the raw ring be deep despite the 227 KB limit.
-template <int BN, bool X3>
+// OCC = 2 is the two-CTAs-per-SM variant for launches of more than one wave: half the shared memory each (2 raw
+// stages + 1 residual slot), so that the prologue/epilogue of one CTA overlaps the main loop of its neighbour; the
+// SM as a whole still has 4 raw stages in flight.
+template <int BN, bool X3, int OCC = 1>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BN * 128;
   static constexpr int RAW_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int LO_BYTES = X3 ? RAW_BYTES : 0;
-  static constexpr int NS_LO = X3 ? 2 : 0;
-  static constexpr int BUDGET = 220 * 1024;
+  static constexpr int NS_LO = X3 ? (OCC == 2 ? 1 : 2) : 0;
+  static constexpr int BUDGET = OCC == 2 ? 110 * 1024 : 220 * 1024;
   static constexpr int NS_RAW_ = (BUDGET - NS_LO * LO_BYTES) / RAW_BYTES;
   static constexpr int NS_RAW = NS_RAW_ > 6 ? 6 : NS_RAW_;
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 256 ? 256 : 512)));
@@ -218,7 +221,8 @@ struct Cfg {
   static constexpr int SMEM_BYTES = TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(NS_RAW >= 2, "tile too large");
   static_assert(BN % 32 == 0 && BN <= 256, "BN");
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(SMEM_BYTES <= 227 * 1024 / OCC, "shared memory budget");
+  static_assert(OCC == 1 || TMEM_COLS <= 256, "two resident CTAs share the 512 TMEM columns");
 };
 
 // split a 16-byte chunk in place into tf32-representable hi and the fp32 residual lo
@@ -233,9 +237,9 @@ __device__ __forceinline__ void split4(float4& v, float4& lo) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int BN, bool X3, class Epi>
-__global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ Params<Epi> p) {
-  using C = Cfg<BN, X3>;
+template <int BN, bool X3, class Epi, int OCC = 1>
+__global__ void __launch_bounds__(NUM_THREADS, OCC) tc_gemm_kernel(const __grid_constant__ Params<Epi> p) {
+  using C = Cfg<BN, X3, OCC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int NR = C::NS_RAW, NL = C::NS_LO > 0 ? C::NS_LO : 1;
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         // epilogues latency-bound.
         constexpr int V4 = BN / 4;
         constexpr int RS = XFORM_THREADS / V4;            // rows covered per pass (BN = 160: 16 threads sit out)
-        constexpr int U = Epi::kBatch;
+        constexpr int U = OCC == 2 && Epi::kBatch > 4 ? 4 : Epi::kBatch;     // 102 registers per thread at OCC = 2
         const int c4 = t % V4, r0 = t / V4;
         const int n = n0 + c4 * 4;
         if (r0 < RS && n < p.N) {

@@ -126,6 +126,44 @@ def op_work(model, B, N, C):
     return w
 
 
+def kernel_roofline(per_kernel, per_op, total, pk, args, B, N, C):
+    """Roofline of the dominant KERNEL of the step: the GEMM launch with the largest average duration (the C ABI
+    records every tensor-core GEMM launch with its shape, 'k:<what> M.. N.. K.. g.. s..'), timed live with CUDA events
+    on the launching stream.  achieved = algorithmic flops of that launch (2*M*N*K per group, ONE pass: the three
+    TF32 passes of the fp32-parity mode are an implementation cost, not work) / its duration; peak = the measured
+    dense bf16 rate.  traffic = dram bytes of the same launch from the committed ncu capture (profiles/), or null."""
+    if per_kernel:
+        top = max(per_kernel, key=per_kernel.get)
+        dims = {t[0]: int(t[1:]) for t in top.split()[1:]}
+        flops = 2.0 * dims["M"] * dims["N"] * dims["K"] * dims["g"]
+        dur = per_kernel[top] * 1e-3
+        ach = flops / dur / 1e12
+        traffic = None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_kernel_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top[2:])
+        return {"kernel": top[2:], "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": ach / pk["tensor"], "traffic": traffic, "ms": per_kernel[top],
+                "share_of_step": per_kernel[top] / total if total else None,
+                "algorithmic_flops": flops,
+                "note": "%s math (3 TF32 passes per product, so <= 1/6 of the bf16 peak is reachable); peak = measured "
+                        "dense bf16 sustained, %s" % (args.precision, pk["src"])}
+    work = op_work(args.model, B, N, C)
+    top = max(per_op, key=per_op.get)
+    kind, amount = work.get(top, ("hbm", 0.0))
+    dur = per_op[top] * 1e-3
+    if kind == "tensor":
+        ach = amount / dur / 1e12
+        return {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": ach / pk["tensor"], "traffic": None, "ms": per_op[top],
+                "share_of_step": per_op[top] / total if total else None,
+                "note": "%s math; peak = measured dense bf16 (sustained), %s" % (args.precision, pk["src"])}
+    ach = amount / dur / 1e9
+    return {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+            "traffic": None, "ms": per_op[top], "share_of_step": per_op[top] / total if total else None,
+            "note": pk["src"]}
+
+
 def make_batch(B, N, C, device, gen):
     v = torch.relu(torch.randn(B, N, D, generator=gen))
     q = 0.1 * torch.relu(torch.randn(B, Q, generator=gen))
@@ -290,7 +328,7 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
     # ---- per-op timing (same step, CUDA events around every plan op) -> roofline of the dominant op
-    roof, breakdown = None, None
+    roof, breakdown, kernels = None, None, None
     nprof = min(args.steps, 10)
     if rank == 0:
         L.vqa_profile_begin()
@@ -301,30 +339,19 @@ def run_ours(args):
     if rank == 0:
         buf = ctypes.create_string_buffer(1 << 16)
         L.vqa_profile_end(buf, len(buf))
-        per_op = {}
+        per_op, per_kernel = {}, {}
         for item in buf.value.decode().split(";"):
             if item:
-                name, rest = item.split("=")
+                name, rest = item.rsplit("=", 1)
                 tot, cnt = rest.split("/")
-                per_op[name] = float(tot) / int(cnt)
+                (per_kernel if name.startswith("k:") else per_op)[name] = float(tot) / int(cnt)
         total = sum(per_op.values())
-        work = op_work(args.model, B, N, C)
         pk = peaks()
         breakdown = {k: round(v, 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])}
-        top = max(per_op, key=per_op.get)
-        kind, amount = work.get(top, ("hbm", 0.0))
-        dur = per_op[top] * 1e-3
-        if kind == "tensor":
-            ach = amount / dur / 1e12
-            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tensor"], "traffic": None,
-                    "note": "%s math; peak = measured dense bf16 (sustained), %s" % (args.precision, pk["src"])}
-        else:
-            ach = amount / dur / 1e9
-            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": ach / pk["hbm"], "traffic": None, "note": pk["src"]}
-        roof["share_of_step"] = per_op[top] / total if total else None
-        roof["ms"] = per_op[top]
+        kernels = {k[2:]: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])[:6]}
+        roof = kernel_roofline(per_kernel, per_op, total, pk, args, B, N, C)
+    if world > 1:
+        dist.barrier()
     if world > 1:
         dist.barrier()
 
@@ -345,7 +372,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "per_op_ms": breakdown,
+            "roofline": roof, "cpu_baseline": cpu, "per_op_ms": breakdown, "top_kernels_ms": kernels,
         }
         print(json.dumps(line))
     if world > 1:

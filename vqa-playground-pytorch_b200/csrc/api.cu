@@ -58,6 +58,7 @@ ProfScope::ProfScope(void* stream, const char* name) : idx(-1), st(stream) {
   g_prof.push_back(r);
   idx = (int)g_prof.size() - 1;
 }
+bool prof_active() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
 ProfScope::~ProfScope() {
   if (idx < 0) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -15,6 +15,7 @@ int check_launch(const char* what);          // cudaGetLastError -> VQA_ECUDA
 int sm_count();
 
 // Times one op of a whole-model plan when vqa_profile_begin() is active (no-op otherwise).
+bool prof_active();
 struct ProfScope {
   int idx; void* st;
   ProfScope(void* stream, const char* name);

@@ -300,6 +300,11 @@ static int launch_occ(const Params<Epi>& p, int groups, cudaStream_t st, const c
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cm; attr[0].val.clusterDim.y = cn; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  // per-kernel record for bench.py's roofline ("k:" entries of vqa_profile_end carry the GEMM shape)
+  char label[160] = "k:";
+  if (prof_active())
+    snprintf(label, sizeof(label), "k:%s M%d N%d K%d g%d s%d", what, p.M, p.N, p.K, groups, p.k_splits);
+  ProfScope ps_(st, label);
   if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return check_launch(what);
   return check_launch(what);
 }

@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the CPU oracle sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (default: train mode)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N>1: run the gradient all-reduce after the graph replay instead of capturing it, bucket by "
+                         "bucket, inside the backward")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -222,6 +225,7 @@ def workload_config(args, C):
                                          "stock config/CoR2.py chain (att1 -> compound -> att2)" if args.model == "CoR2"
                                          else "stock config/ODA.py"),
             "precision": args.precision, "parallelism": "dp%d" % args.gpus,
+            "allreduce": getattr(args, "allreduce", "eager, bucketed, overlapped via gradient-group events"),
             "l2": "inputs rotate over 4 distinct batches and each step touches >0.6 GB of activations (> 126 MB L2)"}
 
 
@@ -266,7 +270,19 @@ def run_ours(args):
     if not args.no_graph:
         from vqa_playground_pytorch_b200.engine import GraphedStep
         v0, q0, a0 = resident[0]
-        graphed = GraphedStep(model, {"v": v0.clone(), "q_idxes": q0.clone(), "a": a0.clone()}, engine)
+        example = {"v": v0.clone(), "q_idxes": q0.clone(), "a": a0.clone()}
+        overlap = world > 1 and not args.no_overlap
+        try:
+            graphed = GraphedStep(model, example, engine, capture_collectives=overlap)
+        except Exception as exc:            # capture of the NCCL calls refused: reduce after the replay instead
+            if not overlap:
+                raise
+            print("graph capture with collectives failed (%s); falling back to reduce-after-replay" % exc, file=sys.stderr)
+            torch.cuda.synchronize()
+            overlap = False
+            graphed = GraphedStep(model, example, engine, capture_collectives=False)
+        args.allreduce = ("bucketed NCCL all-reduce captured inside the step graph, overlapped with the backward" if overlap
+                          else "bucketed NCCL all-reduce after the graph replay") if world > 1 else "none (1 GPU)"
 
     def step(v, q, a):
         if graphed is None:
@@ -374,9 +390,16 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "per_op_ms": breakdown, "top_kernels_ms": kernels,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without NCCL's communicator teardown: with collectives captured in a CUDA graph
+        # destroy_process_group() was seen to block until the launcher's timeout.  Everything is measured and
+        # printed at this point; the barrier keeps the ranks together until rank 0 has flushed its line.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

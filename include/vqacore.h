@@ -406,6 +406,7 @@ typedef struct {
   void* workspace; size_t workspace_bytes;
 } vqa_model_fwd_params;
 
+#define VQA_MAX_GRAD_GROUPS 16
 typedef struct {
   vqa_model_fwd_params fwd;  /* same values as the forward call (workspace holds its stash) */
   const float* dlogits;      /* [B,C] */
@@ -415,7 +416,15 @@ typedef struct {
                                 flat buffer); with accumulate == 0 the plan zero-fills it ONCE and lets every
                                 kernel accumulate, instead of one memset per tensor */
   size_t grads_flat_bytes;
+  /* Optional: cudaEvent_t handles recorded as the plan finishes its gradient GROUPS (vqa_grad_groups below), on the
+   * stream that produced the group, so that a data-parallel caller can all-reduce a bucket of the flat buffer
+   * while the rest of the backward is still running.  NULL entries are skipped. */
+  void* group_events[VQA_MAX_GRAD_GROUPS];
 } vqa_model_bwd_params;
+/* Gradient groups of a backward plan in the order they complete: writes group_of_param[i] (i in state_dict order,
+ * n_params entries) and returns the number of groups (<= VQA_MAX_GRAD_GROUPS), or -1 for an unknown model
+ * (0 = CoR2, 1 = ODA) / wrong n_params.  Pure host function (no GPU needed). */
+int vqa_grad_groups(int model, int* group_of_param, int n_params);
 
 size_t vqa_cor2_workspace_bytes(int64_t B, int64_t N, int64_t C);
 int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream);

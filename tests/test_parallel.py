@@ -91,3 +91,19 @@ def _worker(rank, world, port, name, C):
 @pytest.mark.parametrize("name,C", [("CoR2", 2000), ("ODA", 3000)])
 def test_gloo_world_size_2(name, C):
     mp.spawn(_worker, args=(2, _free_port(), name, C), nprocs=2, join=True)
+
+
+def test_completion_order_matches_the_library_groups():
+    """parallel.COMPLETION_ORDER (flat-buffer layout, bucket cuts) must be the grouping the backward plans signal
+    through vqa_model_bwd_params.group_events (vqa_grad_groups; pure host call, no GPU)."""
+    import ctypes as C
+    from vqa_playground_pytorch_b200 import _lib
+    from vqa_playground_pytorch_b200.parallel import COMPLETION_ORDER
+    L = _lib.lib()
+    for model_id, name, n in ((0, "CoR2", 62), (1, "ODA", 38)):
+        tab = (C.c_int * n)()
+        groups = L.vqa_grad_groups(model_id, tab, n)
+        assert groups == len(COMPLETION_ORDER[name])
+        for g, members in enumerate(COMPLETION_ORDER[name]):
+            assert all(tab[i] == g for i in members), (name, g)
+    assert L.vqa_grad_groups(0, (C.c_int * 10)(), 10) == -1

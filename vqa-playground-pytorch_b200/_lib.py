@@ -122,7 +122,7 @@ class ModelFwd(C.Structure):
 
 class ModelBwd(C.Structure):
     _fields_ = [("fwd", ModelFwd), ("dlogits", fp), ("grads", C.POINTER(fp)), ("accumulate", C.c_int),
-                ("grads_flat", fp), ("grads_flat_bytes", C.c_size_t)]
+                ("grads_flat", fp), ("grads_flat_bytes", C.c_size_t), ("group_events", fp * 16)]
 
 
 STRUCTS = {
@@ -150,6 +150,7 @@ SYMBOLS = {
     "vqa_dropout_bits_batch": (C.c_int, [C.c_float, C.c_uint64, C.c_void_p, C.POINTER(BitsSegment), C.c_int,
                                          C.c_void_p]),
     "vqa_seed_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vqa_grad_groups": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int]),
     "vqa_linear_fwd": _OP(LinearFwd), "vqa_linear_bwd": _OP(LinearBwd),
     "vqa_linear_fwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),
     "vqa_linear_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),

@@ -89,15 +89,19 @@ class GraphedStep:
         loss = step(sample)                                   # copies the sample into the static buffers, replays
     """
 
-    def __init__(self, model, example, engine=None, warmup=3, seed=0x5EED0000):
+    def __init__(self, model, example, engine=None, warmup=3, seed=0x5EED0000, capture_collectives=False):
         dev = example["v"].device
         self.model, self.engine = model, engine
         self.static = {k: torch.empty_like(t) for k, t in example.items() if torch.is_tensor(t)}
         for k, t in self.static.items():
             t.copy_(example[k])
         model.seed_device = torch.tensor([seed], dtype=torch.int64, device=dev)
+        # capture_collectives: the bucketed NCCL all-reduces are captured INSIDE the graph, each forked off the backward
+        # at its bucket's gradient-group events, so that communication overlaps the remaining backward kernels of the
+        # same replay.  Otherwise the reduction runs after the replay (nothing to overlap with).
+        self.capture_collectives = bool(capture_collectives) and engine is not None and engine.world_size > 1
         if engine is not None:
-            engine.defer = True                 # no collectives inside the captured region
+            engine.defer = not self.capture_collectives
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -110,7 +114,9 @@ class GraphedStep:
         n0 = _lib.lib().vqa_launch_count()
         # capture on the SAME side stream the warm-up ran on: autograd caches each parameter's gradient-accumulator
         # stream at first use, and a capture that has to wait on another (uncaptured) stream is invalid
-        with torch.cuda.graph(self.graph, stream=side):
+        # NCCL's watchdog thread queries events while we capture: keep the capture check thread-local in that case
+        mode = {"capture_error_mode": "thread_local"} if self.capture_collectives else {}
+        with torch.cuda.graph(self.graph, stream=side, **mode):
             self.loss = self._body()
         self.launches_per_replay = int(_lib.lib().vqa_launch_count() - n0)    # libvqacore kernels inside the graph
 
@@ -123,6 +129,8 @@ class GraphedStep:
             for p in self.model.parameters():
                 p.grad = None
         loss.backward()
+        if self.capture_collectives:
+            self.engine.wait()                  # joins the communication stream back into the capturing stream
         self.logits = out
         return loss
 
@@ -132,7 +140,7 @@ class GraphedStep:
                 if sample[k].data_ptr() != t.data_ptr():
                     t.copy_(sample[k], non_blocking=True)
         self.graph.replay()
-        if self.engine is not None:
-            self.engine.reduce_all()
+        if self.engine is not None and not self.capture_collectives:
+            self.engine.reduce_all(overlapped=False)
             self.engine.wait()
         return self.loss

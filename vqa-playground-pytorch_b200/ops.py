@@ -421,6 +421,8 @@ class ModelCoreFn(torch.autograd.Function):
         _fill_model_params(pr.fwd, B, N, Cc, train, math, seed, vc, qc, ptab, logits, alpha1, alpha2, v2, ws, seed_dev)
         pr.dlogits, pr.grads, pr.accumulate = dlogits.data_ptr(), gtab, accumulate
         pr.grads_flat, pr.grads_flat_bytes = flat.data_ptr(), flat.numel() * 4
+        for k, ev in enumerate(getattr(sink, "group_events", None) or ()):
+            pr.group_events[k] = ev.cuda_event      # recorded by the plan as gradient group k completes
         _lib.check(getattr(L, bwd)(C.byref(pr), _stream()), bwd)
         if sink is not None:
             sink.after_backward()

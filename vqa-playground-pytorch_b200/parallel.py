@@ -93,6 +93,14 @@ class DataParallelEngine(GradSink):
         self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.is_cuda else None
         self._pending = []
         self.defer = False          # True: the caller triggers the reduction itself (engine.GraphedStep)
+        # One CUDA event per gradient group of the backward plan (include/vqacore.h: group_events): the plan records
+        # event k when group k is complete, and bucket b is reduced on the communication stream as soon as the
+        # events of ITS groups have fired - the rest of the backward keeps running underneath.
+        self.group_events = None
+        if self.is_cuda and self.world_size > 1:
+            self.group_events = [torch.cuda.Event() for _ in COMPLETION_ORDER[model.MODEL]]
+            for ev in self.group_events:
+                ev.record()             # creates the handle (torch events are lazy)
         model.grad_sink = self
 
     def broadcast_parameters(self, src=0):
@@ -101,22 +109,28 @@ class DataParallelEngine(GradSink):
             for p in self.model.parameters():
                 dist.broadcast(p.data, src, group=self.group)
 
-    def reduce_bucket(self, k):
-        """All-reduce (SUM) bucket k on the communication stream once the work enqueued so far is done."""
+    def reduce_bucket(self, k, overlapped=True):
+        """All-reduce (SUM) bucket k on the communication stream: after the events of the bucket's gradient groups
+        (overlapped with the rest of the backward), or after everything enqueued so far (overlapped=False)."""
         if self.world_size == 1:
             return
         lo, hi = self.bucket_ranges[k]
         chunk = self.flat[lo:hi]
         if self.is_cuda:
-            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            if overlapped and self.group_events is not None:
+                g0, g1 = self.bucket_groups[k]
+                for g in range(g0, g1):
+                    self.comm_stream.wait_event(self.group_events[g])
+            else:
+                self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         else:
             self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    def reduce_all(self):
+    def reduce_all(self, overlapped=True):
         for k in range(len(self.bucket_ranges)):
-            self.reduce_bucket(k)
+            self.reduce_bucket(k, overlapped)
 
     def after_backward(self):
         # called by ops.ModelCoreFn.backward right after the backward plan has been enqueued
@@ -125,7 +139,7 @@ class DataParallelEngine(GradSink):
 
     def wait(self):
         for w in self._pending:
-            w.wait()
+            w.wait()                # the current stream waits for the collective's end event (capturable)
         self._pending = []
         if self.is_cuda and self.world_size > 1:
             torch.cuda.current_stream().wait_stream(self.comm_stream)

@@ -83,7 +83,9 @@ def linear_forward(xs, ws, bs, act, p, seed, layers, math=0, outs=None, bits=Non
 
 
 def linear_backward(xs, ws, ys, dys, act, p, seed, layers, need_dx, math=0, dws=None, dbs=None, dxs=None,
-                    accumulate_w=False, accumulate_x=False, bits=None):
+                    accumulate_w=False, accumulate_x=False, bits=None, pool=None):
+    """Backward of the grouped linear (vqa_linear_bwd).  pool = (alpha [M,4], dpooled [M/regions,4,K], regions) adds
+    the gradient of an attention pooling over X_0 into the dX_0 store."""
     g = len(xs)
     M, K = xs[0].shape
     N = ws[0].shape[0]
@@ -106,6 +108,8 @@ def linear_backward(xs, ws, ys, dys, act, p, seed, layers, need_dx, math=0, dws=
         pr.dX[i], pr.lddx[i] = _p(dxs[i]), (dxs[i].stride(0) if dxs[i] is not None else K)
         pr.layer[i], pr.drop_index_base[i] = int(layers[i]), 0
         pr.drop_bits[i] = _p(bits[i]) if bits is not None else None
+    if pool is not None:
+        pr.pool_alpha, pr.pool_dpooled, pr.pool_regions = pool[0].data_ptr(), pool[1].data_ptr(), int(pool[2])
     ws = _workspace(_lib.lib().vqa_linear_bwd_workspace_bytes(pr.math, g, M, K, N), dev)
     pr.workspace, pr.workspace_bytes = _p(ws), (ws.numel() if ws is not None else 0)
     _lib.check(_lib.lib().vqa_linear_bwd(C.byref(pr), _stream()), "vqa_linear_bwd")
@@ -123,6 +127,21 @@ def dropout_bits(p, seed, layer, n, device):
     _lib.check(_lib.lib().vqa_dropout_bits(float(p), int(seed), None, int(layer), int(n), out.data_ptr(), _stream()),
                "vqa_dropout_bits")
     return out
+
+
+def dropout_bits_batch(p, seed, sites, device):
+    """Keep-bits of several dropout sites in one launch (vqa_dropout_bits_batch). sites: [(layer, n), ...];
+    returns one uint8 tensor per site (with a few spare bytes, as the kernels that read quads across byte
+    boundaries expect)."""
+    segs = (_lib.BitsSegment * len(sites))()
+    outs = []
+    for i, (layer, n) in enumerate(sites):
+        out = torch.zeros(((n + 15) // 16 * 2 + 4,), device=device, dtype=torch.uint8)
+        segs[i].layer, segs[i].n, segs[i].out = int(layer), int(n), out.data_ptr()
+        outs.append(out)
+    _lib.check(_lib.lib().vqa_dropout_bits_batch(float(p), int(seed), None, segs, len(sites), _stream()),
+               "vqa_dropout_bits_batch")
+    return outs
 
 
 class LinearFn(torch.autograd.Function):

@@ -96,6 +96,7 @@ class GraphedStep:
         for k, t in self.static.items():
             t.copy_(example[k])
         model.seed_device = torch.tensor([seed], dtype=torch.int64, device=dev)
+        self._one = torch.ones((), dtype=torch.float32, device=dev)
         # capture_collectives: the bucketed NCCL all-reduces are captured INSIDE the graph, each forked off the backward
         # at its bucket's gradient-group events, so that communication overlaps the remaining backward kernels of the
         # same replay.  Otherwise the reduction runs after the replay (nothing to overlap with).
@@ -128,7 +129,7 @@ class GraphedStep:
         if self.engine is None:
             for p in self.model.parameters():
                 p.grad = None
-        loss.backward()
+        loss.backward(gradient=self._one)       # preallocated seed gradient: no fill kernel per step
         if self.capture_collectives:
             self.engine.wait()                  # joins the communication stream back into the capturing stream
         self.logits = out

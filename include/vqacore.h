@@ -421,6 +421,34 @@ typedef struct {
    * while the rest of the backward is still running.  NULL entries are skipped. */
   void* group_events[VQA_MAX_GRAD_GROUPS];
 } vqa_model_bwd_params;
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step over the flat gradient buffer: global-norm clipping + Adam in two launches.
+ * Replaces nn.utils.clip_grad_norm_(model.parameters(), 0.25) + torch.optim.Adam.step()
+ * (train.py:82-86; optimizer at train.py:292: lr, betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad):
+ *   clip  = min(1, max_norm / (||grads_flat||_2 + 1e-6))            (max_norm <= 0: no clipping)
+ *   g     = grad * clip;  m += (g - m)(1 - beta1);  v = beta2 v + (1 - beta2) g^2
+ *   param -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * Parameters stay where they are (segs[i].param); gradients and both moment buffers are flat, segment i at
+ * [offset, offset + numel).  Every element of [0, total) must belong to exactly one segment for the norm to be the
+ * norm of the gradients (a data-parallel flat buffer is exactly that).
+ */
+typedef struct { float* param; int64_t offset; int64_t numel; } vqa_param_segment;
+#define VQA_MAX_PARAM_SEGMENTS 64
+typedef struct {
+  int nsegs;
+  const vqa_param_segment* segs;   /* host array */
+  float* grads_flat;               /* [total], 16-byte aligned */
+  float* exp_avg;                  /* [total] first moment  (zero before step 1) */
+  float* exp_avg_sq;               /* [total] second moment */
+  int64_t total;
+  float lr, beta1, beta2, eps;
+  int64_t step;                    /* 1 for the first update */
+  float max_norm;                  /* clip_grad_norm_'s max_norm; <= 0 disables clipping */
+  int write_clipped_grads;         /* 1: grads_flat *= clip as clip_grad_norm_ does in place; 0: leave them */
+  float* scratch;                  /* 1 float of device memory (holds ||g||^2 on return) when clipping */
+} vqa_clip_adam_params;
+int vqa_clip_adam_step(const vqa_clip_adam_params* p, void* stream);
+
 /* Gradient groups of a backward plan in the order they complete: writes group_of_param[i] (i in state_dict order,
  * n_params entries) and returns the number of groups (<= VQA_MAX_GRAD_GROUPS), or -1 for an unknown model
  * (0 = CoR2, 1 = ODA) / wrong n_params.  Pure host function (no GPU needed). */

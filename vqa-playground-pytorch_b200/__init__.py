@@ -9,4 +9,4 @@ host-side mirror of the reference's Python interface for that path.  No CPU fall
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "ops", "blocks", "config", "parallel", "engine"]
+__all__ = ["_lib", "ops", "blocks", "config", "parallel", "engine", "optim"]

@@ -69,6 +69,17 @@ class BitsSegment(C.Structure):
     _fields_ = [("layer", C.c_uint32), ("n", C.c_uint64), ("out", fp)]
 
 
+class ParamSegment(C.Structure):
+    _fields_ = [("param", fp), ("offset", i64), ("numel", i64)]
+
+
+class ClipAdam(C.Structure):
+    _fields_ = [("nsegs", C.c_int), ("segs", C.POINTER(ParamSegment)), ("grads_flat", fp), ("exp_avg", fp),
+                ("exp_avg_sq", fp), ("total", i64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("step", i64), ("max_norm", C.c_float), ("write_clipped_grads", C.c_int),
+                ("scratch", fp)]
+
+
 class PackSegment(C.Structure):
     _fields_ = [("src", fp), ("dst", fp), ("rows", i64), ("rows_pad", i64), ("K", i64)]
 
@@ -126,7 +137,7 @@ class ModelBwd(C.Structure):
 
 
 STRUCTS = {
-    "vqa_dropout": Dropout, "vqa_pack_segment": PackSegment, "vqa_bits_segment": BitsSegment, "vqa_linear_fwd_params": LinearFwd, "vqa_linear_bwd_params": LinearBwd,
+    "vqa_dropout": Dropout, "vqa_pack_segment": PackSegment, "vqa_bits_segment": BitsSegment, "vqa_param_segment": ParamSegment, "vqa_clip_adam_params": ClipAdam, "vqa_linear_fwd_params": LinearFwd, "vqa_linear_bwd_params": LinearBwd,
     "vqa_mutan_fwd_params": MutanFwd, "vqa_mutan_bwd_params": MutanBwd,
     "vqa_region_softmax_pool_fwd_params": PoolFwd, "vqa_region_softmax_pool_bwd_params": PoolBwd,
     "vqa_cor_compound_fwd_params": CompoundFwd, "vqa_cor_compound_bwd_params": CompoundBwd,
@@ -151,6 +162,7 @@ SYMBOLS = {
                                          C.c_void_p]),
     "vqa_seed_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vqa_grad_groups": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "vqa_clip_adam_step": _OP(ClipAdam),
     "vqa_linear_fwd": _OP(LinearFwd), "vqa_linear_bwd": _OP(LinearBwd),
     "vqa_linear_fwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),
     "vqa_linear_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, i64, i64, i64]),

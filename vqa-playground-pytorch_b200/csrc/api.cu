@@ -134,6 +134,8 @@ extern "C" size_t vqa_sizeof(const char* name) {
   VQA_SZ(vqa_dropout);
   VQA_SZ(vqa_pack_segment);
   VQA_SZ(vqa_bits_segment);
+  VQA_SZ(vqa_param_segment);
+  VQA_SZ(vqa_clip_adam_params);
   VQA_SZ(vqa_linear_fwd_params);
   VQA_SZ(vqa_linear_bwd_params);
   VQA_SZ(vqa_mutan_fwd_params);

@@ -25,7 +25,8 @@ def train_step(model, sample, optimizer=None, scheduler=None, engine=None, clip_
     loss.backward()
     if engine is not None:
         engine.wait()
-    if clip_grad:
+    fused = getattr(optimizer, "clip_grad", None) is not None      # optim.FusedClipAdam clips inside its step
+    if clip_grad and not fused:
         torch.nn.utils.clip_grad_norm_(model.parameters(), clip_grad)
     if optimizer is not None:
         optimizer.step()

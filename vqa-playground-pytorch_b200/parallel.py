@@ -69,6 +69,8 @@ class GradSink:
             first, last = groups[g0][0], groups[g1 - 1][-1]
             self.bucket_ranges.append((offsets[first][0], offsets[last][1]))
         self.accumulate = False
+        self.params = list(params)
+        self.offsets = [offsets[i] for i in range(len(params))]      # (first, last) element of each parameter's slice
         for p, s in zip(params, self.slices):
             p.grad = s
 

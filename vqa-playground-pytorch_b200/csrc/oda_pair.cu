@@ -40,6 +40,24 @@ __global__ void oda_dw_broadcast_kernel(int64_t N, int64_t H, const float* __res
 constexpr int ODA_EPT = 8;
 constexpr int ODA_THREADS = 256;
 
+// v[e] = row[kk[e]], e < 8.  kk holds consecutive feature indices unless the chunk wraps into the next region (or runs
+// past the end); consecutive and 8-byte aligned (even start, even row length) -> four 8-byte loads instead of eight
+// 4-byte ones: lanes sit 32 bytes apart, so every load instruction costs 8 L1 wavefronts whatever its width.
+__device__ __forceinline__ void load_row8(const float* __restrict__ row, const int (&kk)[8], bool contiguous,
+                                          float (&v)[8]) {
+  if (contiguous) {
+    const float2* p = reinterpret_cast<const float2*>(row + kk[0]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __ldg(p + e);
+      v[2 * e] = t.x; v[2 * e + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __ldg(row + kk[e]);
+  }
+}
+
 // keep flags (1.0 / 0.0) of 8 consecutive indices starting at idx.  Fast path idx % 8 == 0: one Philox call.
 __device__ __forceinline__ void keep8(const Drop& d, uint64_t seed, uint64_t idx, float (&keep)[8]) {
   const uint4 r = philox_group(seed, d.layer, idx >> 4);
@@ -89,15 +107,18 @@ oda_pair_logits_train_kernel(int64_t N, int64_t H, Drop d, const float* __restri
       if (++k == H) { k = 0; ++j; }
     }
   }
+  // the 8 features are consecutive in every row (no wrap, no ragged tail) and 8-byte aligned there
+  const bool contig = active && e0 + ODA_EPT <= NH && kk[ODA_EPT - 1] == kk[0] + ODA_EPT - 1 && (kk[0] & 1) == 0 &&
+                      (H & 1) == 0 && (reinterpret_cast<uintptr_t>(vl) & 7) == 0;
   for (int64_t i = 0; i < N; ++i) {
     float acc[G] = {0.f, 0.f, 0.f, 0.f};
     if (active) {
-      float keep[ODA_EPT];
+      float keep[ODA_EPT], vi8[ODA_EPT];
       keep8(d, seed, d.base + (uint64_t)((b * N + i) * NH + e0), keep);
-      const float* vi = vb + i * H;
+      load_row8(vb + i * H, kk, contig, vi8);
 #pragma unroll
       for (int e = 0; e < ODA_EPT; ++e) {          // branch-free: a 50 % mask would diverge on every element
-        const float delta = (__ldg(vi + kk[e]) - vj[e]) * (qk[e] * keep[e]);
+        const float delta = (vi8[e] - vj[e]) * (qk[e] * keep[e]);
 #pragma unroll
         for (int g = 0; g < G; ++g) acc[g] = fmaf(w[g][e], delta, acc[g]);
       }
@@ -172,6 +193,8 @@ oda_pair_bwd_train_e_kernel(int64_t B, int64_t N, int64_t H, Drop d, const float
       if (++k == H) { k = 0; ++j; }
     }
   }
+  const bool contig = e0 + ODA_EPT <= NH && kk[ODA_EPT - 1] == kk[0] + ODA_EPT - 1 && (kk[0] & 1) == 0 && (H & 1) == 0 &&
+                      (reinterpret_cast<uintptr_t>(vl) & 7) == 0;
   const int64_t b0 = (int64_t)blockIdx.y * ODA_BCHUNK;
   const int64_t b1 = b0 + ODA_BCHUNK < B ? b0 + ODA_BCHUNK : B;
   for (int64_t b = b0; b < b1; ++b) {
@@ -188,10 +211,11 @@ oda_pair_bwd_train_e_kernel(int64_t B, int64_t N, int64_t H, Drop d, const float
       keep8(d, seed, d.base + (uint64_t)((b * N + i) * NH + e0), keep);
       const float4 z4 = __ldg(reinterpret_cast<const float4*>(dz + (b * N + i) * G));
       const float zg[G] = {z4.x * d.scale, z4.y * d.scale, z4.z * d.scale, z4.w * d.scale};
-      const float* vi = vb + i * H;
+      float vi8[ODA_EPT];
+      load_row8(vb + i * H, kk, contig, vi8);
 #pragma unroll
       for (int e = 0; e < ODA_EPT; ++e) {          // branch-free
-        const float diff = (__ldg(vi + kk[e]) - vj[e]) * keep[e];
+        const float diff = (vi8[e] - vj[e]) * keep[e];
         const float u = (zg[0] * w[0][e] + zg[1] * w[1][e] + zg[2] * w[2][e] + zg[3] * w[3][e]) * keep[e];
         minus[e] += u;
         dq[e] = fmaf(u, diff, dq[e]);
@@ -218,17 +242,19 @@ oda_pair_bwd_train_e_kernel(int64_t B, int64_t N, int64_t H, Drop d, const float
 // Backward, (i,k)-mapping: thread (i, 16-column slot) loops over j and adds the "+" term
 //   dvl[b,i,k] += ql[b,k] * sum_j u(b,i,(j,k))
 // to the value the e-kernel stored (it is the only "+" writer of (b,i,k)).  W rows of a block of ODA_JB regions j
-// are staged in shared memory (row stride padded to a multiple of 4 floats) and shared by the ODA_IC rows i of the
-// CTA.  grid = (cdiv(N, ODA_IC), B); threads = ODA_IC * cdiv(H,16) rounded up to a warp.
+// are staged in shared memory and shared by the ODA_IC rows i of the CTA.  A thread reads the 16 features
+// k0 .. k0+15 of its slot; the row is stored slot-interleaved, feature k at (k % 16) * KS + k / 16, so that the
+// lanes of a warp (consecutive slots) read consecutive words — the plain layout put them 16 words apart, a 16-way
+// bank conflict on every read.  grid = (cdiv(N, ODA_IC), B); threads = ODA_IC * cdiv(H,16) rounded up to a warp.
 constexpr int ODA_IC = 16, ODA_JB = 8;
 __global__ void __launch_bounds__(320, 2)
 oda_pair_bwd_train_plus_kernel(int64_t N, int64_t H, Drop d, const float* __restrict__ ql,
                                                const float* __restrict__ W, const float* __restrict__ dz,
                                                float* __restrict__ dvl) {
-  extern __shared__ float w_s[];                        // [G][ODA_JB][Hp]
+  extern __shared__ float w_s[];                        // [G][ODA_JB][Hp], Hp = 16 * KS
   const int64_t NH = N * H;
-  const int64_t Hp = (H + 3) / 4 * 4;
   const int KS = (int)((H + 15) / 16);
+  const int64_t Hp = 16 * (int64_t)KS;
   const int64_t b = blockIdx.y;
   const int ii = threadIdx.x / KS, ks = threadIdx.x % KS;
   const int64_t i = (int64_t)blockIdx.x * ODA_IC + ii;
@@ -249,7 +275,7 @@ oda_pair_bwd_train_plus_kernel(int64_t N, int64_t H, Drop d, const float* __rest
     __syncthreads();
     for (int64_t t = threadIdx.x; t < (int64_t)G * nj * H; t += blockDim.x) {
       const int64_t g = t / (nj * H), r = t - g * nj * H, jl = r / H, k = r - jl * H;
-      w_s[(g * ODA_JB + jl) * Hp + k] = W[g * NH + (jb + jl) * H + k];
+      w_s[(g * ODA_JB + jl) * Hp + (k & 15) * KS + (k >> 4)] = W[g * NH + (jb + jl) * H + k];
     }
     __syncthreads();
     if (!active) continue;
@@ -274,12 +300,13 @@ oda_pair_bwd_train_plus_kernel(int64_t N, int64_t H, Drop d, const float* __rest
       uint32_t by[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) by[t] = __funnelshift_r(a[t], a[t + 1], sh);
-      const float* wrow = w_s + jl * Hp + k0;
+      const float* wrow = w_s + jl * Hp + ks;
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const float m = (e < nk && ((by[e >> 2] >> (8 * (e & 3))) & 0xFFu) >= d.thr) ? 1.0f : 0.0f;
-        const float u = zg[0] * wrow[e] + zg[1] * wrow[ODA_JB * Hp + e] + zg[2] * wrow[2 * ODA_JB * Hp + e] +
-                        zg[3] * wrow[3 * ODA_JB * Hp + e];
+        const float u = e < nk ? zg[0] * wrow[e * KS] + zg[1] * wrow[ODA_JB * Hp + e * KS] +
+                                     zg[2] * wrow[2 * ODA_JB * Hp + e * KS] + zg[3] * wrow[3 * ODA_JB * Hp + e * KS]
+                               : 0.0f;
         plus[e] = fmaf(m, u, plus[e]);
       }
     }
@@ -372,7 +399,7 @@ extern "C" int vqa_oda_pair_attn_bwd(const vqa_oda_pair_attn_bwd_params* p, void
     const int KS = (int)((p->H + 15) / 16);
     const int threads = ((ODA_IC * KS + 31) / 32) * 32;
     VQA_REQUIRE(threads <= 1024, "vqa_oda_pair_attn_bwd: H=%lld too large", (long long)p->H);
-    const size_t smem = ((size_t)G * ODA_JB * ((p->H + 3) / 4 * 4) + 16) * sizeof(float);   // +16: masked tail reads
+    const size_t smem = (size_t)G * ODA_JB * 16 * KS * sizeof(float);        // slot-interleaved rows of 16 * KS words
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(oda_pair_bwd_train_plus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)cdiv(p->N, ODA_IC), (unsigned)p->B);

@@ -246,15 +246,18 @@ oda_pair_bwd_train_e_kernel(int64_t B, int64_t N, int64_t H, Drop d, const float
 // k0 .. k0+15 of its slot; the row is stored slot-interleaved, feature k at (k % 16) * KS + k / 16, so that the
 // lanes of a warp (consecutive slots) read consecutive words — the plain layout put them 16 words apart, a 16-way
 // bank conflict on every read.  grid = (cdiv(N, ODA_IC), B); threads = ODA_IC * cdiv(H,16) rounded up to a warp.
+// KSC: slots per row as a compile-time constant (20 for the models' H = 310) so that every shared-memory offset of
+// the inner loop is an immediate; 0 = computed from H at run time.
 constexpr int ODA_IC = 16, ODA_JB = 8;
+template <int KSC>
 __global__ void __launch_bounds__(320, 2)
 oda_pair_bwd_train_plus_kernel(int64_t N, int64_t H, Drop d, const float* __restrict__ ql,
                                                const float* __restrict__ W, const float* __restrict__ dz,
                                                float* __restrict__ dvl) {
   extern __shared__ float w_s[];                        // [G][ODA_JB][Hp], Hp = 16 * KS
   const int64_t NH = N * H;
-  const int KS = (int)((H + 15) / 16);
-  const int64_t Hp = 16 * (int64_t)KS;
+  const int KS = KSC > 0 ? KSC : (int)((H + 15) / 16);
+  const int Hp = 16 * KS;
   const int64_t b = blockIdx.y;
   const int ii = threadIdx.x / KS, ks = threadIdx.x % KS;
   const int64_t i = (int64_t)blockIdx.x * ODA_IC + ii;
@@ -273,9 +276,13 @@ oda_pair_bwd_train_plus_kernel(int64_t N, int64_t H, Drop d, const float* __rest
   for (int64_t jb = 0; jb < N; jb += ODA_JB) {
     const int64_t nj = N - jb < ODA_JB ? N - jb : ODA_JB;
     __syncthreads();
-    for (int64_t t = threadIdx.x; t < (int64_t)G * nj * H; t += blockDim.x) {
-      const int64_t g = t / (nj * H), r = t - g * nj * H, jl = r / H, k = r - jl * H;
-      w_s[(g * ODA_JB + jl) * Hp + (k & 15) * KS + (k >> 4)] = W[g * NH + (jb + jl) * H + k];
+    // (loops instead of one flat index: the flat form spent three 64-bit divisions per staged element — two thirds of
+    // the kernel's instructions)
+    for (int gj = 0; gj < G * (int)nj; ++gj) {
+      const int g = gj / (int)nj, jl = gj - g * (int)nj;
+      const float* src = W + g * NH + (jb + jl) * H;
+      float* dst = w_s + (g * ODA_JB + jl) * Hp;
+      for (int k = threadIdx.x; k < (int)H; k += blockDim.x) dst[(k & 15) * KS + (k >> 4)] = __ldg(src + k);
     }
     __syncthreads();
     if (!active) continue;
@@ -400,10 +407,10 @@ extern "C" int vqa_oda_pair_attn_bwd(const vqa_oda_pair_attn_bwd_params* p, void
     const int threads = ((ODA_IC * KS + 31) / 32) * 32;
     VQA_REQUIRE(threads <= 1024, "vqa_oda_pair_attn_bwd: H=%lld too large", (long long)p->H);
     const size_t smem = (size_t)G * ODA_JB * 16 * KS * sizeof(float);        // slot-interleaved rows of 16 * KS words
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(oda_pair_bwd_train_plus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = KS == 20 ? oda_pair_bwd_train_plus_kernel<20> : oda_pair_bwd_train_plus_kernel<0>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)cdiv(p->N, ODA_IC), (unsigned)p->B);
-    oda_pair_bwd_train_plus_kernel<<<grid, threads, smem, st>>>(p->N, p->H, d, p->ql, p->W, p->dz, p->dvl);
+    kern<<<grid, threads, smem, st>>>(p->N, p->H, d, p->ql, p->W, p->dz, p->dvl);
     VQA_TRY(check_launch("oda_pair_bwd_train_plus"));
   }
   return VQA_OK;

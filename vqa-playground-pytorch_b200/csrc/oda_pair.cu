@@ -206,6 +206,7 @@ oda_pair_bwd_train_e_kernel(int64_t B, int64_t N, int64_t H, Drop d, const float
       qk[e] = ql[b * H + kk[e]];
       minus[e] = 0.0f; dq[e] = 0.0f;
     }
+#pragma unroll 2                                   // two regions in flight: their Philox chains interleave (8 warps per SM)
     for (int64_t i = 0; i < N; ++i) {
       float keep[ODA_EPT];
       keep8(d, seed, d.base + (uint64_t)((b * N + i) * NH + e0), keep);

@@ -371,26 +371,30 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   Cor2Ws w = carve_cor2(p->workspace, B, N, p->C);
   Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT, p->train ? w.bits : nullptr};
   const float* eqp[2] = {w.eq1p, w.eq2p}; const float* clp[1] = {w.clsp}; (void)eqp; (void)clp;
-  if (c.packed) {  // every weight whose rows TMA cannot address, packed once for this step's forward AND backward
-    ProfScope ps_(stream, "pack_weights");
+  // Head of the step.  Main lane: keep-bits of every dropout site, then straight into compress_v (its weight needs
+  // no packing).  Side lane, forked AFTER the bits (the question projections read their masks from them): the
+  // packed copies of every weight whose rows TMA cannot address — made once for this step's forward AND backward,
+  // and off the critical path — then the question-side chain (four projections -> gates).  The main lane first
+  // touches a packed weight after it has waited for the side lane's e_ql.
+  Lanes* L = get_lanes();
+  VQA_REQUIRE(L != nullptr, "vqa_cor2_fwd: cannot create the internal side stream");
+  cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
+  Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
+  cudaEvent_t e_ql, e_gates;
+  if (p->train) {
+    ProfScope ps_(stream, "dropout_bits");
+    VQA_TRY(make_bits(p, w.bits, w.bits_n, stream));
+  }
+  Lanes::wait(ss, L->record(ms));                  // fork
+  if (c.packed) {
+    ProfScope ps_(ss, "pack_weights");
     PackList pl;
     pl.add_mutan(c.W, VQ1_L1, 2, w.vq1_w1p, H); pl.add_mutan(c.W, VQ1_L2, 2, w.vq1_w2p, H);
     pl.add_mutan(c.W, VQ2_L1, 2, w.vq2_w1p, H); pl.add_mutan(c.W, VQ2_L2, 2, w.vq2_w2p, H);
     pl.add_mutan(c.W, FF_L1, 2, w.ff_w1p, 2 * A); pl.add_mutan(c.W, FF_L2, 2, w.ff_w2p, H);
     pl.add(c.W[EQ1], w.eq1p, D, D, H); pl.add(c.W[EQ2], w.eq2p, D, D, H);
     pl.add(c.W[CLASSIF], w.clsp, p->C, p->C, F);
-    VQA_TRY(vqa_pack_weights(pl.s, pl.n, stream));
-  }
-  // fork: the question-side chain (four projections -> gates) runs on the side lane while the region side starts
-  Lanes* L = get_lanes();
-  VQA_REQUIRE(L != nullptr, "vqa_cor2_fwd: cannot create the internal side stream");
-  cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
-  Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
-  Lanes::wait(ss, L->record(ms));
-  cudaEvent_t e_ql, e_gates;
-  if (p->train) {  // keep-bits of every dropout site of the step, shared by its forward and backward kernels
-    ProfScope ps_(stream, "dropout_bits");
-    VQA_TRY(make_bits(p, w.bits, w.bits_n, stream));
+    VQA_TRY(vqa_pack_weights(pl.s, pl.n, ss));
   }
   {  // four 2400->310 question projections in one launch (config/CoR2.py:211,195,196,228)
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
@@ -600,21 +604,23 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   OdaWs w = carve_oda(p->workspace, B, N, p->C);
   Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT, p->train ? w.bits : nullptr};
   const float* clp[1] = {w.clsp}; (void)clp;
-  if (c.packed) {
-    ProfScope ps_(stream, "pack_weights");
-    PackList pl;
-    pl.add_mutan(c.W, FF_L1, 5, w.ff_w1p, A); pl.add_mutan(c.W, FF_L2, 5, w.ff_w2p, H);
-    pl.add(c.W[CLASSIF], w.clsp, p->C, p->C, F);
-    VQA_TRY(vqa_pack_weights(pl.s, pl.n, stream));
-  }
+  // Head of the step as in vqa_cor2_fwd: bits on the main lane, fork, weight packing + question projections on the
+  // side lane (joined before the pairwise attention; the packed weights are first used after that join).
   Lanes* L = get_lanes();
   VQA_REQUIRE(L != nullptr, "vqa_oda_fwd: cannot create the internal side stream");
   cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
   Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
-  Lanes::wait(ss, L->record(ms));               // fork: question projections on the side lane
   if (p->train) {
     ProfScope ps_(stream, "dropout_bits");
     VQA_TRY(make_bits(p, w.bits, w.bits_n, stream));
+  }
+  Lanes::wait(ss, L->record(ms));               // fork
+  if (c.packed) {
+    ProfScope ps_(ss, "pack_weights");
+    PackList pl;
+    pl.add_mutan(c.W, FF_L1, 5, w.ff_w1p, A); pl.add_mutan(c.W, FF_L2, 5, w.ff_w2p, H);
+    pl.add(c.W[CLASSIF], w.clsp, p->C, p->C, F);
+    VQA_TRY(vqa_pack_weights(pl.s, pl.n, ss));
   }
   {  // compress_v (config/ODA.py:211)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};

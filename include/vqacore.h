@@ -132,7 +132,10 @@ typedef struct {
   float* Y[VQA_MAX_GROUPS];        int64_t ldy[VQA_MAX_GROUPS];
   uint32_t layer[VQA_MAX_GROUPS];
   uint64_t drop_index_base[VQA_MAX_GROUPS];
-  const uint8_t* drop_bits[VQA_MAX_GROUPS];  /* optional: packed keep-bits of X_g from vqa_dropout_bits() */
+  const uint8_t* drop_bits[VQA_MAX_GROUPS];  /* optional: packed keep-bits of X_g (bit i = element i) from
+                                                vqa_dropout_bits[_batch](p, seed, layer[g], M*K); used when
+                                                drop_index_base[g] == 0; the buffer needs 2 readable bytes past
+                                                its last one (rows that are not a multiple of 4 long) */
   const float* Wp[VQA_MAX_GROUPS];           /* optional: W_g re-laid by vqa_pack_weights() as [N, roundup(K,4)] */
   void* workspace;          /* >= vqa_linear_fwd_workspace_bytes(); may be NULL when that is 0 */
   size_t workspace_bytes;

@@ -374,6 +374,11 @@ static int launch(Params<Epi> p, int groups, bool x3, cudaStream_t st, const cha
   return x3 ? launch_cfg<128, true>(p, groups, st, what) : launch_cfg<128, false>(p, groups, st, what);
 }
 
+// the keep-bit cache of a group is indexed from element 0 of X_g: only usable when the group's mask is, too
+static inline const uint8_t* cached_bits(const uint8_t* const* bits, const uint64_t* base, int g) {
+  return base[g] == 0 ? bits[g] : nullptr;
+}
+
 static void fill_drop(Drop& d, GroupDrop& gd, float pdrop, uint64_t seed, const uint32_t* layer, const uint64_t* base,
                       int groups, const uint64_t* seed_dev = nullptr) {
   d = make_drop(pdrop, seed, 0, 0, 1, seed_dev);
@@ -651,7 +656,7 @@ int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
   q.drop_on = p->p > 0.0f;
   fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
   q.drop_ld = p->K; q.drop_rows = p->M;
-  for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = p->drop_bits[g < p->groups ? g : 0];
+  for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = cached_bits(p->drop_bits, p->drop_index_base, g < p->groups ? g : 0);
   q.epi.act = p->act;
   q.epi.atomic = q.k_splits > 1;
   if (q.epi.atomic)
@@ -695,7 +700,7 @@ static int dgrad_launch(const vqa_linear_bwd_params* p, float* dz, float* wpk, i
   q.epi.drop_on = p->p > 0.0f;
   fill_drop(q.epi.drop, q.epi.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
   q.epi.drop_ld = p->K; q.epi.wide_bits = (p->K & 3) != 0;
-  for (int g = 0; g < MAXG; ++g) q.epi.bits[g] = p->drop_bits[g < p->groups ? g : 0];
+  for (int g = 0; g < MAXG; ++g) q.epi.bits[g] = cached_bits(p->drop_bits, p->drop_index_base, g < p->groups ? g : 0);
   if constexpr (POOL) {
     q.epi.pool_alpha = p->pool_alpha; q.epi.pool_dp = p->pool_dpooled;
     q.epi.pool_regions = p->pool_regions; q.epi.pool_ld = p->K;
@@ -760,7 +765,7 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
     q.drop_on = p->p > 0.0f;
     fill_drop(q.drop, q.gd, p->p, p->seed, p->layer, p->drop_index_base, p->groups, p->seed_dev);
     q.drop_ld = p->K; q.drop_rows = p->M;
-    for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = p->drop_bits[g < p->groups ? g : 0];
+    for (int g = 0; g < MAXG; ++g) q.drop_bits[g] = cached_bits(p->drop_bits, p->drop_index_base, g < p->groups ? g : 0);
     // split the reduction (over the M rows) so that the grid covers the chip
     q.k_splits = pick_splits_wgrad(cdiv(p->K, BM) * cdiv(p->N, bn) * p->groups, p->M);
     if (!p->accumulate_w)

@@ -5,10 +5,12 @@
 // One CTA computes a 128 x BN tile (of one k-split).  Warp roles (320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a STAGES-deep smem ring
 //   warp 1      TMEM allocator + the single thread that issues tcgen05.mma and tcgen05.commit
-//   warps 2-9   operand transform in shared memory between TMA landing and MMA issue
-//               (Philox input-dropout on A, hi/lo split for 3xTF32; every thread keeps several independent
-//               16-byte chunks in flight), then the epilogue: tcgen05.ld the accumulator rows (two warps per
-//               TMEM lane quadrant, splitting the columns), apply the epilogue functor, store
+//   warps 2-9   operand transform in shared memory between TMA landing and MMA issue (input dropout on A — from the
+//               keep-bit cache, fetched one k-block ahead, or Philox regenerated in registers — and the hi/lo split
+//               for 3xTF32; every thread keeps several independent 16-byte chunks in flight), then the epilogue:
+//               tcgen05.ld the accumulator rows (two warps per TMEM lane quadrant, splitting the columns), stage the
+//               tile in shared memory, and let every thread walk one 4-column group (or, for wgrad, one 4-row group
+//               of the transposed tile) with all of a batch's global reads issued before their first use
 // Operands are described by TMA tensor maps and may be K-major (row-major [rows,K]) or MN-major
 // (row-major [K,rows], i.e. the transposed view used by wgrad/dgrad) — no transposed copies are made.
 // Shared-memory/instruction descriptor layouts follow cute/arch/mma_sm100_desc.hpp and

@@ -225,7 +225,9 @@ def workload_config(args, C):
                                          "stock config/CoR2.py chain (att1 -> compound -> att2)" if args.model == "CoR2"
                                          else "stock config/ODA.py"),
             "precision": args.precision, "parallelism": "dp%d" % args.gpus,
-            "allreduce": getattr(args, "allreduce", "eager, bucketed, overlapped via gradient-group events"),
+            "allreduce": getattr(args, "allreduce", None) or (
+                "none (1 GPU)" if args.gpus == 1 else
+                "bucketed NCCL all-reduce captured inside the step graph, overlapped with the backward"),
             "l2": "inputs rotate over 4 distinct batches and each step touches >0.6 GB of activations (> 126 MB L2)"}
 
 

@@ -266,11 +266,16 @@ static int mutan_bwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int
 }
 
 // one launch for the keep-bits of every dropout site of a plan
-static int make_bits(const vqa_model_fwd_params* p, uint8_t* const* bits, const int64_t* n, void* stream) {
+// `first` >= 0: only that layer (the site the main lane needs at once) / every layer but that one (the rest, made on
+// the side lane under the first GEMM)
+static int make_bits(const vqa_model_fwd_params* p, uint8_t* const* bits, const int64_t* n, void* stream, int first,
+                     bool only_first) {
   vqa_bits_segment s[VQA_MAX_BITS_SEGMENTS];
   int k = 0;
   for (int i = 0; i < 32; ++i)
-    if (bits[i] && n[i] > 0) { s[k].layer = (uint32_t)i; s[k].n = (uint64_t)n[i]; s[k].out = bits[i]; ++k; }
+    if (bits[i] && n[i] > 0 && ((i == first) == only_first)) {
+      s[k].layer = (uint32_t)i; s[k].n = (uint64_t)n[i]; s[k].out = bits[i]; ++k;
+    }
   return vqa_dropout_bits_batch(P_DROP, p->seed, p->seed_dev, s, k, stream);
 }
 
@@ -371,21 +376,25 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   Cor2Ws w = carve_cor2(p->workspace, B, N, p->C);
   Ctx c{p, stream, p->params, nullptr, 0, w.lin_ws, w.lin_ws_bytes, p->math != VQA_MATH_FP32_SIMT, p->train ? w.bits : nullptr};
   const float* eqp[2] = {w.eq1p, w.eq2p}; const float* clp[1] = {w.clsp}; (void)eqp; (void)clp;
-  // Head of the step.  Main lane: keep-bits of every dropout site, then straight into compress_v (its weight needs
-  // no packing).  Side lane, forked AFTER the bits (the question projections read their masks from them): the
-  // packed copies of every weight whose rows TMA cannot address — made once for this step's forward AND backward,
-  // and off the critical path — then the question-side chain (four projections -> gates).  The main lane first
-  // touches a packed weight after it has waited for the side lane's e_ql.
+  // Head of the step.  Main lane: keep-bits of compress_v's input, then straight into compress_v (its weight needs
+  // no packing).  Side lane: the keep-bits of every other dropout site (the question projections below read theirs
+  // in stream order; the main lane reads its next ones only after waiting for e_ql), the packed copies of every
+  // weight whose rows TMA cannot address — made once for this step's forward AND backward — then the
+  // question-side chain (four projections -> gates).  The main lane first touches a packed weight after e_ql too.
   Lanes* L = get_lanes();
   VQA_REQUIRE(L != nullptr, "vqa_cor2_fwd: cannot create the internal side stream");
   cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
   Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
   cudaEvent_t e_ql, e_gates;
-  if (p->train) {
+  if (p->train) {                                  // the mask compress_v needs right away
     ProfScope ps_(stream, "dropout_bits");
-    VQA_TRY(make_bits(p, w.bits, w.bits_n, stream));
+    VQA_TRY(make_bits(p, w.bits, w.bits_n, stream, L_COMPRESS_V, true));
   }
   Lanes::wait(ss, L->record(ms));                  // fork
+  if (p->train) {                                  // every other site: first read after the main lane's e_ql wait
+    ProfScope ps_(ss, "dropout_bits.rest");
+    VQA_TRY(make_bits(p, w.bits, w.bits_n, ss, L_COMPRESS_V, false));
+  }
   if (c.packed) {
     ProfScope ps_(ss, "pack_weights");
     PackList pl;
@@ -612,9 +621,13 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
   if (p->train) {
     ProfScope ps_(stream, "dropout_bits");
-    VQA_TRY(make_bits(p, w.bits, w.bits_n, stream));
+    VQA_TRY(make_bits(p, w.bits, w.bits_n, stream, L_COMPRESS_V, true));
   }
   Lanes::wait(ss, L->record(ms));               // fork
+  if (p->train) {
+    ProfScope ps_(ss, "dropout_bits.rest");
+    VQA_TRY(make_bits(p, w.bits, w.bits_n, ss, L_COMPRESS_V, false));
+  }
   if (c.packed) {
     ProfScope ps_(ss, "pack_weights");
     PackList pl;

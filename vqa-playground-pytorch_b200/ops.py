@@ -122,8 +122,9 @@ def seed_advance(seed_dev):
 
 
 def dropout_bits(p, seed, layer, n, device):
-    """Packed keep-bits of n elements (vqa_dropout_bits)."""
-    out = torch.empty(((n + 15) // 16 * 2,), device=device, dtype=torch.uint8)
+    """Packed keep-bits of n elements (vqa_dropout_bits); 4 spare bytes at the end, which the kernels that read a
+    quad's bits across a byte boundary may touch."""
+    out = torch.zeros(((n + 15) // 16 * 2 + 4,), device=device, dtype=torch.uint8)
     _lib.check(_lib.lib().vqa_dropout_bits(float(p), int(seed), None, int(layer), int(n), out.data_ptr(), _stream()),
                "vqa_dropout_bits")
     return out

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VQA_ABI_VERSION 1
+#define VQA_ABI_VERSION 2
 
 enum {
   VQA_OK = 0,
@@ -140,8 +140,12 @@ typedef struct {
   void* workspace;          /* >= vqa_linear_fwd_workspace_bytes(); may be NULL when that is 0 */
   size_t workspace_bytes;
 } vqa_linear_fwd_params;
-/* Scratch the tensor-core paths need (padded copies of weights whose row stride is not a multiple of 16
- * bytes, which TMA cannot address; the activation-gradient dZ in the backward). 0 for VQA_MATH_FP32_SIMT. */
+/* Scratch the tensor-core paths need (padded copies of operands whose row stride is not a multiple of 16
+ * bytes, which TMA cannot address; the activation-gradient dZ in the backward). 0 for VQA_MATH_FP32_SIMT.
+ * The query sees shapes only: it covers W and a contiguous X when K is not a multiple of 4.  An X_g whose BASE is
+ * not 16-byte aligned or whose ldx is not a multiple of 4 although K is needs groups * (M * roundup(K,4) * 4 + 256)
+ * bytes more.  A tensor-core math mode never falls back to the CUDA-core GEMM: a workspace too small for the repack
+ * is VQA_EINVAL. */
 size_t vqa_linear_fwd_workspace_bytes(int math, int groups, int64_t M, int64_t K, int64_t N);
 size_t vqa_linear_bwd_workspace_bytes(int math, int groups, int64_t M, int64_t K, int64_t N);
 int vqa_linear_fwd(const vqa_linear_fwd_params* p, void* stream);
@@ -267,12 +271,14 @@ typedef struct {
 int vqa_region_softmax_pool_fwd(const vqa_region_softmax_pool_fwd_params* p, void* stream);
 
 /* Backward (SURVEY.md §8a "K-pool"):
- *   dalpha[b,i,g] = <dpooled[b,g,:], x[b,i,:]> + (g==0 ? dalpha0_ext[b] : 0)
+ *   dalpha[b,i,g] = <dpooled[b,g,:], x[b,i,:]> + (g==0 ? dalpha0_ext[b] : 0) + dalpha_ext[b,i,g]
  *   dz = alpha (.) (dalpha - sum_i alpha*dalpha)
  *   dWc (+)= sum_{b,i} dz[b,i,g]*dropout(fuse)[b,i,c];  dbc (+)= sum dz
  *   dfuse[b,i,c] = (sum_g dz[b,i,g] Wc[g,c]) * mask/(1-p)
  *   dx[b,i,:] (+)= sum_g alpha[b,i,g] dpooled[b,g,:]      (dx NULL: x is a graph input)
- * dalpha0_ext ([B] or NULL) carries CoR2's d(s)/d(alpha) term from vqa_cor_compound_bwd.
+ * dalpha0_ext ([B] or NULL) carries CoR2's d(s)/d(alpha) term from vqa_cor_compound_bwd; dalpha_ext ([B,N,G] or
+ * NULL) is a general incoming gradient of alpha (a caller that uses the attention weights downstream, as the
+ * reference's (alpha1[0] * v2_cat).sum(1) does, config/CoR2.py:216).
  */
 typedef struct {
   int64_t B, N, Ff, D;
@@ -289,6 +295,7 @@ typedef struct {
   float* dfuse;                /* [B,N,Ff] or NULL */
   float* dx;                   /* [B,N,D] or NULL */
   const uint8_t* drop_bits;    /* optional, as in the forward */
+  const float* dalpha_ext;     /* [B,N,G] or NULL */
 } vqa_region_softmax_pool_bwd_params;
 int vqa_region_softmax_pool_bwd(const vqa_region_softmax_pool_bwd_params* p, void* stream);
 
@@ -449,6 +456,14 @@ typedef struct {
   float max_norm;                  /* clip_grad_norm_'s max_norm; <= 0 disables clipping */
   int write_clipped_grads;         /* 1: grads_flat *= clip as clip_grad_norm_ does in place; 0: leave them */
   float* scratch;                  /* 1 float of device memory (holds ||g||^2 on return) when clipping */
+  /* Optional device-resident optimizer clock, for a step captured in a CUDA graph (every replay must be the same
+   * launch): when step_dev is non-NULL the call first enqueues *step_dev += 1 (and *lr_dev *= lr_gamma when lr_dev is
+   * non-NULL and lr_gamma > 0 — ExponentialLR stepped BEFORE the optimizer, train.py:75-76, :296), then the update
+   * reads the step count from *step_dev and the learning rate from *lr_dev (lr above when lr_dev is NULL);
+   * `step` is ignored. */
+  int64_t* step_dev;
+  double* lr_dev;
+  double lr_gamma;
 } vqa_clip_adam_params;
 int vqa_clip_adam_step(const vqa_clip_adam_params* p, void* stream);
 

@@ -79,10 +79,11 @@ def mask_bytes(seed, layer, n, start=0):
     return ((word >> shift) & np.uint32(0xFF)).astype(np.uint8)
 
 
-def dropout_mask(seed, layer, shape, p):
-    """float32 {0,1} keep-mask of `shape` (row-major linear index = element index)."""
+def dropout_mask(seed, layer, shape, p, start=0):
+    """float32 {0,1} keep-mask of `shape` (row-major linear index = start + element index; `start` lets a batch be
+    processed in chunks with the masks of the full-batch tensor)."""
     n = int(np.prod(shape))
-    keep = mask_bytes(seed, layer, n) >= np.uint8(threshold(p))
+    keep = mask_bytes(seed, layer, n, start=start) >= np.uint8(threshold(p))
     return keep.astype(np.float32).reshape(shape)
 
 

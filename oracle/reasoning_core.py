@@ -64,11 +64,13 @@ def torch_drop(x, p, layer_id):
 class PhiloxDrop:
     """Deterministic train-mode dropout: x * keep / (1-p), keep from oracle/philox.py."""
 
-    def __init__(self, seed):
+    def __init__(self, seed, batch_offset=0):
         self.seed = int(seed)
+        self.batch_offset = int(batch_offset)     # x holds samples [batch_offset, batch_offset + x.shape[0]) of the batch
 
     def __call__(self, x, p, layer_id):
-        m = philox.dropout_mask(self.seed, layer_id, tuple(x.shape), p)
+        start = self.batch_offset * int(x[0].numel()) if self.batch_offset else 0
+        m = philox.dropout_mask(self.seed, layer_id, tuple(x.shape), p, start=start)
         return x * torch.from_numpy(m).to(x.dtype) * (1.0 / (1.0 - p))
 
 

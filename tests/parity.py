@@ -12,6 +12,8 @@ GOLDEN_CASES = ["oda_eval_b4", "oda_train_b4", "cor2_eval_b4", "cor2_train_b4", 
 # Parity metric of SURVEY.md §8d: max|new-ref| / max(max|ref|, floor), floor = 1e-6 * largest gradient max-abs,
 # so structurally-zero gradients (conv_att biases, fusion_vq biases) compare as ~0 instead of noise/noise.
 FP32_TOL = 1e-4
+# precision names that claim the fp32-parity bound (1e-4): CUDA-core fp32 and the error-compensated tensor-core modes
+PARITY_MODES = ["fp32", "tf32x3"]
 
 
 def rel_err(new, ref, floor=0.0):
@@ -104,7 +106,52 @@ def oracle_with_same_relu_pattern(model, sd, v, q, a, out, N=36, train_seed=None
     return ref
 
 
-def run_cuda_model(model, sd, v, q, a, N=36, train_seed=None, precision="fp32", device="cuda:0"):
+def oracle_chunked(model, sd, v, q, a, chunk, N=36, train_seed=None, relu_masks=None, tie_tol=1e-4):
+    """The oracle's fwd+bwd over a large batch in chunks of `chunk` samples: samples are independent through the
+    forward and the loss is a SUM (train.py:541), so logits / alphas concatenate and gradients add.  Dropout masks
+    are those of the full-batch tensors (PhiloxDrop.batch_offset).  With `relu_masks` (the activation patterns of the
+    implementation under test, full batch) each chunk replays its rows, as oracle_with_same_relu_pattern does."""
+    B = v.shape[0]
+    logits, alphas, grads, loss, nflips = [], {}, None, 0.0, 0
+    for b0 in range(0, B, chunk):
+        b1 = min(B, b0 + chunk)
+        ties = None
+        if relu_masks is not None:
+            sl = {}
+            for name, m in relu_masks.items():
+                per = m.shape[0] // B
+                sl[name] = m[b0 * per:b1 * per]
+            ties = rc.ReluTies(masks=sl)
+        drop = rc.no_drop if train_seed is None else rc.PhiloxDrop(train_seed, batch_offset=b0)
+        r = rc.step(model, sd, v[b0:b1], q[b0:b1], a[b0:b1], drop=drop, num_regions=N, ties=ties)
+        if ties is not None:
+            for name, mask in ties.masks.items():
+                z = ties.pre[name]
+                if isinstance(z, dict):
+                    zz = torch.zeros(mask.shape)
+                    for (c0, c1), t in z.items():
+                        zz[:, c0:c1] = t
+                    z = zz
+                z = z.reshape(mask.shape)
+                flipped = (z > 0) != mask
+                if flipped.any():
+                    worst = z[flipped].abs().max().item() / max(z.abs().max().item(), 1e-30)
+                    assert worst <= tie_tol, "ReLU pattern of %s differs at |z|/max|z| = %.3e" % (name, worst)
+                    nflips += int(flipped.sum())
+        logits.append(r["logits"])
+        loss += r["loss"].item()
+        for k, val in flatten_alpha(r["alpha_dict"]).items():
+            alphas.setdefault(k, []).append(val)
+        if grads is None:
+            grads = {k: g.clone() for k, g in r["grads"].items()}
+        else:
+            for k, g in r["grads"].items():
+                grads[k] += g
+    return {"logits": torch.cat(logits), "loss": torch.tensor(loss), "alpha_dict": {k: torch.cat(t) for k, t in alphas.items()},
+            "grads": grads, "relu_ties": nflips}
+
+
+def run_cuda_model(model, sd, v, q, a, N=36, train_seed=None, precision="tf32x3", device="cuda:0"):
     """fwd + KLD loss + bwd through the product's public API (config.<model>.Model)."""
     import importlib
     cf = importlib.import_module("vqa_playground_pytorch_b200.config." + model)

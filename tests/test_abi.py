@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layouts(lib):
     L = lib.lib()
-    assert L.vqa_abi_version() == 1
+    assert L.vqa_abi_version() == lib.ABI_VERSION == 2
     for name, st in lib.STRUCTS.items():
         assert L.vqa_sizeof(name.encode()) == ctypes.sizeof(st), name
     assert L.vqa_sizeof(b"no_such_struct") == 0

@@ -52,6 +52,15 @@ def test_kernel_roofline_record():
     flops = 2.0 * 9216 * 2048 * 310
     assert abs(r["achieved"] - flops / 0.150e-3 / 1e12) < 1e-6 and abs(r["frac"] - r["achieved"] / 1414.3) < 1e-12
     assert r["peak"] == 1414.3 and r["traffic"] == 45470000 and abs(r["share_of_step"] - 0.075) < 1e-12
+    # a bandwidth-bound kernel dominates: its algorithmic bytes against the measured copy bandwidth
+    r3 = bench.kernel_roofline({"k:pool_bwd hbm=75497472": 0.2, "k:tc_linear_fwd M256 N310 K2400 g4 s9": 0.06}, per_op, 2.0, pk,
+                               argparse.Namespace(precision="tf32x3", model="CoR2"), 256, 36, 2000)
+    assert r3["kernel"] == "pool_bwd" and r3["bound"] == "hbm" and r3["unit"] == "GB/s" and r3["peak"] == 6452.8
+    assert abs(r3["achieved"] - 75497472 / 0.2e-3 / 1e9) < 1e-6
+    # a CUDA-core kernel (ODA pairwise terms) dominates: quoted against the fp32 FMA rate
+    r4 = bench.kernel_roofline({"k:oda_pair_bwd_train_e flop=2000000000": 0.3}, per_op, 2.0, pk,
+                               argparse.Namespace(precision="tf32x3", model="ODA"), 256, 36, 3000)
+    assert r4["kernel"] == "oda_pair_bwd_train_e" and r4["unit"] == "TFLOP/s" and 70 < r4["peak"] < 80
     # no per-kernel records (an op that is not a GEMM dominates): falls back to the per-op table
     r2 = bench.kernel_roofline({}, {"compound.bwd": 0.03}, 1.0, pk, argparse.Namespace(precision="tf32x3", model="CoR2"), 256, 36, 2000)
     assert r2["bound"] == "hbm" and r2["unit"] == "GB/s" and r2["traffic"] is None

@@ -23,15 +23,32 @@ def _check_against_oracle(out, ref, tol=parity.FP32_TOL):
         assert parity.rel_err(out["grads"][k], g, 1e-6 * gmax) <= tol, k
 
 
+# fp32-parity modes: the CUDA-core path and every tensor-core mode that claims the 1e-4 bound.  The product default
+# (config.*.precision) must be one of them: goldens and oracle cases run on the path that is benchmarked.
+TIE_TOL = {"fp32": 1e-5}
+
+
+def _tie_tol(precision):
+    return TIE_TOL.get(precision, 1e-4)
+
+
+def test_default_precision_is_a_parity_mode():
+    from vqa_playground_pytorch_b200.config import CoR2, ODA
+    assert CoR2.precision in parity.PARITY_MODES and ODA.precision in parity.PARITY_MODES
+    assert CoR2.precision != "fp32"            # the benchmarked default is a tensor-core mode
+
+
+@pytest.mark.parametrize("precision", parity.PARITY_MODES)
 @pytest.mark.parametrize("name", parity.GOLDEN_CASES)
-def test_cuda_matches_reference_golden(cuda, name):
+def test_cuda_matches_reference_golden(cuda, name, precision):
+    """Golden vectors written by the UNMODIFIED reference (oracle/make_golden.py) against every parity mode."""
     from oracle import reasoning_core as rc
     z, meta = parity.load_golden(name)
     seed = None if meta["train_seed"] < 0 else int(meta["train_seed"])
     model, B, C = meta["model"], int(meta["B"]), int(meta["num_ans"])
     sd = rc.synth_state_dict(model, C, seed=int(meta["weight_seed"]))
     v, q, a = rc.synth_inputs(B, 36, C, seed=int(meta["input_seed"]))
-    out = parity.run_cuda_model(model, sd, v, q, a, train_seed=seed)
+    out = parity.run_cuda_model(model, sd, v, q, a, train_seed=seed, precision=precision)
     assert parity.rel_err(out["logits"], z["logits"]) <= parity.FP32_TOL
     assert abs(out["loss"].item() - float(z["loss"])) <= parity.FP32_TOL * abs(float(z["loss"]))
     for k, t in parity.flatten_alpha(out["alpha_dict"]).items():
@@ -43,50 +60,148 @@ def test_cuda_matches_reference_golden(cuda, name):
         assert parity.compare_grad_to_golden(z, n, out["grads"][n], floor) <= parity.FP32_TOL, n
 
 
+@pytest.mark.parametrize("precision", parity.PARITY_MODES)
 @pytest.mark.parametrize("model,C", [("CoR2", 2000), ("ODA", 3000)])
 @pytest.mark.parametrize("B,N,seed", [(2, 36, None), (7, 36, 11), (3, 10, None), (3, 10, 5), (2, 100, None),
-                                      (2, 100, 9), (33, 36, 3)])
-def test_cuda_matches_oracle(cuda, model, C, B, N, seed):
+                                      (2, 100, 9), (33, 36, 3), (130, 36, 21)])
+def test_cuda_matches_oracle(cuda, model, C, B, N, seed, precision):
+    if B == 130 and precision == "fp32":
+        pytest.skip("the large case runs on the tensor-core modes")
     sd, (v, q, a), _ = parity.oracle_case(model, B, C, N=N, weight_seed=21, input_seed=B * 1000 + N, run=False)
-    out = parity.run_cuda_model(model, sd, v, q, a, N=N, train_seed=seed)
-    ref = parity.oracle_with_same_relu_pattern(model, sd, v, q, a, out, N=N, train_seed=seed, tie_tol=1e-5)
-    _check_against_oracle(out, ref)
-
-
-@pytest.mark.parametrize("model,C", [("CoR2", 2000), ("ODA", 3000)])
-@pytest.mark.parametrize("B,N,seed", [(5, 36, None), (9, 36, 13), (3, 100, 2), (130, 36, 21)])
-def test_tensor_core_fp32_parity_mode(cuda, model, C, B, N, seed):
-    """precision='tf32x3' (tcgen05, error-compensated 3xTF32, fp32 accumulate in TMEM) must meet the same 1e-4
-    bound as the CUDA-core fp32 path (BASELINE.json: fp32 mode max relative error <= 1e-4)."""
-    sd, (v, q, a), _ = parity.oracle_case(model, B, C, N=N, weight_seed=31, input_seed=B * 77 + N, run=False)
-    out = parity.run_cuda_model(model, sd, v, q, a, N=N, train_seed=seed, precision="tf32x3")
+    out = parity.run_cuda_model(model, sd, v, q, a, N=N, train_seed=seed, precision=precision)
     # gradients are compared on the SAME ReLU activation pattern; the patterns may differ only at rounding-level
-    # ties (|z| <= 1e-4 max|z|, the forward tolerance) — one tie alone moves a wgrad row by ~1/sqrt(rows)
-    ref = parity.oracle_with_same_relu_pattern(model, sd, v, q, a, out, N=N, train_seed=seed, tie_tol=1e-4)
+    # ties (|z| <= tie_tol * max|z|) — one tie alone moves a wgrad row by ~1/sqrt(rows)
+    ref = parity.oracle_with_same_relu_pattern(model, sd, v, q, a, out, N=N, train_seed=seed, tie_tol=_tie_tol(precision))
     _check_against_oracle(out, ref)
 
 
+def _relu_count(out):
+    return sum(m.numel() for m in out["relu_masks"].values())
+
+
+@pytest.mark.parametrize("model,C,B,N,chunk", [("CoR2", 2000, 256, 36, 64), ("ODA", 3000, 512, 100, 16)])
+def test_benchmarked_configurations_match_the_oracle(cuda, model, C, B, N, chunk):
+    """BASELINE.json configs[1] (CoR2, batch 256 x 36, train mode) and configs[2]'s shape (ODA, batch 512 x 100) in
+    the product-default precision against the oracle, which runs the batch in chunks (samples are independent and
+    the loss is a sum: logits concatenate, gradients add).  Also bounds the number of ReLU ties that the gradient
+    comparison replays: they must be rounding-level (|z| <= 1e-4 max|z|, asserted) AND rare."""
+    import importlib
+    cf = importlib.import_module("vqa_playground_pytorch_b200.config." + model)
+    sd, (v, q, a), _ = parity.oracle_case(model, B, C, N=N, weight_seed=10, input_seed=4242, run=False)
+    seed = 20261017
+    out = parity.run_cuda_model(model, sd, v, q, a, N=N, train_seed=seed, precision=cf.precision)
+    ref = parity.oracle_chunked(model, sd, v, q, a, chunk, N=N, train_seed=seed, relu_masks=out["relu_masks"],
+                                tie_tol=_tie_tol(cf.precision))
+    _check_against_oracle(out, ref)
+    n_relu = _relu_count(out)
+    print("%s B=%d N=%d %s: %d replayed ReLU ties of %d activations" % (model, B, N, cf.precision, ref["relu_ties"], n_relu))
+    assert ref["relu_ties"] <= max(8, 2e-5 * n_relu)
+
+
 @pytest.mark.parametrize("model,C", [("CoR2", 2000), ("ODA", 3000)])
-def test_tf32_throughput_mode(cuda, model, C):
-    """precision='tf32' (single-pass TF32 tensor cores): the reduced-precision bound of BASELINE.json, <= 2e-2 on
-    logits (fp32 reference), attention weights likewise."""
+def test_gradient_error_without_replaying_relu_ties(cuda, model, C):
+    """The same comparison WITHOUT the replay (the oracle uses its own activation pattern): reports the error a tie
+    causes and checks it stays of the size one tie predicts (a wgrad row moves by ~1/sqrt(rows)), i.e. that nothing
+    else hides behind the replay."""
+    import importlib
+    cf = importlib.import_module("vqa_playground_pytorch_b200.config." + model)
+    B, N, seed = 33, 36, 3
+    sd, (v, q, a), ref_free = parity.oracle_case(model, B, C, N=N, weight_seed=21, input_seed=B * 1000 + N, train_seed=seed)
+    out = parity.run_cuda_model(model, sd, v, q, a, N=N, train_seed=seed, precision=cf.precision)
+    ref = parity.oracle_with_same_relu_pattern(model, sd, v, q, a, out, N=N, train_seed=seed, tie_tol=_tie_tol(cf.precision))
+    gmax = max(g.abs().max().item() for g in ref_free["grads"].values())
+    worst = max((parity.rel_err(out["grads"][k], g, 1e-6 * gmax), k) for k, g in ref_free["grads"].items()
+                if not k.endswith("conv_att.conv.bias"))
+    print("%s %s un-replayed: %d ties, worst gradient error %.2e (%s)" % (model, cf.precision, ref["relu_ties"], worst[0], worst[1]))
+    assert parity.rel_err(out["logits"], ref_free["logits"]) <= parity.FP32_TOL       # the forward needs no replay
+    assert ref["relu_ties"] <= 8
+    assert worst[0] <= (parity.FP32_TOL if ref["relu_ties"] == 0 else 5e-2), worst
+
+
+REDUCED = ["tf32", "bf16"]
+
+
+@pytest.mark.parametrize("precision", REDUCED)
+@pytest.mark.parametrize("model,C", [("CoR2", 2000), ("ODA", 3000)])
+def test_reduced_precision_modes(cuda, model, C, precision):
+    """BASELINE.json north_star: reduced-precision modes keep logits within 2e-2 of the fp32 reference, gradients
+    likewise (SURVEY.md §8d metric), train mode with the shared Philox masks."""
     sd, (v, q, a), ref = parity.oracle_case(model, 16, C, train_seed=4, weight_seed=5, input_seed=6)
-    out = parity.run_cuda_model(model, sd, v, q, a, train_seed=4, precision="tf32")
+    out = parity.run_cuda_model(model, sd, v, q, a, train_seed=4, precision=precision)
     assert parity.rel_err(out["logits"], ref["logits"]) <= 2e-2
     fa, fb = parity.flatten_alpha(out["alpha_dict"]), parity.flatten_alpha(ref["alpha_dict"])
     for k in fb:
         assert parity.rel_err(fa[k], fb[k]) <= 2e-2, k
+    gmax = max(g.abs().max().item() for g in ref["grads"].values())
+    worst = max((parity.rel_err(out["grads"][k], g, 1e-3 * gmax), k) for k, g in ref["grads"].items()
+                if not k.endswith("conv_att.conv.bias"))
+    print("%s %s: logits %.2e, worst gradient %.2e (%s)" % (model, precision, parity.rel_err(out["logits"], ref["logits"]),
+                                                            worst[0], worst[1]))
+    assert worst[0] <= 2e-2, worst
 
 
+@pytest.mark.parametrize("precision", REDUCED)
+def test_reduced_precision_top1_agreement(cuda, precision):
+    """>= 99.9 % top-1 answer agreement with the fp32 reference over >= 10 000 synthetic samples.
+    A randomly initialised classifier gives near-uniform logits whose argmax is decided by noise for ANY
+    implementation, so — as §8d prescribes — the classifier is trained on the synthetic targets first.  The training
+    is closed-form: the oracle (fp32 CPU, eval mode) produces the 510-d fused feature of every sample (identity
+    classifier), sample b is assigned answer b mod C, and linear_classif becomes the nearest-class-mean classifier of
+    those features (weight = class mean - global mean, bias = -<global mean, weight>).  Everything upstream of the
+    classifier keeps its random initialisation, so the reduced-precision error of the whole chain is what is tested.
+    ODA 10 240 + CoR2 4 096 samples."""
+    import importlib
+    from oracle import reasoning_core as rc
+    agree = total = 0
+    for model, C, n in (("ODA", 3000, 10240), ("CoR2", 2000, 4096)):
+        cf = importlib.import_module("vqa_playground_pytorch_b200.config." + model)
+        sd = rc.synth_state_dict(model, 510, seed=77)
+        sd["linear_classif.linear.weight"] = torch.eye(510)
+        sd["linear_classif.linear.bias"] = torch.zeros(510)
+        batches, feats = [], []
+        gen = torch.Generator().manual_seed(9000)
+        for b0 in range(0, n, 512):
+            v = torch.relu(torch.randn(512, 36, 2048, generator=gen))          # SURVEY.md §8d synthetic features
+            q = 0.1 * torch.relu(torch.randn(512, 2400, generator=gen))
+            with torch.no_grad():
+                xf, _ = rc.FORWARD[model](sd, v, q, rc.no_drop, 36)
+            batches.append((v, q))
+            feats.append(xf)
+        xf = torch.cat(feats)                                     # [n, 510] oracle features
+        labels = torch.arange(n) % C
+        mu = xf.mean(0)
+        W = torch.zeros(C, 510).index_add_(0, labels, xf - mu) / torch.bincount(labels, minlength=C).clamp(min=1).unsqueeze(1)
+        W = W / W.norm(dim=1).mean()                              # O(1) logits
+        bias = -(W @ mu)
+        ref_logits = xf @ W.t() + bias
+        print("%s: the trained classifier labels %.2f%% of its training samples correctly (fp32 oracle)" %
+              (model, 100.0 * (ref_logits.argmax(1) == labels).float().mean().item()))
+        sd2 = dict(sd)
+        sd2["linear_classif.linear.weight"], sd2["linear_classif.linear.bias"] = W, bias
+        m = cf.Model(None, C, precision=precision)
+        m.load_state_dict(sd2)
+        m = m.cuda().eval()
+        for i, (v, q) in enumerate(batches):
+            with torch.no_grad():
+                got = m({"v": v.cuda(), "q_idxes": q.cuda()}).cpu()
+            ref = ref_logits[i * 512:(i + 1) * 512]
+            assert parity.rel_err(got, ref) <= 2e-2
+            agree += int((got.argmax(1) == ref.argmax(1)).sum())
+            total += 512
+    print("%s top-1 agreement %d / %d = %.4f%%" % (precision, agree, total, 100.0 * agree / total))
+    assert total >= 10000 and agree >= 0.999 * total
+
+
+@pytest.mark.parametrize("precision", parity.PARITY_MODES)
 @pytest.mark.parametrize("model,C", [("CoR2", 2000), ("ODA", 3000)])
-def test_batch_of_one(cuda, model, C):
+def test_batch_of_one(cuda, model, C, precision):
     """The reference crashes at B=1 (e.squeeze() drops the batch dim); parity is taken from
     the B=2 oracle run with the row duplicated."""
     sd, (v, q, a), ref = parity.oracle_case(model, 2, C, weight_seed=4, input_seed=8)
     v2, q2, a2 = v[:1].repeat(2, 1, 1), q[:1].repeat(2, 1), a[:1].repeat(2, 1)
     from oracle import reasoning_core as rc
     ref2 = rc.step(model, sd, v2, q2, a2)
-    out = parity.run_cuda_model(model, sd, v[:1], q[:1], a[:1])
+    out = parity.run_cuda_model(model, sd, v[:1], q[:1], a[:1], precision=precision)
     assert parity.rel_err(out["logits"], ref2["logits"][:1]) <= parity.FP32_TOL
     gmax = max(g.abs().max().item() for g in ref2["grads"].values())
     for k, g in ref2["grads"].items():

@@ -10,6 +10,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libvqacore_sm100a.so")
 
+ABI_VERSION = 2
 MAXG = 8
 GLIMPSES = 4
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
@@ -77,7 +78,7 @@ class ClipAdam(C.Structure):
     _fields_ = [("nsegs", C.c_int), ("segs", C.POINTER(ParamSegment)), ("grads_flat", fp), ("exp_avg", fp),
                 ("exp_avg_sq", fp), ("total", i64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("eps", C.c_float), ("step", i64), ("max_norm", C.c_float), ("write_clipped_grads", C.c_int),
-                ("scratch", fp)]
+                ("scratch", fp), ("step_dev", fp), ("lr_dev", fp), ("lr_gamma", C.c_double)]
 
 
 class PackSegment(C.Structure):
@@ -95,7 +96,7 @@ class PoolBwd(C.Structure):
                 ("accumulate_w", C.c_int), ("accumulate_x", C.c_int),
                 ("fuse", fp), ("Wc", fp), ("x", fp), ("alpha", fp), ("dpooled", fp), ("dalpha0_ext", fp),
                 ("dalpha", fp), ("dz", fp), ("dWc", fp), ("dbc", fp), ("dfuse", fp), ("dx", fp),
-                ("drop_bits", fp)]
+                ("drop_bits", fp), ("dalpha_ext", fp)]
 
 
 class CompoundFwd(C.Structure):
@@ -197,8 +198,8 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)           # AttributeError if the .so lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.vqa_abi_version() != 1:
-            raise RuntimeError("libvqacore ABI version %d, binding expects 1" % L.vqa_abi_version())
+        if L.vqa_abi_version() != ABI_VERSION:
+            raise RuntimeError("libvqacore ABI version %d, binding expects %d" % (L.vqa_abi_version(), ABI_VERSION))
         _lib = L
     return _lib
 

@@ -67,6 +67,7 @@ pool_fwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* 
 int launch_pool_fwd(int64_t B, int64_t N, int64_t D, const float* x, const float* alpha, float* pooled,
                     cudaStream_t st) {
   dim3 grid((unsigned)cdiv(D / 4, POOL_THREADS), (unsigned)B);
+  KProf kp_(st, "pool_fwd", "hbm", 4.0 * ((double)B * N * D + (double)B * G * D + (double)B * N * G));
   pool_fwd_kernel<<<grid, POOL_THREADS, (size_t)N * G * sizeof(float), st>>>(N, D, x, alpha, pooled);
   return check_launch("pool_fwd");
 }
@@ -80,8 +81,9 @@ constexpr int POOL_BWD_RW = 4;
 constexpr int POOL_BWD_MAX_WARPS = 12;
 __global__ void __launch_bounds__(POOL_BWD_MAX_WARPS * 32)
 pool_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* __restrict__ alpha,
-                const float* __restrict__ dpooled, const float* __restrict__ dalpha0_ext, float* __restrict__ dalpha,
-                float* __restrict__ dx, int accumulate_x) {
+                const float* __restrict__ dpooled, const float* __restrict__ dalpha0_ext,
+                const float* __restrict__ dalpha_ext, float* __restrict__ dalpha, float* __restrict__ dx,
+                int accumulate_x) {
   constexpr int RW = POOL_BWD_RW;
   const int64_t b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,17 +149,23 @@ pool_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* 
       if (r >= nr) break;
       if (dalpha0_ext) dot[r][0] += dalpha0_ext[b];
 #pragma unroll
-      for (int g = 0; g < G; ++g) dalpha[(b * N + i0 + r) * G + g] = dot[r][g];
+      for (int g = 0; g < G; ++g) {
+        const int64_t o = (b * N + i0 + r) * G + g;
+        dalpha[o] = dalpha_ext ? dot[r][g] + dalpha_ext[o] : dot[r][g];
+      }
     }
   }
 }
 
 int launch_pool_bwd(int64_t B, int64_t N, int64_t D, const float* x, const float* alpha, const float* dpooled,
-                    const float* dalpha0_ext, float* dalpha, float* dx, int accumulate_x, cudaStream_t st) {
+                    const float* dalpha0_ext, float* dalpha, float* dx, int accumulate_x, cudaStream_t st,
+                    const float* dalpha_ext) {
   int64_t warps = cdiv(N, POOL_BWD_RW);
   if (warps > POOL_BWD_MAX_WARPS) warps = 8;
   dim3 grid((unsigned)cdiv(N, warps * POOL_BWD_RW), (unsigned)B);
-  pool_bwd_kernel<<<grid, (unsigned)(warps * 32), 0, st>>>(N, D, x, alpha, dpooled, dalpha0_ext, dalpha, dx, accumulate_x);
+  KProf kp_(st, "pool_bwd", "hbm", 4.0 * ((double)B * N * D * (dx ? 2 : 1) + (double)B * G * D));
+  pool_bwd_kernel<<<grid, (unsigned)(warps * 32), 0, st>>>(N, D, x, alpha, dpooled, dalpha0_ext, dalpha_ext, dalpha, dx,
+                                                           accumulate_x);
   return check_launch("pool_bwd");
 }
 
@@ -180,8 +188,11 @@ extern "C" int vqa_region_softmax_pool_fwd(const vqa_region_softmax_pool_fwd_par
                  p->drop.p > 0.0f ? p->drop_bits : nullptr};
   auto kern = att_logits_softmax_kernel<FuseGeneric>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<(unsigned)p->B, ATT_THREADS, smem, st>>>(fs, p->N, p->Ff, p->Wc, p->bc, p->alpha);
-  VQA_TRY(check_launch("att_logits_softmax"));
+  {
+    KProf kp_(st, "att_logits_softmax", "hbm", 4.0 * ((double)p->B * p->N * p->Ff + (double)p->B * p->N * G));
+    kern<<<(unsigned)p->B, ATT_THREADS, smem, st>>>(fs, p->N, p->Ff, p->Wc, p->bc, p->alpha);
+    VQA_TRY(check_launch("att_logits_softmax"));
+  }
   return launch_pool_fwd(p->B, p->N, p->D, p->x, p->alpha, p->pooled, st);
 }
 
@@ -194,7 +205,7 @@ extern "C" int vqa_region_softmax_pool_bwd(const vqa_region_softmax_pool_bwd_par
   if (p->B == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   VQA_TRY(launch_pool_bwd(p->B, p->N, p->D, p->x, p->alpha, p->dpooled, p->dalpha0_ext, p->dalpha, p->dx,
-                          p->accumulate_x, st));
+                          p->accumulate_x, st, p->dalpha_ext));
   if (!p->accumulate_w) {
     cudaMemsetAsync(p->dWc, 0, (size_t)G * p->Ff * sizeof(float), st);
     if (p->dbc) cudaMemsetAsync(p->dbc, 0, G * sizeof(float), st);
@@ -204,6 +215,7 @@ extern "C" int vqa_region_softmax_pool_bwd(const vqa_region_softmax_pool_bwd_par
   const int64_t groups = p->B < 2 * (int64_t)sm_count() ? p->B : 2 * (int64_t)sm_count();
   dim3 grid((unsigned)groups, (unsigned)cdiv(p->Ff, ATT_THREADS));
   const size_t smem = (size_t)2 * p->N * G * sizeof(float);
+  KProf kp_(st, "att_logits_softmax_bwd", "hbm", 4.0 * (double)p->B * p->N * p->Ff * (p->dfuse ? 2 : 1));
   att_logits_softmax_bwd_kernel<FuseGeneric, false><<<grid, ATT_THREADS, smem, st>>>(
       fs, p->B, p->N, p->Ff, p->Wc, p->alpha, p->dalpha, p->dz, p->dWc, p->dbc, p->dfuse, nullptr);
   return check_launch("att_logits_softmax_bwd");

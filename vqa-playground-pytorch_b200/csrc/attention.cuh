@@ -129,7 +129,8 @@ int launch_pool_fwd(int64_t B, int64_t N, int64_t D, const float* x, const float
                     cudaStream_t st);
 // dalpha (into dz buffer) and optional dx
 int launch_pool_bwd(int64_t B, int64_t N, int64_t D, const float* x, const float* alpha, const float* dpooled,
-                    const float* dalpha0_ext, float* dalpha, float* dx, int accumulate_x, cudaStream_t st);
+                    const float* dalpha0_ext, float* dalpha, float* dx, int accumulate_x, cudaStream_t st,
+                    const float* dalpha_ext = nullptr);
 
 // ---- backward of logits+softmax --------------------------------------------------------------
 // grid = (sample groups, cdiv(Ff, ATT_THREADS)); each thread owns one column c for its samples.

@@ -22,6 +22,21 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// Per-KERNEL record for bench.py's roofline (only while vqa_profile_begin() is active): "k:<name> <kind>=<work>" with
+// kind = hbm (algorithmic bytes of the launch) or flop (algorithmic fp32 CUDA-core flops).  The tensor-core GEMMs
+// write their own "k:<what> M.. N.. K.. g.. s.." records.
+struct KProf {
+  char label[128];
+  ProfScope ps;
+  static const char* make(char* buf, size_t cap, const char* name, const char* kind, double work) {
+    if (!prof_active()) return "k:";
+    snprintf(buf, cap, "k:%s %s=%.0f", name, kind, work);
+    return buf;
+  }
+  KProf(void* stream, const char* name, const char* kind, double work)
+      : ps(stream, make(label, sizeof(label), name, kind, work)) {}
+};
+
 #define VQA_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

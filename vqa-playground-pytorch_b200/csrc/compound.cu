@@ -103,6 +103,7 @@ extern "C" int vqa_cor_compound_fwd(const vqa_cor_compound_fwd_params* p, void* 
   VQA_REQUIRE(p->x && p->pooled && p->alpha && p->g1 && p->g2 && p->v2, "vqa_cor_compound_fwd: null pointer");
   if (p->B == 0) return VQA_OK;
   dim3 grid((unsigned)cdiv(p->D / 4, CMP_THREADS), (unsigned)p->B);
+  KProf kp_(stream, "cor_compound_fwd", "hbm", 8.0 * (double)p->B * p->N * p->D);
   cor_compound_fwd_kernel<<<grid, CMP_THREADS, 0, (cudaStream_t)stream>>>(p->N, p->D, p->x, p->pooled, p->alpha, p->g1,
                                                                           p->g2, p->v2);
   return check_launch("cor_compound_fwd");
@@ -115,6 +116,7 @@ extern "C" int vqa_cor_compound_bwd(const vqa_cor_compound_bwd_params* p, void* 
                   p->dalpha0_ext,
               "vqa_cor_compound_bwd: null pointer");
   if (p->B == 0) return VQA_OK;
+  KProf kp_(stream, "cor_compound_bwd", "hbm", 8.0 * (double)p->B * p->N * p->D);
   cor_compound_bwd_kernel<<<(unsigned)p->B, CMPB_THREADS, 0, (cudaStream_t)stream>>>(
       p->N, p->D, p->x, p->pooled, p->alpha, p->g1, p->g2, p->dv2, p->dg1, p->dg2, p->dpooled, p->dalpha0_ext);
   return check_launch("cor_compound_bwd");

@@ -429,16 +429,17 @@ dz_colsum_kernel(DzArgs a, int64_t M, int64_t N, int64_t ldz, int act, int rows_
 // Padded copy of weights whose row stride (K*4 bytes) is not a multiple of 16 and therefore cannot be
 // addressed by TMA: dst[g][r, 0..Kp) = src[g][r, 0..K) | 0 for r < rows, zero rows up to rows_pad.
 // grid = (blocks, groups)
-struct PackArgs { const float* src[MAXG]; };
+struct PackArgs { const float* src[MAXG]; int64_t ld[MAXG]; };
 __global__ void pack_rows_kernel(PackArgs a, float* __restrict__ dst, int64_t rows, int64_t rows_pad, int64_t K,
                                  int64_t Kp) {
   const int g = blockIdx.y;
   const float* src = a.src[g];
+  const int64_t ld = a.ld[g];
   float* d = dst + (size_t)g * rows_pad * Kp;
   const int64_t total = rows_pad * Kp;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = t / Kp, k = t - r * Kp;
-    d[t] = (k < K && r < rows) ? src[r * K + k] : 0.0f;
+    d[t] = (k < K && r < rows) ? src[r * ld + k] : 0.0f;
   }
 }
 
@@ -446,9 +447,9 @@ static inline int64_t roundup(int64_t x, int64_t m) { return cdiv(x, m) * m; }
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int pack_weights(const float* const* W, int groups, int64_t rows, int64_t rows_pad, int64_t K, float* dst,
-                        cudaStream_t st) {
+                        cudaStream_t st, const int64_t* ld = nullptr) {
   PackArgs a = {};
-  for (int g = 0; g < MAXG; ++g) a.src[g] = W[g < groups ? g : 0];
+  for (int g = 0; g < MAXG; ++g) { a.src[g] = W[g < groups ? g : 0]; a.ld[g] = ld ? ld[g < groups ? g : 0] : K; }
   const int64_t Kp = roundup(K, 4);
   int64_t blocks = cdiv(rows_pad * Kp, 256);
   if (blocks > 4096) blocks = 4096;
@@ -622,30 +623,43 @@ mutan_dh_kernel(int64_t M, int64_t F, int64_t Fp, int64_t rows_per, int R, const
 }  // namespace tc
 
 // ============================================================================================ linear fwd
+// Operands TMA cannot address (row stride not a multiple of 16 bytes: K = 310 / 510 activations handed over as
+// contiguous [M, K] tensors) are copied into padded scratch first — the tensor-core path is never silently
+// replaced by the CUDA-core one; what cannot be packed either is an error.
+static int tc_fail(const char* who, const char* why) {
+  set_error("%s: a tensor-core math mode was requested but %s (there is no silent CUDA-core fallback; use "
+            "math = VQA_MATH_FP32_SIMT explicitly)", who, why);
+  return VQA_EINVAL;
+}
+
 int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
   using namespace tc;
-  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return VQA_TC_UNSUPPORTED;
-  if (p->M > INT32_MAX || p->K > INT32_MAX || p->N > INT32_MAX) return VQA_TC_UNSUPPORTED;
-  bool pack = false;
+  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return tc_fail("vqa_linear_fwd", "this math mode is not built for this op");
+  if (p->M > INT32_MAX || p->K > INT32_MAX || p->N > INT32_MAX) return tc_fail("vqa_linear_fwd", "a dimension exceeds 2^31");
+  bool pack = false, packx = false;
   for (int g = 0; g < p->groups; ++g) {
-    if (!tma_ok(p->X[g], p->ldx[g])) return VQA_TC_UNSUPPORTED;
+    packx |= !tma_ok(p->X[g], p->ldx[g]);
     pack |= !tma_ok(p->W[g], p->K);
   }
   const int64_t Kp = roundup(p->K, 4);
-  float* wpk = reinterpret_cast<float*>(p->workspace);
   bool prepacked = pack;
   for (int g = 0; g < p->groups; ++g) prepacked &= p->Wp[g] != nullptr;
-  if (pack && !prepacked) {
-    if (!wpk || p->workspace_bytes < (size_t)p->groups * p->N * Kp * sizeof(float) ||
-        reinterpret_cast<uintptr_t>(wpk) % 16 != 0)
-      return VQA_TC_UNSUPPORTED;
-    VQA_TRY(pack_weights(p->W, p->groups, p->N, p->N, p->K, wpk, st));
+  const size_t w_bytes = (pack && !prepacked) ? align256((size_t)p->groups * p->N * Kp * sizeof(float)) : 0;
+  const size_t x_bytes = packx ? align256((size_t)p->groups * p->M * Kp * sizeof(float)) : 0;
+  if (w_bytes + x_bytes) {
+    if (!p->workspace || p->workspace_bytes < w_bytes + x_bytes || reinterpret_cast<uintptr_t>(p->workspace) % 16 != 0)
+      return tc_fail("vqa_linear_fwd", "the workspace is missing, misaligned or smaller than vqa_linear_fwd_workspace_bytes()");
   }
+  float* wpk = reinterpret_cast<float*>(p->workspace);
+  float* xpk = reinterpret_cast<float*>(reinterpret_cast<char*>(p->workspace) + w_bytes);
+  if (w_bytes) VQA_TRY(pack_weights(p->W, p->groups, p->N, p->N, p->K, wpk, st));
+  if (x_bytes) VQA_TRY(pack_weights(p->X, p->groups, p->M, p->M, p->K, xpk, st, p->ldx));
   const int bn = pick_bn(p->N);
   Params<EpiBiasAct> q = {};
   for (int g = 0; g < MAXG; ++g) {
     const int s = g < p->groups ? g : 0;
-    VQA_TRY(operand_tmap(&q.tmA[g], p->X[s], false, p->M, p->K, p->ldx[s], BM));
+    if (packx) VQA_TRY(operand_tmap(&q.tmA[g], xpk + (size_t)s * p->M * Kp, false, p->M, p->K, Kp, BM));
+    else VQA_TRY(operand_tmap(&q.tmA[g], p->X[s], false, p->M, p->K, p->ldx[s], BM));
     if (prepacked) VQA_TRY(operand_tmap(&q.tmB[g], p->Wp[s], false, p->N, p->K, Kp, bn));
     else if (pack) VQA_TRY(operand_tmap(&q.tmB[g], wpk + (size_t)s * p->N * Kp, false, p->N, p->K, Kp, bn));
     else VQA_TRY(operand_tmap(&q.tmB[g], p->W[s], false, p->N, p->K, p->K, bn));
@@ -710,29 +724,33 @@ static int dgrad_launch(const vqa_linear_bwd_params* p, float* dz, float* wpk, i
 
 int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
   using namespace tc;
-  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return VQA_TC_UNSUPPORTED;
-  if (p->M > INT32_MAX || p->K > INT32_MAX || p->N > INT32_MAX) return VQA_TC_UNSUPPORTED;
+  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return tc_fail("vqa_linear_bwd", "this math mode is not built for this op");
+  if (p->M > INT32_MAX || p->K > INT32_MAX || p->N > INT32_MAX) return tc_fail("vqa_linear_bwd", "a dimension exceeds 2^31");
   const bool x3 = p->math == VQA_MATH_TF32X3;
   const int64_t ldz = roundup(p->N, 32);
   const int64_t Kp = roundup(p->K, 4);
   const size_t dz_bytes = align256((size_t)p->groups * p->M * ldz * sizeof(float));
-  bool any_w = false, any_x = false, pack = false;
+  bool any_w = false, any_x = false, pack = false, packx = false;
   for (int g = 0; g < p->groups; ++g) {
-    if (!tma_ok(p->X[g], p->ldx[g])) return VQA_TC_UNSUPPORTED;
     any_w |= p->dW[g] != nullptr || p->db[g] != nullptr;
     if (p->dX[g]) {
       any_x = true;
       pack |= !tma_ok(p->W[g], p->K);
     }
   }
-  const size_t need = dz_bytes + (pack ? (size_t)p->groups * p->N * Kp * sizeof(float) : 0);
-  if (!p->workspace || p->workspace_bytes < need) return VQA_TC_UNSUPPORTED;
-  float* dz = reinterpret_cast<float*>(p->workspace);
-  float* wpk = reinterpret_cast<float*>(reinterpret_cast<char*>(p->workspace) + dz_bytes);
-  if (reinterpret_cast<uintptr_t>(dz) % 16 != 0) return VQA_TC_UNSUPPORTED;
+  if (any_w)
+    for (int g = 0; g < p->groups; ++g) packx |= !tma_ok(p->X[g], p->ldx[g]);
   bool prepacked = pack;
   for (int g = 0; g < p->groups; ++g) prepacked &= p->Wp[g] != nullptr;
-  if (pack && !prepacked) VQA_TRY(pack_weights(p->W, p->groups, p->N, p->N, p->K, wpk, st));
+  const size_t w_bytes = (pack && !prepacked) ? align256((size_t)p->groups * p->N * Kp * sizeof(float)) : 0;
+  const size_t x_bytes = packx ? align256((size_t)p->groups * p->M * Kp * sizeof(float)) : 0;
+  if (!p->workspace || p->workspace_bytes < dz_bytes + w_bytes + x_bytes || reinterpret_cast<uintptr_t>(p->workspace) % 16 != 0)
+    return tc_fail("vqa_linear_bwd", "the workspace is missing, misaligned or smaller than vqa_linear_bwd_workspace_bytes()");
+  float* dz = reinterpret_cast<float*>(p->workspace);
+  float* wpk = reinterpret_cast<float*>(reinterpret_cast<char*>(p->workspace) + dz_bytes);
+  float* xpk = reinterpret_cast<float*>(reinterpret_cast<char*>(p->workspace) + dz_bytes + w_bytes);
+  if (w_bytes) VQA_TRY(pack_weights(p->W, p->groups, p->N, p->N, p->K, wpk, st));
+  if (x_bytes) VQA_TRY(pack_weights(p->X, p->groups, p->M, p->M, p->K, xpk, st, p->ldx));
 
   // 1. dZ (padded) + bias gradient
   {
@@ -747,6 +765,7 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
         if (p->db[g]) cudaMemsetAsync(p->db[g], 0, (size_t)p->N * sizeof(float), st);
     const int rows_per_cta = 64;
     dim3 grid((unsigned)cdiv(ldz, 32), (unsigned)cdiv(p->M, rows_per_cta), (unsigned)p->groups);
+    KProf kp_(st, "dz_colsum", "hbm", 4.0 * (double)p->groups * p->M * p->N * (p->act != VQA_ACT_NONE ? 3 : 2));
     dz_colsum_kernel<<<grid, 256, 0, st>>>(a, p->M, p->N, ldz, p->act, rows_per_cta);
     VQA_TRY(check_launch("tc_linear_bwd.dz"));
   }
@@ -756,7 +775,8 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
     const int bn = pick_bn(p->N);
     for (int g = 0; g < MAXG; ++g) {
       const int s = g < p->groups ? g : 0;
-      VQA_TRY(operand_tmap(&q.tmA[g], p->X[s], true, p->K, p->M, p->ldx[s], BM));
+      if (packx) VQA_TRY(operand_tmap(&q.tmA[g], xpk + (size_t)s * p->M * Kp, true, p->K, p->M, Kp, BM));
+      else VQA_TRY(operand_tmap(&q.tmA[g], p->X[s], true, p->K, p->M, p->ldx[s], BM));
       VQA_TRY(operand_tmap(&q.tmB[g], dz + (size_t)s * p->M * ldz, true, p->N, p->M, ldz, bn));
       q.epi.dW[g] = p->dW[s];
     }
@@ -782,10 +802,12 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
 // ============================================================================================ Mutan
 // Workspace layout (floats): W1pk [R*Fp, K1p] | W2pk [R*Fp, K2p] | dH1cat [M, R*Fp] | dH2cat [Mh, R*Fp]
 struct MutanWs {
-  float *w1pk, *w2pk, *dh1, *dh2;
+  float *w1pk, *w2pk, *dh1, *dh2, *x1pk, *x2pk;
   size_t bytes;
 };
-static MutanWs mutan_ws(void* base, int R, int64_t M, int64_t Mh, int64_t K1, int64_t K2, int64_t F, bool bwd) {
+// packx1 / packx2: X1 / X2 are not TMA-addressable as given and get a padded copy
+static MutanWs mutan_ws(void* base, int R, int64_t M, int64_t Mh, int64_t K1, int64_t K2, int64_t F, bool bwd,
+                        bool packx1 = false, bool packx2 = false) {
   using namespace tc;
   const int64_t Fp = roundup(F, 32), K1p = roundup(K1, 4), K2p = roundup(K2, 4);
   char* b = reinterpret_cast<char*>(base);
@@ -796,24 +818,31 @@ static MutanWs mutan_ws(void* base, int R, int64_t M, int64_t Mh, int64_t K1, in
   w.w2pk = take(R * Fp * K2p);
   w.dh1 = bwd ? take(M * R * Fp) : nullptr;
   w.dh2 = bwd ? take(Mh * R * Fp) : nullptr;
+  w.x1pk = packx1 ? take(M * K1p) : nullptr;
+  w.x2pk = packx2 ? take(Mh * K2p) : nullptr;
   w.bytes = off;
   return w;
 }
 size_t tc_mutan_ws(int math, int R, int64_t M, int64_t rows_per, int64_t K1, int64_t K2, int64_t F, int bwd) {
   if (math == VQA_MATH_FP32_SIMT) return 0;
-  return mutan_ws(nullptr, R, M, M / rows_per, K1, K2, F, bwd != 0).bytes;
+  return mutan_ws(nullptr, R, M, M / rows_per, K1, K2, F, bwd != 0, K1 % 4 != 0, K2 % 4 != 0).bytes;   // upper bound
 }
 
 int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
   using namespace tc;
-  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return VQA_TC_UNSUPPORTED;
-  if (!tma_ok(p->X1, p->ldx1) || !tma_ok(p->X2, p->ldx2) || p->M > INT32_MAX) return VQA_TC_UNSUPPORTED;
+  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return tc_fail("vqa_mutan_fwd", "this math mode is not built for this op");
+  if (p->M > INT32_MAX) return tc_fail("vqa_mutan_fwd", "a dimension exceeds 2^31");
   const int64_t Mh = p->M / p->rows_per_h2;
-  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, false);
+  const bool packx1 = !tma_ok(p->X1, p->ldx1), packx2 = !tma_ok(p->X2, p->ldx2);
+  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, false, packx1, packx2);
   if (!p->workspace || p->workspace_bytes < w.bytes || reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0)
-    return VQA_TC_UNSUPPORTED;
+    return tc_fail("vqa_mutan_fwd", "the workspace is missing, not 256-byte aligned or smaller than vqa_mutan_workspace_bytes()");
   const bool x3 = p->math == VQA_MATH_TF32X3;
   const int64_t Fp = roundup(p->F, 32), K1p = roundup(p->K1, 4), K2p = roundup(p->K2, 4);
+  const float* X1 = p->X1; const float* X2 = p->X2;
+  int64_t ldx1 = p->ldx1, ldx2 = p->ldx2;
+  if (packx1) { VQA_TRY(pack_weights(&p->X1, 1, p->M, p->M, p->K1, w.x1pk, st, &p->ldx1)); X1 = w.x1pk; ldx1 = K1p; }
+  if (packx2) { VQA_TRY(pack_weights(&p->X2, 1, Mh, Mh, p->K2, w.x2pk, st, &p->ldx2)); X2 = w.x2pk; ldx2 = K2p; }
   if (p->W1p && p->W2p) {
     w.w1pk = const_cast<float*>(p->W1p); w.w2pk = const_cast<float*>(p->W2p);
   } else {
@@ -825,7 +854,7 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
     Params<EpiBiasAct> q = {};
     for (int g = 0; g < MAXG; ++g) {
       const int s = g < p->R ? g : 0;
-      VQA_TRY(operand_tmap(&q.tmA[g], p->X2, false, Mh, p->K2, p->ldx2, BM));
+      VQA_TRY(operand_tmap(&q.tmA[g], X2, false, Mh, p->K2, ldx2, BM));
       VQA_TRY(operand_tmap(&q.tmB[g], w.w2pk + (size_t)s * Fp * K2p, false, p->F, p->K2, K2p, bn));
       q.epi.Y[g] = p->H2 + (size_t)s * Mh * p->F; q.epi.bias[g] = p->b2[s]; q.epi.ld[g] = p->F;
     }
@@ -839,7 +868,7 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
   auto fill = [&](Params<EpiMutan>& q, int r0) -> int {
     for (int g = 0; g < MAXG; ++g) {
       const int r = (r0 + g) < p->R ? (r0 + g) : r0;
-      VQA_TRY(operand_tmap(&q.tmA[g], p->X1, false, p->M, p->K1, p->ldx1, BM));
+      VQA_TRY(operand_tmap(&q.tmA[g], X1, false, p->M, p->K1, ldx1, BM));
       VQA_TRY(operand_tmap(&q.tmB[g], w.w1pk + (size_t)r * Fp * K1p, false, p->F, p->K1, K1p, bn));
       q.epi.bias[g] = p->b1[r]; q.epi.H2[g] = p->H2 + (size_t)r * Mh * p->F;
       q.epi.H1[g] = p->H1 ? p->H1 + (size_t)r * p->M * p->F : nullptr;
@@ -869,15 +898,20 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
 
 int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
   using namespace tc;
-  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return VQA_TC_UNSUPPORTED;
-  if (!tma_ok(p->X1, p->ldx1) || !tma_ok(p->X2, p->ldx2) || p->M > INT32_MAX) return VQA_TC_UNSUPPORTED;
+  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return tc_fail("vqa_mutan_bwd", "this math mode is not built for this op");
+  if (p->M > INT32_MAX) return tc_fail("vqa_mutan_bwd", "a dimension exceeds 2^31");
   const int64_t Mh = p->M / p->rows_per_h2;
-  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, true);
+  const bool packx1 = !tma_ok(p->X1, p->ldx1), packx2 = !tma_ok(p->X2, p->ldx2);
+  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, true, packx1, packx2);
   if (!p->workspace || p->workspace_bytes < w.bytes || reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0)
-    return VQA_TC_UNSUPPORTED;
+    return tc_fail("vqa_mutan_bwd", "the workspace is missing, not 256-byte aligned or smaller than vqa_mutan_workspace_bytes()");
   const bool x3 = p->math == VQA_MATH_TF32X3;
   const int R = p->R;
   const int64_t Fp = roundup(p->F, 32), K1p = roundup(p->K1, 4), K2p = roundup(p->K2, 4), RF = R * Fp;
+  const float* X1 = p->X1; const float* X2 = p->X2;
+  int64_t ldx1 = p->ldx1, ldx2 = p->ldx2;
+  if (packx1) { VQA_TRY(pack_weights(&p->X1, 1, p->M, p->M, p->K1, w.x1pk, st, &p->ldx1)); X1 = w.x1pk; ldx1 = K1p; }
+  if (packx2) { VQA_TRY(pack_weights(&p->X2, 1, Mh, Mh, p->K2, w.x2pk, st, &p->ldx2)); X2 = w.x2pk; ldx2 = K2p; }
   if (p->W1p && p->W2p) {
     w.w1pk = const_cast<float*>(p->W1p); w.w2pk = const_cast<float*>(p->W2p);
   } else {
@@ -897,6 +931,7 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
     const bool vec2 = p->F % 2 == 0 && p->lddy % 2 == 0 && reinterpret_cast<uintptr_t>(p->dY) % 8 == 0 &&
                       reinterpret_cast<uintptr_t>(p->H1) % 8 == 0;
     const dim3 grid((unsigned)Mh, (unsigned)R);
+    KProf kp_(st, "mutan_dh", "hbm", 4.0 * (double)p->M * p->F * (1.0 + 2.0 * R));
     if (vec2)
       mutan_dh_kernel<2><<<grid, 256, 0, st>>>(p->M, p->F, Fp, p->rows_per_h2, R, p->dY, p->lddy, p->H1, p->H2, w.dh1,
                                               w.dh2, db1, db2);
@@ -937,9 +972,9 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
     if (q.epi.atomic && !accumulate) zero_window(dX, lddx, rows, Kin, st);
     return launch(q, 1, x3, st, what);
   };
-  VQA_TRY(wgrad(p->X1, p->ldx1, p->M, p->K1, w.dh1, p->dW1, "tc_mutan_bwd.dw1"));
+  VQA_TRY(wgrad(X1, ldx1, p->M, p->K1, w.dh1, p->dW1, "tc_mutan_bwd.dw1"));
   if (p->dX1) VQA_TRY(dgrad(w.dh1, p->M, w.w1pk, p->K1, K1p, p->dX1, p->lddx1, p->accumulate_x1, "tc_mutan_bwd.dx1"));
-  VQA_TRY(wgrad(p->X2, p->ldx2, Mh, p->K2, w.dh2, p->dW2, "tc_mutan_bwd.dw2"));
+  VQA_TRY(wgrad(X2, ldx2, Mh, p->K2, w.dh2, p->dW2, "tc_mutan_bwd.dw2"));
   if (p->dX2) VQA_TRY(dgrad(w.dh2, Mh, w.w2pk, p->K2, K2p, p->dX2, p->lddx2, p->accumulate_x2, "tc_mutan_bwd.dx2"));
   return VQA_OK;
 }
@@ -987,19 +1022,23 @@ int tc_dropout_bits_batch(float pdrop, uint64_t seed, const uint64_t* seed_dev, 
   if (a.first[nsegs] == 0) return VQA_OK;
   uint64_t blocks = (a.first[nsegs] + 255) / 256;
   if (blocks > 16384) blocks = 16384;
+  KProf kp_(st, "dropout_bits_batch", "hbm", (double)a.first[nsegs] * 2.0);
   tc::dropout_bits_batch_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed, seed_dev, drop_threshold(pdrop), a);
   return check_launch("dropout_bits_batch");
 }
 
+// Upper bounds: a K that is not a multiple of 4 floats makes W (and a contiguous [M, K] X) un-addressable by TMA.
 size_t tc_linear_fwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N) {
-  (void)M;
   if (math == VQA_MATH_FP32_SIMT || K % 4 == 0) return 0;
-  return tc::align256((size_t)groups * N * tc::roundup(K, 4) * sizeof(float));
+  return tc::align256((size_t)groups * N * tc::roundup(K, 4) * sizeof(float)) +
+         tc::align256((size_t)groups * M * tc::roundup(K, 4) * sizeof(float));
 }
 size_t tc_linear_bwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N) {
   if (math == VQA_MATH_FP32_SIMT) return 0;
   size_t b = tc::align256((size_t)groups * M * tc::roundup(N, 32) * sizeof(float));
-  if (K % 4 != 0) b += tc::align256((size_t)groups * N * tc::roundup(K, 4) * sizeof(float));
+  if (K % 4 != 0)
+    b += tc::align256((size_t)groups * N * tc::roundup(K, 4) * sizeof(float)) +
+         tc::align256((size_t)groups * M * tc::roundup(K, 4) * sizeof(float));
   return b;
 }
 

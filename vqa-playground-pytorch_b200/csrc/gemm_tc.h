@@ -4,9 +4,8 @@
 
 namespace vqa {
 
-// Returned when the tensor-core path does not cover a shape/flag combination; the caller then
-// uses the fp32 CUDA-core kernel (still on the GPU, strictly more precise — never a CPU path).
-constexpr int VQA_TC_UNSUPPORTED = 999;
+// A tensor-core math mode that cannot run as asked (unbuilt mode, workspace too small, operand TMA cannot address
+// and that cannot be packed) is an error (VQA_EINVAL with a message) — never a silent CUDA-core fallback.
 
 int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st);
 int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st);

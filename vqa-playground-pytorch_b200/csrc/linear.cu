@@ -170,10 +170,7 @@ extern "C" int vqa_linear_fwd(const vqa_linear_fwd_params* p, void* stream) {
                 "vqa_linear_fwd: group %d has a null pointer or a short leading dimension", g);
   if (p->M == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->math != VQA_MATH_FP32_SIMT) {
-    int rc = tc_linear_fwd(p, st);
-    if (rc != VQA_TC_UNSUPPORTED) return rc;
-  }
+  if (p->math != VQA_MATH_FP32_SIMT) return tc_linear_fwd(p, st);      // tensor-core modes never fall back to the CUDA-core GEMM
   XDropLoader a; WLoader b; BiasActStore e;
   a.K = p->K; b.K = p->K; e.act = p->act;
   a.d = make_drop(p->p, p->seed, 0, 0, 1, p->seed_dev);
@@ -204,10 +201,7 @@ extern "C" int vqa_linear_bwd(const vqa_linear_bwd_params* p, void* stream) {
                 "vqa_linear_bwd: the pooling addend needs one group, dX, K %% 4 == 0 and M a multiple of pool_regions");
   if (p->M == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->math != VQA_MATH_FP32_SIMT) {
-    int rc = tc_linear_bwd(p, st);
-    if (rc != VQA_TC_UNSUPPORTED) return rc;
-  }
+  if (p->math != VQA_MATH_FP32_SIMT) return tc_linear_bwd(p, st);      // tensor-core modes never fall back to the CUDA-core GEMM
   if (any_w) {
     DzT_Loader a; XDropT_Loader b; WgradStore e;
     a.act = p->act; b.K = p->K; e.K = p->K; e.accumulate = p->accumulate_w;

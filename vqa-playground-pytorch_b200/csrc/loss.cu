@@ -70,6 +70,7 @@ extern "C" int vqa_kld_logsoftmax_fwd_bwd(const vqa_kld_logsoftmax_params* p, vo
   VQA_REQUIRE(p->B >= 0 && p->C >= 1, "vqa_kld_logsoftmax_fwd_bwd: bad shape");
   VQA_REQUIRE(p->logits && p->target && p->loss_rows, "vqa_kld_logsoftmax_fwd_bwd: null pointer");
   if (p->B == 0) return VQA_OK;
+  KProf kp_(stream, "kld_logsoftmax", "hbm", 12.0 * (double)p->B * p->C);
   kld_logsoftmax_kernel<<<(unsigned)p->B, LOSS_THREADS, 0, (cudaStream_t)stream>>>(p->C, p->grad_scale, p->logits,
                                                                                   p->target, p->loss_rows, p->dlogits);
   return check_launch("kld_logsoftmax");

@@ -186,10 +186,7 @@ extern "C" int vqa_mutan_fwd(const vqa_mutan_fwd_params* p, void* stream) {
   for (int r = 0; r < p->R; ++r) VQA_REQUIRE(p->W1[r] && p->W2[r], "vqa_mutan_fwd: null weight for rank %d", r);
   if (p->M == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->math != VQA_MATH_FP32_SIMT) {
-    int rc = tc_mutan_fwd(p, st);
-    if (rc != VQA_TC_UNSUPPORTED) return rc;
-  }
+  if (p->math != VQA_MATH_FP32_SIMT) return tc_mutan_fwd(p, st);      // tensor-core modes never fall back to the CUDA-core GEMM
   const int64_t Mh = p->M / p->rows_per_h2;
   {
     PlainLoader a{p->X2, p->ldx2};
@@ -229,10 +226,7 @@ extern "C" int vqa_mutan_bwd(const vqa_mutan_bwd_params* p, void* stream) {
   for (int r = 0; r < p->R; ++r) VQA_REQUIRE(p->W1[r] && p->W2[r], "vqa_mutan_bwd: null weight for rank %d", r);
   if (p->M == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->math != VQA_MATH_FP32_SIMT) {
-    int rc = tc_mutan_bwd(p, st);
-    if (rc != VQA_TC_UNSUPPORTED) return rc;
-  }
+  if (p->math != VQA_MATH_FP32_SIMT) return tc_mutan_bwd(p, st);      // tensor-core modes never fall back to the CUDA-core GEMM
   const int64_t Mh = p->M / p->rows_per_h2;
   const int64_t RF = (int64_t)p->R * p->F;
 

@@ -360,6 +360,7 @@ extern "C" int vqa_oda_pair_attn_fwd(const vqa_oda_pair_attn_fwd_params* p, void
     dim3 grid((unsigned)cdiv(cdiv(NH, ODA_EPT), ODA_THREADS), (unsigned)p->B);
     const size_t smem = (size_t)(ODA_THREADS / 32) * p->N * G * sizeof(float);
     VQA_REQUIRE(smem <= 48 * 1024, "vqa_oda_pair_attn_fwd: N=%lld too large", (long long)p->N);
+    KProf kp_(st, "oda_pair_logits_train", "flop", (double)p->B * p->N * p->N * p->H * (2.0 * G + 2.0));
     oda_pair_logits_train_kernel<<<grid, ODA_THREADS, smem, st>>>(p->N, p->H, d, p->vl, p->ql, p->W, p->alpha);
     VQA_TRY(check_launch("oda_pair_logits_train"));
     softmax_regions_kernel<<<(unsigned)p->B, 128, (size_t)p->N * G * sizeof(float), st>>>(p->N, p->alpha);
@@ -399,6 +400,7 @@ extern "C" int vqa_oda_pair_attn_bwd(const vqa_oda_pair_attn_bwd_params* p, void
   cudaMemsetAsync(p->dql, 0, (size_t)p->B * p->H * sizeof(float), st);
   {
     dim3 grid((unsigned)cdiv(cdiv(NH, ODA_EPT), 128), (unsigned)cdiv(p->B, ODA_BCHUNK));
+    KProf kp_(st, "oda_pair_bwd_train_e", "flop", (double)p->B * p->N * p->N * p->H * (4.0 * G + 4.0));
     oda_pair_bwd_train_e_kernel<<<grid, 128, 0, st>>>(p->B, p->N, p->H, d, p->vl, p->ql, p->W, p->dz, p->dW, p->dvl,
                                                       p->dql);
     VQA_TRY(check_launch("oda_pair_bwd_train_e"));
@@ -411,6 +413,7 @@ extern "C" int vqa_oda_pair_attn_bwd(const vqa_oda_pair_attn_bwd_params* p, void
     auto kern = KS == 20 ? oda_pair_bwd_train_plus_kernel<20> : oda_pair_bwd_train_plus_kernel<0>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((unsigned)cdiv(p->N, ODA_IC), (unsigned)p->B);
+    KProf kp_(st, "oda_pair_bwd_train_plus", "flop", (double)p->B * p->N * p->N * p->H * (2.0 * G + 1.0));
     kern<<<grid, threads, smem, st>>>(p->N, p->H, d, p->ql, p->W, p->dz, p->dvl);
     VQA_TRY(check_launch("oda_pair_bwd_train_plus"));
   }

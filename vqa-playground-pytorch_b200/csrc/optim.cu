@@ -34,11 +34,27 @@ struct SegTable { vqa_param_segment s[VQA_MAX_PARAM_SEGMENTS]; };
 
 // grid = (blocks, segments).  Same arithmetic, in the same order, as torch.optim.Adam's single-tensor path:
 //   g *= clip;  m = m + (g - m)(1 - b1);  v = b2 v + (1 - b2) g g;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// *step += 1 and, with a decay factor, *lr *= gamma: the reference's scheduler.step() (ExponentialLR) runs BEFORE
+// optimizer.step() (train.py:75-76, :296), so the decayed rate is the one this update uses.
+__global__ void adam_tick_kernel(int64_t* __restrict__ step, double* __restrict__ lr, double gamma) {
+  *step += 1;
+  if (lr && gamma > 0.0) *lr *= gamma;
+}
+
+// step_dev / lr_dev non-null: the step count (already ticked) and the learning rate are read from device memory, so the
+// launch is identical every step and can be replayed from a CUDA graph.
 __global__ void __launch_bounds__(OPT_THREADS)
 clip_adam_kernel(SegTable tab, float* __restrict__ grads, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                  const float* __restrict__ sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
-                 float bias_c1, float sqrt_bias_c2, int write_grads) {
+                 float bias_c1, float sqrt_bias_c2, int write_grads, const int64_t* __restrict__ step_dev,
+                 const double* __restrict__ lr_dev) {
   const vqa_param_segment sg = tab.s[blockIdx.y];
+  if (step_dev) {
+    const double t = (double)__ldg(step_dev);
+    bias_c1 = (float)(1.0 - pow((double)beta1, t));
+    sqrt_bias_c2 = (float)sqrt(1.0 - pow((double)beta2, t));
+  }
+  if (lr_dev) lr = (float)__ldg(lr_dev);
   float clip = 1.0f;
   if (max_norm > 0.0f) {
     const float c = max_norm / (sqrtf(__ldg(sumsq)) + 1e-6f);      // clip_grad_norm_: coef clamped to 1
@@ -66,7 +82,8 @@ extern "C" int vqa_clip_adam_step(const vqa_clip_adam_params* p, void* stream) {
   VQA_REQUIRE(p != nullptr, "vqa_clip_adam_step: null params");
   VQA_REQUIRE(p->nsegs >= 0 && p->nsegs <= VQA_MAX_PARAM_SEGMENTS && p->segs, "vqa_clip_adam_step: bad segment table");
   VQA_REQUIRE(p->grads_flat && p->exp_avg && p->exp_avg_sq && p->total >= 0, "vqa_clip_adam_step: null buffer");
-  VQA_REQUIRE(p->step >= 1 && p->beta1 >= 0.0f && p->beta1 < 1.0f && p->beta2 >= 0.0f && p->beta2 < 1.0f && p->eps >= 0.0f,
+  VQA_REQUIRE((p->step >= 1 || p->step_dev) && p->beta1 >= 0.0f && p->beta1 < 1.0f && p->beta2 >= 0.0f &&
+                  p->beta2 < 1.0f && p->eps >= 0.0f,
               "vqa_clip_adam_step: bad hyper-parameter (step counts from 1)");
   VQA_REQUIRE(p->max_norm <= 0.0f || p->scratch, "vqa_clip_adam_step: clipping needs the 1-float scratch");
   VQA_REQUIRE(reinterpret_cast<uintptr_t>(p->grads_flat) % 16 == 0, "vqa_clip_adam_step: grads_flat must be 16-byte aligned");
@@ -88,12 +105,16 @@ extern "C" int vqa_clip_adam_step(const vqa_clip_adam_params* p, void* stream) {
     sumsq_kernel<<<(unsigned)blocks, OPT_THREADS, 0, st>>>(p->total, p->grads_flat, p->scratch);
     VQA_TRY(check_launch("sumsq"));
   }
-  const double bc1 = 1.0 - pow((double)p->beta1, (double)p->step);
-  const double bc2 = 1.0 - pow((double)p->beta2, (double)p->step);
+  if (p->step_dev) {
+    adam_tick_kernel<<<1, 1, 0, st>>>(p->step_dev, p->lr_dev, p->lr_gamma);
+    VQA_TRY(check_launch("adam_tick"));
+  }
+  const double bc1 = p->step_dev ? 1.0 : 1.0 - pow((double)p->beta1, (double)p->step);
+  const double bc2 = p->step_dev ? 1.0 : 1.0 - pow((double)p->beta2, (double)p->step);
   int64_t blocks = cdiv(biggest, OPT_THREADS * 4);
   if (blocks > 1024) blocks = 1024;
   clip_adam_kernel<<<dim3((unsigned)blocks, (unsigned)p->nsegs), OPT_THREADS, 0, st>>>(
       tab, p->grads_flat, p->exp_avg, p->exp_avg_sq, p->scratch, p->max_norm, p->lr, p->beta1, p->beta2, p->eps,
-      (float)bc1, (float)sqrt(bc2), p->write_clipped_grads);
+      (float)bc1, (float)sqrt(bc2), p->write_clipped_grads, p->step_dev, p->lr_dev);
   return check_launch("clip_adam");
 }

@@ -78,32 +78,51 @@ class HostPrefetcher:
 
 
 class GraphedStep:
-    """fwd + KLD loss + bwd of one fixed-shape batch captured in a CUDA graph and replayed every step.
+    """fwd + KLD loss + bwd (+ gradient all-reduce, + optimizer step) of one fixed-shape batch captured in a CUDA graph
+    and replayed every step.
 
     Everything the step launches (the forward plan, the loss kernel, the backward plan — ~90 kernels and memsets)
     becomes one graph launch, which removes the per-launch CPU cost and most of the inter-kernel gaps.  The Philox
     dropout key lives in device memory (`model.seed_device`) and is advanced by a kernel captured at the head of
-    the graph, so every replay draws a fresh mask.  With a data-parallel engine the gradient all-reduce runs
-    after the replay (engine.after_backward / wait), outside the graph.
+    the graph, so every replay draws a fresh mask; the model reads that key only inside this step (eager forwards
+    keep drawing their own keys from ops.next_seed()).  The initial key comes from ops.next_seed() mixed with the
+    rank, so `ops.manual_seed()` controls it and data-parallel ranks draw different masks.
+    `optimizer` (an optim.FusedClipAdam with device_clock=True) puts clip_grad_norm_ + Adam of train.py:82-86 in
+    the graph as well.
 
         step = GraphedStep(model, example_sample, engine)     # warms up, then captures
         loss = step(sample)                                   # copies the sample into the static buffers, replays
     """
 
-    def __init__(self, model, example, engine=None, warmup=3, seed=0x5EED0000, capture_collectives=False):
+    def __init__(self, model, example, engine=None, warmup=3, seed=None, capture_collectives=False, optimizer=None):
         dev = example["v"].device
-        self.model, self.engine = model, engine
+        self.model, self.engine, self.optimizer = model, engine, optimizer
+        if optimizer is not None and not getattr(optimizer, "device_clock", False):
+            raise ValueError("GraphedStep: the optimizer must keep its step count on the device "
+                             "(optim.FusedClipAdam(..., device_clock=True)) to be captured")
         self.static = {k: torch.empty_like(t) for k, t in example.items() if torch.is_tensor(t)}
         for k, t in self.static.items():
             t.copy_(example[k])
+        if seed is None:
+            rank = torch.distributed.get_rank() if (torch.distributed.is_available() and
+                                                    torch.distributed.is_initialized()) else 0
+            seed = (ops.next_seed() ^ (rank * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF
         model.seed_device = torch.tensor([seed], dtype=torch.int64, device=dev)
         self._one = torch.ones((), dtype=torch.float32, device=dev)
         # capture_collectives: the bucketed NCCL all-reduces are captured INSIDE the graph, each forked off the backward
         # at its bucket's gradient-group events, so that communication overlaps the remaining backward kernels of the
         # same replay.  Otherwise the reduction runs after the replay (nothing to overlap with).
         self.capture_collectives = bool(capture_collectives) and engine is not None and engine.world_size > 1
+        if optimizer is not None and engine is not None and engine.world_size > 1 and not self.capture_collectives:
+            raise ValueError("GraphedStep: a captured optimizer step needs the all-reduce in the graph too "
+                             "(capture_collectives=True)")
         if engine is not None:
             engine.defer = not self.capture_collectives
+        # the warm-up steps update the parameters and the optimizer state when an optimizer is captured: restore after
+        saved = None
+        if optimizer is not None:
+            saved = ([p.detach().clone() for p in model.parameters()], optimizer.exp_avg.clone(),
+                     optimizer.exp_avg_sq.clone(), optimizer.step_dev.clone(), optimizer.lr_dev.clone())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -121,18 +140,31 @@ class GraphedStep:
         with torch.cuda.graph(self.graph, stream=side, **mode):
             self.loss = self._body()
         self.launches_per_replay = int(_lib.lib().vqa_launch_count() - n0)    # libvqacore kernels inside the graph
+        if saved is not None:
+            with torch.no_grad():
+                for p, t in zip(model.parameters(), saved[0]):
+                    p.copy_(t)
+                optimizer.exp_avg.copy_(saved[1]); optimizer.exp_avg_sq.copy_(saved[2])
+                optimizer.step_dev.copy_(saved[3]); optimizer.lr_dev.copy_(saved[4])
+        model.seed_device.fill_(seed)            # replays continue from the initial key, whatever the warm-up drew
 
     def _body(self):
-        if self.model.training:
-            ops.seed_advance(self.model.seed_device)
-        out = self.model(self.static)
-        loss = kld_loss(out, self.static["a"])
-        if self.engine is None:
-            for p in self.model.parameters():
-                p.grad = None
-        loss.backward(gradient=self._one)       # preallocated seed gradient: no fill kernel per step
-        if self.capture_collectives:
-            self.engine.wait()                  # joins the communication stream back into the capturing stream
+        self.model.use_seed_device = True
+        try:
+            if self.model.training:
+                ops.seed_advance(self.model.seed_device)
+            out = self.model(self.static)
+            loss = kld_loss(out, self.static["a"])
+            if self.engine is None:
+                for p in self.model.parameters():
+                    p.grad = None
+            loss.backward(gradient=self._one)       # preallocated seed gradient: no fill kernel per step
+            if self.capture_collectives:
+                self.engine.wait()                  # joins the communication stream back into the capturing stream
+            if self.optimizer is not None:
+                self.optimizer.step()
+        finally:
+            self.model.use_seed_device = False
         self.logits = out
         return loss
 

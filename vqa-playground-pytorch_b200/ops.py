@@ -58,6 +58,17 @@ def _math(math):
     return _lib.MATH_BY_NAME[math] if isinstance(math, str) else int(math)
 
 
+def _repack_bytes(tensors, K):
+    """Extra scratch for operands TMA cannot address as given (base not 16-byte aligned or row stride not a multiple
+    of 4 floats) when K itself is a multiple of 4 — the case vqa_linear_*_workspace_bytes() cannot see from the shapes
+    (include/vqacore.h).  The tensor-core ops copy such an operand into padded scratch instead of leaving the tensor
+    cores."""
+    if K % 4 != 0:
+        return 0                      # already counted by the workspace query
+    bad = [t for t in tensors if t.data_ptr() % 16 or t.stride(0) % 4]
+    return sum(t.shape[0] * ((K + 3) // 4 * 4) * 4 + 256 for t in tensors) if bad else 0
+
+
 # =========================================================================== grouped linear
 def linear_forward(xs, ws, bs, act, p, seed, layers, math=0, outs=None, bits=None):
     """Y_g = act(dropout(X_g) W_g^T + b_g). xs/ws/bs: lists (one entry per group), X_g [M,K] (row stride
@@ -76,7 +87,8 @@ def linear_forward(xs, ws, bs, act, p, seed, layers, math=0, outs=None, bits=Non
         pr.Y[i], pr.ldy[i] = outs[i].data_ptr(), outs[i].stride(0)
         pr.layer[i], pr.drop_index_base[i] = int(layers[i]), 0
         pr.drop_bits[i] = _p(bits[i]) if bits is not None else None
-    ws = _workspace(_lib.lib().vqa_linear_fwd_workspace_bytes(pr.math, g, M, K, N), xs[0].device)
+    nbytes = _lib.lib().vqa_linear_fwd_workspace_bytes(pr.math, g, M, K, N) + (_repack_bytes(xs, K) if pr.math else 0)
+    ws = _workspace(nbytes, xs[0].device)
     pr.workspace, pr.workspace_bytes = _p(ws), (ws.numel() if ws is not None else 0)
     _lib.check(_lib.lib().vqa_linear_fwd(C.byref(pr), _stream()), "vqa_linear_fwd")
     return outs
@@ -110,7 +122,8 @@ def linear_backward(xs, ws, ys, dys, act, p, seed, layers, need_dx, math=0, dws=
         pr.drop_bits[i] = _p(bits[i]) if bits is not None else None
     if pool is not None:
         pr.pool_alpha, pr.pool_dpooled, pr.pool_regions = pool[0].data_ptr(), pool[1].data_ptr(), int(pool[2])
-    ws = _workspace(_lib.lib().vqa_linear_bwd_workspace_bytes(pr.math, g, M, K, N), dev)
+    nbytes = _lib.lib().vqa_linear_bwd_workspace_bytes(pr.math, g, M, K, N) + (_repack_bytes(xs, K) if pr.math else 0)
+    ws = _workspace(nbytes, dev)
     pr.workspace, pr.workspace_bytes = _p(ws), (ws.numel() if ws is not None else 0)
     _lib.check(_lib.lib().vqa_linear_bwd(C.byref(pr), _stream()), "vqa_linear_bwd")
     return dws, dbs, dxs
@@ -241,8 +254,9 @@ class MutanFn(torch.autograd.Function):
 # =========================================================================== region softmax + pooling
 class RegionSoftmaxPoolFn(torch.autograd.Function):
     """alpha = softmax_regions(conv_att(dropout(fuse))); pooled = alpha^T x.  Returns (pooled, alpha).
-    alpha is a side output (its incoming gradient is only honoured for glimpse 0 through
-    `CorCompoundFn`, which is how the reference uses it; config/CoR2.py:216)."""
+    Both outputs are differentiable: an incoming gradient of alpha [B,N,G] (the reference uses alpha1[0] downstream,
+    config/CoR2.py:216) is added to <dpooled, x> before the softmax backward (vqa_region_softmax_pool_bwd,
+    `dalpha_ext`)."""
 
     @staticmethod
     def forward(ctx, x, fuse, wc, bc, p, seed, layer):
@@ -269,11 +283,10 @@ class RegionSoftmaxPoolFn(torch.autograd.Function):
         B, N, Dd = xc.shape
         Ff = fc.shape[2]
         dev = xc.device
+        if dpooled is None:
+            dpooled = torch.zeros((B, GLIMPSES, Dd), device=dev, dtype=torch.float32)
         dpooled = dpooled.contiguous()
-        ext = None
-        if dalpha_in is not None:
-            # only a per-sample scalar added to glimpse 0 is representable (CoR2's d s / d alpha term)
-            ext = dalpha_in[:, 0, 0].contiguous()
+        ext = dalpha_in.contiguous() if dalpha_in is not None else None
         dalpha = torch.empty_like(alpha)
         dz = torch.empty_like(alpha)
         dwc = torch.empty_like(wc2)
@@ -285,11 +298,105 @@ class RegionSoftmaxPoolFn(torch.autograd.Function):
         pr.drop.p, pr.drop.layer, pr.drop.seed = float(p), int(layer), int(seed)
         pr.accumulate_w, pr.accumulate_x = 0, 0
         pr.fuse, pr.Wc, pr.x, pr.alpha = fc.data_ptr(), wc2.data_ptr(), xc.data_ptr(), alpha.data_ptr()
-        pr.dpooled, pr.dalpha0_ext = dpooled.data_ptr(), _p(ext)
+        pr.dpooled, pr.dalpha0_ext, pr.dalpha_ext = dpooled.data_ptr(), None, _p(ext)
         pr.dalpha, pr.dz, pr.dWc, pr.dbc = dalpha.data_ptr(), dz.data_ptr(), dwc.data_ptr(), dbc.data_ptr()
         pr.dfuse, pr.dx = _p(dfuse), _p(dx)
         _lib.check(_lib.lib().vqa_region_softmax_pool_bwd(C.byref(pr), _stream()), "vqa_region_softmax_pool_bwd")
         return dx, dfuse, dwc.reshape(wshape), dbc, None, None, None
+
+
+# =========================================================================== CoR2 compound objects
+class CorCompoundFn(torch.autograd.Function):
+    """v2[b,j,:] = pooled[b,0,:]*g1[b,:] + (sum_i alpha[b,i,0]) * x[b,j,:]*g2[b,:]  — decare_cat + the alpha1[0]-weighted
+    sum of config/CoR2.py:191-199, :215-216 in collapsed form (vqa_cor_compound_fwd / _bwd).
+    Differentiable in pooled (glimpse 0), alpha (glimpse 0), g1, g2; `x` is the graph input v there and gets no
+    gradient (requesting one raises)."""
+
+    @staticmethod
+    def forward(ctx, x, pooled, alpha, g1, g2):
+        xc, pc, ac = _chk(x, "x", 3), _chk(pooled, "pooled", 3), _chk(alpha, "alpha", 3)
+        g1c, g2c = _chk(g1, "g1", 2), _chk(g2, "g2", 2)
+        B, N, Dd = xc.shape
+        v2 = torch.empty_like(xc)
+        pr = _lib.CompoundFwd()
+        pr.B, pr.N, pr.D = B, N, Dd
+        pr.x, pr.pooled, pr.alpha, pr.g1, pr.g2, pr.v2 = (xc.data_ptr(), pc.data_ptr(), ac.data_ptr(), g1c.data_ptr(),
+                                                          g2c.data_ptr(), v2.data_ptr())
+        _lib.check(_lib.lib().vqa_cor_compound_fwd(C.byref(pr), _stream()), "vqa_cor_compound_fwd")
+        ctx.save_for_backward(xc, pc, ac, g1c, g2c)
+        return v2
+
+    @staticmethod
+    def backward(ctx, dv2):
+        xc, pc, ac, g1c, g2c = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("CorCompoundFn: no gradient for x (it is the graph input v in CoR2; "
+                                      "config/CoR2.py:215 passes v, v)")
+        B, N, Dd = xc.shape
+        dv2 = dv2.contiguous()
+        dg1, dg2 = torch.empty_like(g1c), torch.empty_like(g2c)
+        dpooled = torch.zeros_like(pc)                 # the kernel ACCUMULATES into the glimpse-0 slice
+        ext = torch.empty((B,), device=xc.device, dtype=torch.float32)
+        pr = _lib.CompoundBwd()
+        pr.B, pr.N, pr.D = B, N, Dd
+        pr.x, pr.pooled, pr.alpha, pr.g1, pr.g2 = xc.data_ptr(), pc.data_ptr(), ac.data_ptr(), g1c.data_ptr(), g2c.data_ptr()
+        pr.dv2, pr.dg1, pr.dg2, pr.dpooled, pr.dalpha0_ext = (dv2.data_ptr(), dg1.data_ptr(), dg2.data_ptr(),
+                                                              dpooled.data_ptr(), ext.data_ptr())
+        _lib.check(_lib.lib().vqa_cor_compound_bwd(C.byref(pr), _stream()), "vqa_cor_compound_bwd")
+        dalpha = torch.zeros_like(ac)
+        dalpha[:, :, 0] = ext.unsqueeze(1)              # d s / d alpha[b,i,0] = 1 for every region i
+        return None, dpooled, dalpha, dg1, dg2
+
+
+# =========================================================================== ODA object-difference attention
+class OdaPairAttnFn(torch.autograd.Function):
+    """ODA's pairwise-difference attention (config/ODA.py:216-226): logits over the never-materialised
+    [B,N,N*H] tensor, region softmax, pooling.  Returns (pooled [B,G,D], alpha [B,N,G]); gradients for vl, ql, the
+    conv_att weight [G,N*H(,1)] and bias.  x (= v) is a graph input; alpha is a side output here."""
+
+    @staticmethod
+    def forward(ctx, x, vl, ql, w, bc, p, seed, layer):
+        xc, vlc, qlc = _chk(x, "inputs", 3), _chk(vl, "vl", 3), _chk(ql, "ql", 2)
+        B, N, Dd = xc.shape
+        Hd = vlc.shape[2]
+        w2 = _chk(w, "conv_att.weight").reshape(GLIMPSES, N * Hd)
+        dev = xc.device
+        alpha = torch.empty((B, N, GLIMPSES), device=dev, dtype=torch.float32)
+        pooled = torch.empty((B, GLIMPSES, Dd), device=dev, dtype=torch.float32)
+        wsum = torch.empty((GLIMPSES, Hd), device=dev, dtype=torch.float32)
+        pr = _lib.OdaFwd()
+        pr.B, pr.N, pr.H, pr.D, pr.train = B, N, Hd, Dd, int(p > 0.0)
+        pr.drop.p, pr.drop.layer, pr.drop.seed = float(p), int(layer), int(seed)
+        pr.vl, pr.ql, pr.W, pr.bc, pr.x = vlc.data_ptr(), qlc.data_ptr(), w2.data_ptr(), bc.data_ptr(), xc.data_ptr()
+        pr.wsum, pr.alpha, pr.pooled = wsum.data_ptr(), alpha.data_ptr(), pooled.data_ptr()
+        _lib.check(_lib.lib().vqa_oda_pair_attn_fwd(C.byref(pr), _stream()), "vqa_oda_pair_attn_fwd")
+        ctx.save_for_backward(xc, vlc, qlc, w2, alpha, wsum)
+        ctx.meta = (p, seed, layer, w.shape)
+        ctx.mark_non_differentiable(alpha)
+        return pooled, alpha
+
+    @staticmethod
+    def backward(ctx, dpooled, _dalpha):
+        xc, vlc, qlc, w2, alpha, wsum = ctx.saved_tensors
+        p, seed, layer, wshape = ctx.meta
+        B, N, Dd = xc.shape
+        Hd = vlc.shape[2]
+        dev = xc.device
+        dpooled = dpooled.contiguous()
+        dalpha, dz = torch.empty_like(alpha), torch.empty_like(alpha)
+        dwsum = torch.empty_like(wsum)
+        dW, dbc = torch.empty_like(w2), torch.empty((GLIMPSES,), device=dev, dtype=torch.float32)
+        dvl, dql = torch.empty_like(vlc), torch.empty_like(qlc)
+        pr = _lib.OdaBwd()
+        pr.B, pr.N, pr.H, pr.D, pr.train = B, N, Hd, Dd, int(p > 0.0)
+        pr.drop.p, pr.drop.layer, pr.drop.seed = float(p), int(layer), int(seed)
+        pr.accumulate_w = 0
+        pr.vl, pr.ql, pr.W, pr.x, pr.alpha, pr.wsum = (vlc.data_ptr(), qlc.data_ptr(), w2.data_ptr(), xc.data_ptr(),
+                                                       alpha.data_ptr(), wsum.data_ptr())
+        pr.dpooled, pr.dalpha, pr.dz, pr.dwsum = dpooled.data_ptr(), dalpha.data_ptr(), dz.data_ptr(), dwsum.data_ptr()
+        pr.dW, pr.dbc, pr.dvl, pr.dql = dW.data_ptr(), dbc.data_ptr(), dvl.data_ptr(), dql.data_ptr()
+        _lib.check(_lib.lib().vqa_oda_pair_attn_bwd(C.byref(pr), _stream()), "vqa_oda_pair_attn_bwd")
+        return None, dvl, dql, dW.reshape(wshape), dbc, None, None, None
 
 
 # =========================================================================== loss

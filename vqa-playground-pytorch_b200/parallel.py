@@ -71,11 +71,19 @@ class GradSink:
         self.accumulate = False
         self.params = list(params)
         self.offsets = [offsets[i] for i in range(len(params))]      # (first, last) element of each parameter's slice
-        for p, s in zip(params, self.slices):
-            p.grad = s
+        self.bind()
+
+    def bind(self):
+        """p.grad of every parameter is its slice of the flat buffer.  Re-done after every backward: the reference's
+        step calls optimizer.zero_grad() (train.py:77), which in current torch sets p.grad = None — the kernels keep
+        writing into the flat buffer regardless, but torch.optim.Adam / clip_grad_norm_ skip parameters without
+        .grad, so a stale binding would silently stop training."""
+        for p, s in zip(self.params, self.slices):
+            if p.grad is not s:
+                p.grad = s
 
     def after_backward(self):
-        pass
+        self.bind()
 
 
 class DataParallelEngine(GradSink):
@@ -136,6 +144,7 @@ class DataParallelEngine(GradSink):
 
     def after_backward(self):
         # called by ops.ModelCoreFn.backward right after the backward plan has been enqueued
+        self.bind()
         if not self.defer:
             self.reduce_all()
 

@@ -1,0 +1,20 @@
+"""Data-parallel correctness on real GPUs (needs >= 2 devices: `gpurun --gpus 2 -- python -m pytest tests -m gpu`).
+Replaces the reference's nn.DataParallel wrap (train.py:517); see tests/dp_worker.py for what is checked."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_rank_graph_step_matches_one_gpu_global_batch(cuda):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tests", "dp_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "DP_OK" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])

@@ -125,9 +125,12 @@ REDUCED = ["tf32", "bf16"]
 @pytest.mark.parametrize("model,C", [("CoR2", 2000), ("ODA", 3000)])
 def test_reduced_precision_modes(cuda, model, C, precision):
     """BASELINE.json north_star: reduced-precision modes keep logits within 2e-2 of the fp32 reference, gradients
-    likewise (SURVEY.md §8d metric), train mode with the shared Philox masks."""
-    sd, (v, q, a), ref = parity.oracle_case(model, 16, C, train_seed=4, weight_seed=5, input_seed=6)
+    likewise (SURVEY.md §8d metric), train mode with the shared Philox masks.  Gradients are taken on the same ReLU
+    activation pattern, which may differ only where |z| <= 2e-2 max|z| (the mode's own tolerance): at 16 rows a single
+    flipped unit moves a whole weight-gradient row."""
+    sd, (v, q, a), _ = parity.oracle_case(model, 16, C, train_seed=4, weight_seed=5, input_seed=6, run=False)
     out = parity.run_cuda_model(model, sd, v, q, a, train_seed=4, precision=precision)
+    ref = parity.oracle_with_same_relu_pattern(model, sd, v, q, a, out, train_seed=4, tie_tol=2e-2)
     assert parity.rel_err(out["logits"], ref["logits"]) <= 2e-2
     fa, fb = parity.flatten_alpha(out["alpha_dict"]), parity.flatten_alpha(ref["alpha_dict"])
     for k in fb:

@@ -117,8 +117,8 @@ def test_optimizer_state_dict_round_trip_and_torch_layout(cuda):
     o2.load_state_dict(sd_opt)
     assert o2.step_count == 2 and o2.param_groups[0]["lr"] == 1e-3
     run(m2, o2, batches[2], 3)
-    for p, r in zip(m2.core_parameters(), m1.core_parameters()):
-        assert torch.equal(p, r)
+    for p, r in zip(m2.core_parameters(), m1.core_parameters()):      # same state, same gradients up to atomic ordering
+        assert (p.detach() - r.detach()).abs().max().item() <= 1e-3 * 1e-3          # << one update (lr = 1e-3)
     # torch.optim.Adam accepts the same dict, and its own state_dict loads here
     twins = [p.detach().clone().requires_grad_() for p in m2.core_parameters()]
     stock = torch.optim.Adam(twins, lr=1e-3)
@@ -165,8 +165,10 @@ def test_graph_captured_optimizer_step_matches_the_reference_order(cuda):
         loss.backward()
         torch.nn.utils.clip_grad_norm_(m2.core_parameters(), 0.25)
         ref.step()
+    # The two sides compute their gradients separately (atomic ordering differs at the 1e-7 level) and Adam turns
+    # noise-level gradients into O(lr) updates, so the bound is in units of lr: 0.2 % of the four updates.  Stepping the
+    # scheduler AFTER the optimizer instead would change every update by 1 - gamma = 1.4 %, seven times the bound.
     for p, r in zip(m1.core_parameters(), m2.core_parameters()):
-        scale = max(r.abs().max().item(), 1e-12)
-        assert (p.detach() - r.detach()).abs().max().item() <= 5e-6 * scale
+        assert (p.detach() - r.detach()).abs().max().item() <= 0.002 * 1e-3 * 4
     fresh = FusedClipAdam(s1, lr=1e-3, clip_grad=0.25, device_clock=True, lr_gamma=gamma)     # epoch reset
     assert fresh.steps_done() == 0 and fresh.lr_dev.item() == 1e-3 and not fresh.exp_avg.any()

@@ -52,9 +52,16 @@ enum {
 
 enum { VQA_ACT_NONE = 0, VQA_ACT_RELU = 1, VQA_ACT_SIGMOID = 2 };
 
-/* GEMM arithmetic. FP32_SIMT: fp32 FMA on CUDA cores (exact-fp32 parity path).
- * TF32X3 / TF32 / BF16: tcgen05 tensor cores, fp32 accumulate in TMEM. */
-enum { VQA_MATH_FP32_SIMT = 0, VQA_MATH_TF32X3 = 1, VQA_MATH_TF32 = 2, VQA_MATH_BF16 = 3 };
+/* GEMM arithmetic.  Every mode but FP32_SIMT runs on the tcgen05 tensor cores with fp32 accumulation in
+ * TMEM and NEVER falls back to the CUDA-core GEMM: what a mode cannot run is VQA_EINVAL.
+ *   FP32_SIMT  fp32 FMA on CUDA cores (exact fp32 arithmetic, bitwise reproducible)
+ *   TF32X3     fp32 operands, error-compensated 3xTF32 (x = hi + lo, three kind::tf32 MMAs): fp32-parity, <= 1e-4
+ *   TF32       fp32 operands, one TF32 pass: reduced precision, <= 2e-2
+ *   BF16X3     fp32-parity on bf16 tensor cores: the large-M GEMMs (M >= 1024, the region-side contractions) read
+ *              bf16 operand PLANES x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) written by their producers and issue
+ *              three kind::f16 MMAs per product (hi.hi + hi.lo + lo.hi); small-M GEMMs run TF32X3.  <= 1e-4
+ *   BF16       reduced precision: large-M GEMMs on ONE bf16 plane, small-M GEMMs one TF32 pass.  <= 2e-2 */
+enum { VQA_MATH_FP32_SIMT = 0, VQA_MATH_TF32X3 = 1, VQA_MATH_TF32 = 2, VQA_MATH_BF16 = 3, VQA_MATH_BF16X3 = 4 };
 
 #define VQA_MAX_GROUPS 8
 #define VQA_GLIMPSES 4

@@ -14,9 +14,9 @@ ABI_VERSION = 2
 MAXG = 8
 GLIMPSES = 4
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
-MATH_FP32_SIMT, MATH_TF32X3, MATH_TF32, MATH_BF16 = 0, 1, 2, 3
+MATH_FP32_SIMT, MATH_TF32X3, MATH_TF32, MATH_BF16, MATH_BF16X3 = 0, 1, 2, 3, 4
 MATH_BY_NAME = {"fp32": MATH_FP32_SIMT, "fp32_simt": MATH_FP32_SIMT, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32,
-                "bf16": MATH_BF16}
+                "bf16": MATH_BF16, "bf16x3": MATH_BF16X3}
 VQA_OK, VQA_EINVAL, VQA_ECUDA, VQA_ENODEVICE, VQA_EWORKSPACE = 0, -1, -2, -3, -4
 
 fp = C.c_void_p          # device pointers travel as integers

@@ -8,7 +8,7 @@
 #include <mutex>
 
 
-#include "tc_gemm.cuh"
+#include "tc_epilogues.cuh"
 
 namespace vqa {
 namespace tc {
@@ -77,85 +77,6 @@ static int operand_tmap(CUtensorMap* out, const float* ptr, bool mn_major, int64
   return make_tmap(out, ptr, k_extent, mn_extent, ld, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
-// ------------------------------------------------------------------------------------------ epilogues
-// Each receives 32 consecutive accumulator columns [n0, n0+32) of row m.
-
-// 4 consecutive row elements with whatever vector width the destination alignment allows; nv = valid count
-__device__ __forceinline__ void store4(float* dst, const float (&o)[4], int nv) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
-  if (nv == 4 && (a & 15) == 0) {
-    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-  } else if (nv == 4 && (a & 7) == 0) {
-    *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
-    *reinterpret_cast<float2*>(dst + 2) = make_float2(o[2], o[3]);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (e < nv) dst[e] = o[e];
-  }
-}
-// o[0..nv) added to dst[0..nv) with reductions that return nothing: one 16-byte red when the quad is whole and aligned
-__device__ __forceinline__ void red_add4(float* dst, const float (&o)[4], int nv) {
-  if (nv == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3])
-                 : "memory");
-  } else if (nv == 4 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(dst), "f"(o[0]), "f"(o[1]) : "memory");
-    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(dst + 2), "f"(o[2]), "f"(o[3]) : "memory");
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (e < nv) atomicAdd(dst + e, o[e]);
-  }
-}
-__device__ __forceinline__ void load4(const float* src, float (&o)[4], int nv) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-  if (nv == 4 && (a & 15) == 0) {
-    const float4 t = *reinterpret_cast<const float4*>(src);
-    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-  } else if (nv == 4 && (a & 7) == 0) {
-    const float2 t0 = *reinterpret_cast<const float2*>(src), t1 = *reinterpret_cast<const float2*>(src + 2);
-    o[0] = t0.x; o[1] = t0.y; o[2] = t1.x; o[3] = t1.y;
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[e] = e < nv ? src[e] : 0.0f;
-  }
-}
-
-// y = act(acc + bias), row-major store.  With k-splits (atomic != 0) the partial sums are accumulated into a
-// zeroed Y with red.global.add, split 0 contributes the bias, and the activation is applied afterwards by
-// act_inplace_kernel.
-struct EpiBiasAct {
-  static constexpr bool kOcc2 = false;
-  static constexpr bool kStaged = true;
-  static constexpr int kBatch = 8;
-  float* Y[MAXG];
-  const float* bias[MAXG];
-  int64_t ld[MAXG];
-  int act;
-  int atomic;
-  struct Col { float* y; int64_t ld; float b[4]; int nv; };
-  struct Pre {};
-  __device__ __forceinline__ void column(Col& c, int g, int split, int n, int N) const {
-    c.y = Y[g] + n; c.ld = ld[g]; c.nv = N - n < 4 ? N - n : 4;
-    const float* bp = bias[g];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) c.b[e] = (bp && e < c.nv && (!atomic || split == 0)) ? __ldg(bp + n + e) : 0.0f;
-  }
-  __device__ __forceinline__ void preload(Pre&, const Col&, int) const {}
-  __device__ __forceinline__ void row4(const Col& c, int m, const float4 v, const Pre&) const {
-    float* y = c.y + (int64_t)m * c.ld;
-    float o[4] = {v.x + c.b[0], v.y + c.b[1], v.z + c.b[2], v.w + c.b[3]};
-    if (atomic) {
-      red_add4(y, o, c.nv);
-      return;
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[e] = act_apply(act, o[e]);
-    store4(y, o, c.nv);
-  }
-};
-
 // y = act(y) in place over a [M, N] window of row stride ld; grid.z = group
 struct ActArgs { float* Y[MAXG]; int64_t ld[MAXG]; };
 __global__ void act_inplace_kernel(ActArgs a, int64_t M, int64_t N, int act) {
@@ -167,110 +88,6 @@ __global__ void act_inplace_kernel(ActArgs a, int64_t M, int64_t N, int act) {
     y[m * ld + n] = act_apply(act, y[m * ld + n]);
   }
 }
-
-// wgrad: D'(m' = input feature k, n' = output feature n) accumulated into dW[n, k] (row stride ldw) with
-// red.global.add (split-K partials and the "+=" of a flat gradient buffer are the same operation).
-struct EpiWgradT {
-  static constexpr bool kOcc2 = false;
-  static constexpr bool kStaged = false;
-  static constexpr int kBatch = 8;
-  float* dW[MAXG];
-  int64_t ldw;
-  struct Row { float* w; int nv; };
-  __device__ __forceinline__ void rowquad(Row& r, int g, int m, int M) const {
-    r.w = dW[g] ? dW[g] + m : nullptr;             // consecutive tile rows m are consecutive addresses of dW[n, :]
-    r.nv = M - m < 4 ? M - m : 4;
-  }
-  __device__ __forceinline__ void col4(const Row& r, int n, const float4 v) const {
-    if (!r.w) return;
-    const float o[4] = {v.x, v.y, v.z, v.w};
-    red_add4(r.w + (int64_t)n * ldw, o, r.nv);
-  }
-};
-
-// dgrad: dX[m, n] (=|+=) acc * mask(m*drop_ld + n) / (1-p)
-// POOL: additionally dX[m, n] += sum_g alpha[m, g] * dpooled[m / regions, g, n] — the gradient of an attention pooling
-// over the same X (MyATT's bmatmul over v2, config/CoR2.py), which would otherwise cost a full write of dX by the
-// pooling backward and a read-modify-write here.
-template <bool POOL>
-struct EpiDgradT {
-  static constexpr bool kOcc2 = false;
-  static constexpr bool kStaged = true;
-  static constexpr int kBatch = POOL ? 4 : 8;
-  float* dX[MAXG];
-  int64_t ld[MAXG];
-  int accumulate;
-  int atomic;       // k-splits: every partial is masked and added with red.global.add (dX zeroed or "+=")
-  int drop_on;
-  Drop drop;
-  GroupDrop gd;
-  int64_t drop_ld;
-  int wide_bits;               // drop_ld % 4 != 0: a quad's mask bits may run into the next byte
-  const uint8_t* bits[MAXG];
-  const float* pool_alpha;      // [M, 4]
-  const float* pool_dp;         // [M / pool_regions, 4, pool_ld]
-  int64_t pool_regions, pool_ld;
-  struct Col { float* x; int64_t ld; int n, nv, first; const uint8_t* bits; const float* dp; uint32_t layer; uint64_t base; };
-  struct PreBase { float old[4]; uint32_t byte, byte_hi; };
-  struct PrePool : PreBase { float4 al; float4 dp[4]; };
-  using Pre = typename std::conditional<POOL, PrePool, PreBase>::type;
-  __device__ __forceinline__ void column(Col& c, int g, int split, int n, int N) const {
-    c.first = split == 0;
-    c.x = dX[g] ? dX[g] + n : nullptr; c.ld = ld[g]; c.n = n; c.nv = N - n < 4 ? N - n : 4;
-    c.bits = drop_on ? bits[g] : nullptr; c.layer = gd.layer[g]; c.base = gd.base[g];
-    c.dp = POOL ? pool_dp + n : nullptr;
-  }
-  __device__ __forceinline__ void preload(Pre& r, const Col& c, int m) const {
-    if (!c.x) return;
-    if (c.bits) {            // the quad's 4 mask bits start at bit (e & 7) and may run into the next byte
-      const uint64_t e = (uint64_t)m * (uint64_t)drop_ld + (uint64_t)c.n;
-      r.byte = __ldg(c.bits + (e >> 3));
-      if (wide_bits) r.byte_hi = __ldg(c.bits + (e >> 3) + 1);      // combined at use: no load is waited for here
-    }
-    if (accumulate && !atomic) load4(c.x + (int64_t)m * c.ld, r.old, c.nv);
-    if constexpr (POOL) {
-      r.al = __ldg(reinterpret_cast<const float4*>(pool_alpha) + m);
-      const float* dp = c.dp + (int64_t)((uint32_t)m / (uint32_t)pool_regions) * 4 * pool_ld;   // N % 4 == 0 (host check)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r.dp[j] = __ldg(reinterpret_cast<const float4*>(dp + j * pool_ld));
-    }
-  }
-  __device__ __forceinline__ void row4(const Col& c, int m, const float4 v, const Pre& pre) const {
-    if (!c.x) return;
-    float* x = c.x + (int64_t)m * c.ld;
-    float o[4] = {v.x, v.y, v.z, v.w};
-    if (c.bits) {
-      const uint32_t nb = (wide_bits ? (pre.byte | (pre.byte_hi << 8)) : pre.byte) >>
-                          (((uint32_t)m * (uint32_t)drop_ld + (uint32_t)c.n) & 7u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = ((nb >> j) & 1u) ? o[j] * drop.scale : 0.0f;
-    } else if (drop_on) {
-      const uint32_t bt = philox_bytes4(drop.key(), c.layer, c.base + ((uint64_t)m * (uint64_t)drop_ld + (uint64_t)c.n));
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = ((bt >> (8 * e)) & 0xFFu) >= drop.thr ? o[e] * drop.scale : 0.0f;
-    }
-    if constexpr (POOL) {
-      if (c.first) {
-        const float al[4] = {pre.al.x, pre.al.y, pre.al.z, pre.al.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          o[0] = fmaf(al[j], pre.dp[j].x, o[0]); o[1] = fmaf(al[j], pre.dp[j].y, o[1]);
-          o[2] = fmaf(al[j], pre.dp[j].z, o[2]); o[3] = fmaf(al[j], pre.dp[j].w, o[3]);
-        }
-      }
-    }
-    if (atomic) {
-      red_add4(x, o, c.nv);
-      return;
-    }
-    if (accumulate) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] += pre.old[e];
-    }
-    store4(x, o, c.nv);
-  }
-};
-using EpiDgrad = EpiDgradT<false>;
 
 // ------------------------------------------------------------------------------------------ launch
 static int occ2_mode() {                 // VQA_TC_OCC2=0 disables the two-CTAs-per-SM variant (experiments)
@@ -509,48 +326,6 @@ __global__ void dropout_bits_batch_kernel(uint64_t seed, const uint64_t* seed_pt
 }
 
 // ------------------------------------------------------------------------------------------ Mutan pieces
-// forward epilogue for rank r = group: h1 = acc + b1_r;  H1_r[m,n] = h1;  Y[m,n] += h1 * H2_r[m / rows_per, n].
-// Non-atomic mode runs rank by rank in stream order (r == 0 stores, r > 0 read-modify-writes Y);
-// atomic mode (k-splits, small M) accumulates every partial into zeroed Y / H1 with red.global.add.
-struct EpiMutan {
-  static constexpr bool kOcc2 = true;
-  static constexpr bool kStaged = true;
-  static constexpr int kBatch = 8;
-  const float* bias[MAXG]; const float* H2[MAXG]; float* H1[MAXG]; float* Y;
-  int64_t ldh, ldy, rows_per; int accumulate; int atomic;
-  struct Col { const float* h2; float* h1; float* y; float b[4]; int nv; };
-  struct Pre { float h2[4]; float old[4]; };
-  __device__ __forceinline__ void column(Col& c, int g, int split, int n, int N) const {
-    c.nv = N - n < 4 ? N - n : 4;
-    c.h2 = H2[g] + n; c.h1 = H1[g] ? H1[g] + n : nullptr; c.y = Y + n;
-    const float* bp = bias[g];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) c.b[e] = (bp && e < c.nv && split == 0) ? __ldg(bp + n + e) : 0.0f;
-  }
-  __device__ __forceinline__ void preload(Pre& r, const Col& c, int m) const {
-    load4(c.h2 + (int64_t)((uint32_t)m / (uint32_t)rows_per) * ldh, r.h2, c.nv);
-    if (accumulate && !atomic) load4(c.y + (int64_t)m * ldy, r.old, c.nv);
-  }
-  __device__ __forceinline__ void row4(const Col& c, int m, const float4 v, const Pre& pre) const {
-    float h[4] = {v.x + c.b[0], v.y + c.b[1], v.z + c.b[2], v.w + c.b[3]}, o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[e] = e < c.nv ? h[e] * pre.h2[e] : 0.0f;
-    float* y = c.y + (int64_t)m * ldy;
-    float* h1 = c.h1 ? c.h1 + (int64_t)m * ldh : nullptr;
-    if (atomic) {
-      if (h1) red_add4(h1, h, c.nv);
-      red_add4(y, o, c.nv);
-      return;
-    }
-    if (h1) store4(h1, h, c.nv);
-    if (accumulate) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] += pre.old[e];
-    }
-    store4(y, o, c.nv);
-  }
-};
-
 struct DbTable { float* p[MAXG]; };
 
 // Both Mutan gradient operands in one pass over dY (one CTA per (h2 row, rank)):
@@ -562,7 +337,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 mutan_dh_kernel(int64_t M, int64_t F, int64_t Fp, int64_t rows_per, int R, const float* __restrict__ dY, int64_t lddy,
                 const float* __restrict__ H1, const float* __restrict__ H2, float* __restrict__ dH1cat,
-                float* __restrict__ dH2cat, DbTable db1, DbTable db2) {
+                float* __restrict__ dH2cat, DbTable db1, DbTable db2, __nv_bfloat16* __restrict__ dH1p,
+                int64_t dh1_plane, int np) {
   const int64_t mh = blockIdx.x;
   const int r = blockIdx.y;
   const int64_t Mh = M / rows_per, RF = (int64_t)R * Fp;
@@ -602,9 +378,23 @@ mutan_dh_kernel(int64_t M, int64_t F, int64_t Fp, int64_t rows_per, int R, const
           accb[e] += v[e];
           acc2[e] = fmaf(dy[u][e], h1[u][e], acc2[e]);
         }
-        float* o = dH1cat + m * RF + (int64_t)r * Fp + f;
-        if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(v[0], v[VEC - 1]);
-        else o[0] = v[0];
+        const int64_t oi = m * RF + (int64_t)r * Fp + f;
+        if (dH1p) {                 // bf16 operand planes for the bf16-plane GEMMs instead of the fp32 tensor
+          __nv_bfloat16 hi[VEC], lo[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) split_bf16(v[e], hi[e], lo[e]);
+          if (VEC == 2) {
+            *reinterpret_cast<__nv_bfloat162*>(dH1p + oi) = __halves2bfloat162(hi[0], hi[VEC - 1]);
+            if (np == 2) *reinterpret_cast<__nv_bfloat162*>(dH1p + dh1_plane + oi) = __halves2bfloat162(lo[0], lo[VEC - 1]);
+          } else {
+            dH1p[oi] = hi[0];
+            if (np == 2) dH1p[dh1_plane + oi] = lo[0];
+          }
+        } else {
+          float* o = dH1cat + oi;
+          if (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(v[0], v[VEC - 1]);
+          else o[0] = v[0];
+        }
       }
     }
     float* o2 = dH2cat + mh * RF + (int64_t)r * Fp + f;
@@ -632,8 +422,14 @@ static int tc_fail(const char* who, const char* why) {
   return VQA_EINVAL;
 }
 
-int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st) {
+int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st, const LinExt* ext) {
   using namespace tc;
+  if (is_bf16_math(p->math)) {
+    if (p->M >= TC16_MIN_M) return tc16_linear_fwd(p, st, ext);
+    vqa_linear_fwd_params q = *p;
+    q.math = small_math_of(p->math);
+    return tc_linear_fwd(&q, st, nullptr);
+  }
   if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return tc_fail("vqa_linear_fwd", "this math mode is not built for this op");
   if (p->M > INT32_MAX || p->K > INT32_MAX || p->N > INT32_MAX) return tc_fail("vqa_linear_fwd", "a dimension exceeds 2^31");
   bool pack = false, packx = false;
@@ -722,8 +518,14 @@ static int dgrad_launch(const vqa_linear_bwd_params* p, float* dz, float* wpk, i
   return launch(q, p->groups, x3, st, "tc_linear_bwd.dgrad");
 }
 
-int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st) {
+int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st, const LinExt* ext) {
   using namespace tc;
+  if (is_bf16_math(p->math)) {
+    if (p->M >= TC16_MIN_M) return tc16_linear_bwd(p, st, ext);
+    vqa_linear_bwd_params q = *p;
+    q.math = small_math_of(p->math);
+    return tc_linear_bwd(&q, st, nullptr);
+  }
   if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return tc_fail("vqa_linear_bwd", "this math mode is not built for this op");
   if (p->M > INT32_MAX || p->K > INT32_MAX || p->N > INT32_MAX) return tc_fail("vqa_linear_bwd", "a dimension exceeds 2^31");
   const bool x3 = p->math == VQA_MATH_TF32X3;
@@ -806,38 +608,44 @@ struct MutanWs {
   size_t bytes;
 };
 // packx1 / packx2: X1 / X2 are not TMA-addressable as given and get a padded copy
+// big16: the X1-side GEMMs run on the bf16-plane kernel, which carves its own scratch behind this one
 static MutanWs mutan_ws(void* base, int R, int64_t M, int64_t Mh, int64_t K1, int64_t K2, int64_t F, bool bwd,
-                        bool packx1 = false, bool packx2 = false) {
+                        bool packx1 = false, bool packx2 = false, bool big16 = false) {
   using namespace tc;
   const int64_t Fp = roundup(F, 32), K1p = roundup(K1, 4), K2p = roundup(K2, 4);
   char* b = reinterpret_cast<char*>(base);
   size_t off = 0;
   MutanWs w;
   auto take = [&](int64_t n) { float* p = b ? reinterpret_cast<float*>(b + off) : nullptr; off += align256((size_t)n * 4); return p; };
-  w.w1pk = take(R * Fp * K1p);
+  w.w1pk = big16 ? nullptr : take(R * Fp * K1p);
   w.w2pk = take(R * Fp * K2p);
-  w.dh1 = bwd ? take(M * R * Fp) : nullptr;
+  w.dh1 = (bwd && !big16) ? take(M * R * Fp) : nullptr;
   w.dh2 = bwd ? take(Mh * R * Fp) : nullptr;
-  w.x1pk = packx1 ? take(M * K1p) : nullptr;
+  w.x1pk = (packx1 && !big16) ? take(M * K1p) : nullptr;
   w.x2pk = packx2 ? take(Mh * K2p) : nullptr;
   w.bytes = off;
   return w;
 }
 size_t tc_mutan_ws(int math, int R, int64_t M, int64_t rows_per, int64_t K1, int64_t K2, int64_t F, int bwd) {
   if (math == VQA_MATH_FP32_SIMT) return 0;
+  if (is_bf16_math(math) && M >= TC16_MIN_M)
+    return mutan_ws(nullptr, R, M, M / rows_per, K1, K2, F, bwd != 0, false, K2 % 4 != 0, true).bytes +
+           tc16_mutan_ws(math == VQA_MATH_BF16X3 ? 2 : 1, R, M, K1, F, bwd);
   return mutan_ws(nullptr, R, M, M / rows_per, K1, K2, F, bwd != 0, K1 % 4 != 0, K2 % 4 != 0).bytes;   // upper bound
 }
 
-int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
+int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st, const MutanExt* ext) {
   using namespace tc;
-  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return tc_fail("vqa_mutan_fwd", "this math mode is not built for this op");
+  const bool big16 = is_bf16_math(p->math) && p->M >= TC16_MIN_M;
+  const int math = small_math_of(p->math);
+  if (math != VQA_MATH_TF32X3 && math != VQA_MATH_TF32) return tc_fail("vqa_mutan_fwd", "this math mode is not built for this op");
   if (p->M > INT32_MAX) return tc_fail("vqa_mutan_fwd", "a dimension exceeds 2^31");
   const int64_t Mh = p->M / p->rows_per_h2;
-  const bool packx1 = !tma_ok(p->X1, p->ldx1), packx2 = !tma_ok(p->X2, p->ldx2);
-  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, false, packx1, packx2);
+  const bool packx1 = !big16 && !tma_ok(p->X1, p->ldx1), packx2 = !tma_ok(p->X2, p->ldx2);
+  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, false, packx1, packx2, big16);
   if (!p->workspace || p->workspace_bytes < w.bytes || reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0)
     return tc_fail("vqa_mutan_fwd", "the workspace is missing, not 256-byte aligned or smaller than vqa_mutan_workspace_bytes()");
-  const bool x3 = p->math == VQA_MATH_TF32X3;
+  const bool x3 = math == VQA_MATH_TF32X3;
   const int64_t Fp = roundup(p->F, 32), K1p = roundup(p->K1, 4), K2p = roundup(p->K2, 4);
   const float* X1 = p->X1; const float* X2 = p->X2;
   int64_t ldx1 = p->ldx1, ldx2 = p->ldx2;
@@ -845,8 +653,10 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
   if (packx2) { VQA_TRY(pack_weights(&p->X2, 1, Mh, Mh, p->K2, w.x2pk, st, &p->ldx2)); X2 = w.x2pk; ldx2 = K2p; }
   if (p->W1p && p->W2p) {
     w.w1pk = const_cast<float*>(p->W1p); w.w2pk = const_cast<float*>(p->W2p);
+  } else if (p->W2p && big16) {
+    w.w2pk = const_cast<float*>(p->W2p);
   } else {
-    VQA_TRY(pack_weights(p->W1, p->R, p->F, Fp, p->K1, w.w1pk, st));
+    if (!big16) VQA_TRY(pack_weights(p->W1, p->R, p->F, Fp, p->K1, w.w1pk, st));
     VQA_TRY(pack_weights(p->W2, p->R, p->F, Fp, p->K2, w.w2pk, st));
   }
   const int bn = pick_bn(p->F);
@@ -863,6 +673,12 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
     q.epi.act = VQA_ACT_NONE; q.epi.atomic = q.k_splits > 1;
     if (q.epi.atomic) cudaMemsetAsync(p->H2, 0, (size_t)p->R * Mh * p->F * sizeof(float), st);
     VQA_TRY(launch(q, p->R, x3, st, "tc_mutan_fwd.h2"));
+  }
+  if (big16) {      // the X1-side GEMMs on the bf16-plane kernel, its scratch behind this function's
+    vqa_mutan_fwd_params q = *p;
+    q.workspace = reinterpret_cast<char*>(p->workspace) + w.bytes;
+    q.workspace_bytes = p->workspace_bytes - w.bytes;
+    return tc16_mutan_fwd_h1(&q, st, ext);
   }
   const int splits = pick_splits(cdiv(p->M, BM) * cdiv(p->F, bn) * p->R, p->K1);
   auto fill = [&](Params<EpiMutan>& q, int r0) -> int {
@@ -896,16 +712,26 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st) {
   return VQA_OK;
 }
 
-int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
+int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st, const MutanExt* ext) {
   using namespace tc;
-  if (p->math != VQA_MATH_TF32X3 && p->math != VQA_MATH_TF32) return tc_fail("vqa_mutan_bwd", "this math mode is not built for this op");
+  const bool big16 = is_bf16_math(p->math) && p->M >= TC16_MIN_M;
+  const int math = small_math_of(p->math);
+  if (math != VQA_MATH_TF32X3 && math != VQA_MATH_TF32) return tc_fail("vqa_mutan_bwd", "this math mode is not built for this op");
   if (p->M > INT32_MAX) return tc_fail("vqa_mutan_bwd", "a dimension exceeds 2^31");
   const int64_t Mh = p->M / p->rows_per_h2;
-  const bool packx1 = !tma_ok(p->X1, p->ldx1), packx2 = !tma_ok(p->X2, p->ldx2);
-  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, true, packx1, packx2);
+  const bool packx1 = !big16 && !tma_ok(p->X1, p->ldx1), packx2 = !tma_ok(p->X2, p->ldx2);
+  MutanWs w = mutan_ws(p->workspace, p->R, p->M, Mh, p->K1, p->K2, p->F, true, packx1, packx2, big16);
   if (!p->workspace || p->workspace_bytes < w.bytes || reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0)
     return tc_fail("vqa_mutan_bwd", "the workspace is missing, not 256-byte aligned or smaller than vqa_mutan_workspace_bytes()");
-  const bool x3 = p->math == VQA_MATH_TF32X3;
+  const bool x3 = math == VQA_MATH_TF32X3;
+  Mutan16Ops ops16 = {};
+  ops16.np = 1;
+  if (big16) {      // operand planes of the X1-side GEMMs (scratch behind this function's)
+    vqa_mutan_bwd_params q = *p;
+    q.workspace = reinterpret_cast<char*>(p->workspace) + w.bytes;
+    q.workspace_bytes = p->workspace_bytes - w.bytes;
+    VQA_TRY(tc16_mutan_bwd_prepare(&q, st, ext, &ops16));
+  }
   const int R = p->R;
   const int64_t Fp = roundup(p->F, 32), K1p = roundup(p->K1, 4), K2p = roundup(p->K2, 4), RF = R * Fp;
   const float* X1 = p->X1; const float* X2 = p->X2;
@@ -914,8 +740,10 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
   if (packx2) { VQA_TRY(pack_weights(&p->X2, 1, Mh, Mh, p->K2, w.x2pk, st, &p->ldx2)); X2 = w.x2pk; ldx2 = K2p; }
   if (p->W1p && p->W2p) {
     w.w1pk = const_cast<float*>(p->W1p); w.w2pk = const_cast<float*>(p->W2p);
+  } else if (p->W2p && big16) {
+    w.w2pk = const_cast<float*>(p->W2p);
   } else {
-    VQA_TRY(pack_weights(p->W1, R, p->F, Fp, p->K1, w.w1pk, st));
+    if (!big16) VQA_TRY(pack_weights(p->W1, R, p->F, Fp, p->K1, w.w1pk, st));
     VQA_TRY(pack_weights(p->W2, R, p->F, Fp, p->K2, w.w2pk, st));
   }
   if (!p->accumulate_w)
@@ -934,10 +762,10 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
     KProf kp_(st, "mutan_dh", "hbm", 4.0 * (double)p->M * p->F * (1.0 + 2.0 * R));
     if (vec2)
       mutan_dh_kernel<2><<<grid, 256, 0, st>>>(p->M, p->F, Fp, p->rows_per_h2, R, p->dY, p->lddy, p->H1, p->H2, w.dh1,
-                                              w.dh2, db1, db2);
+                                              w.dh2, db1, db2, big16 ? ops16.dh1 : nullptr, p->M * RF, ops16.np);
     else
       mutan_dh_kernel<1><<<grid, 256, 0, st>>>(p->M, p->F, Fp, p->rows_per_h2, R, p->dY, p->lddy, p->H1, p->H2, w.dh1,
-                                              w.dh2, db1, db2);
+                                              w.dh2, db1, db2, big16 ? ops16.dh1 : nullptr, p->M * RF, ops16.np);
     VQA_TRY(check_launch("tc_mutan_bwd.dh"));
   }
   auto wgrad = [&](const float* X, int64_t ldx, int64_t Krows, int64_t Kin, const float* dHcat, float* const* dW,
@@ -972,8 +800,12 @@ int tc_mutan_bwd(const vqa_mutan_bwd_params* p, cudaStream_t st) {
     if (q.epi.atomic && !accumulate) zero_window(dX, lddx, rows, Kin, st);
     return launch(q, 1, x3, st, what);
   };
-  VQA_TRY(wgrad(X1, ldx1, p->M, p->K1, w.dh1, p->dW1, "tc_mutan_bwd.dw1"));
-  if (p->dX1) VQA_TRY(dgrad(w.dh1, p->M, w.w1pk, p->K1, K1p, p->dX1, p->lddx1, p->accumulate_x1, "tc_mutan_bwd.dx1"));
+  if (big16) {
+    VQA_TRY(tc16_mutan_bwd_big(p, st, &ops16));
+  } else {
+    VQA_TRY(wgrad(X1, ldx1, p->M, p->K1, w.dh1, p->dW1, "tc_mutan_bwd.dw1"));
+    if (p->dX1) VQA_TRY(dgrad(w.dh1, p->M, w.w1pk, p->K1, K1p, p->dX1, p->lddx1, p->accumulate_x1, "tc_mutan_bwd.dx1"));
+  }
   VQA_TRY(wgrad(X2, ldx2, Mh, p->K2, w.dh2, p->dW2, "tc_mutan_bwd.dw2"));
   if (p->dX2) VQA_TRY(dgrad(w.dh2, Mh, w.w2pk, p->K2, K2p, p->dX2, p->lddx2, p->accumulate_x2, "tc_mutan_bwd.dx2"));
   return VQA_OK;
@@ -1029,11 +861,19 @@ int tc_dropout_bits_batch(float pdrop, uint64_t seed, const uint64_t* seed_dev, 
 
 // Upper bounds: a K that is not a multiple of 4 floats makes W (and a contiguous [M, K] X) un-addressable by TMA.
 size_t tc_linear_fwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N) {
+  if (is_bf16_math(math)) {
+    if (M >= TC16_MIN_M) return tc16_linear_fwd_ws(math == VQA_MATH_BF16X3 ? 2 : 1, groups, M, K, N);
+    math = small_math_of(math);
+  }
   if (math == VQA_MATH_FP32_SIMT || K % 4 == 0) return 0;
   return tc::align256((size_t)groups * N * tc::roundup(K, 4) * sizeof(float)) +
          tc::align256((size_t)groups * M * tc::roundup(K, 4) * sizeof(float));
 }
 size_t tc_linear_bwd_ws(int math, int groups, int64_t M, int64_t K, int64_t N) {
+  if (is_bf16_math(math)) {
+    if (M >= TC16_MIN_M) return tc16_linear_bwd_ws(math == VQA_MATH_BF16X3 ? 2 : 1, groups, M, K, N);
+    math = small_math_of(math);
+  }
   if (math == VQA_MATH_FP32_SIMT) return 0;
   size_t b = tc::align256((size_t)groups * M * tc::roundup(N, 32) * sizeof(float));
   if (K % 4 != 0)

@@ -4,7 +4,7 @@
 // Parameter tables follow the reference's state_dict order (seq2vec.* excluded).
 #include <string.h>
 
-#include "common.cuh"
+#include "gemm_tc.h"
 
 namespace vqa {
 
@@ -85,6 +85,10 @@ struct Cor2Ws {
   uint8_t* bits[32];           // packed dropout keep-bits of every dropout site, by layer id (train mode)
   int64_t bits_n[32];          // element count of each site
   float *vq1_w1p, *vq1_w2p, *vq2_w1p, *vq2_w2p, *ff_w1p, *ff_w2p, *eq1p, *eq2p, *clsp;   // vqa_pack_weights copies
+  // bf16 math modes: operand planes [np][rows][ld] handed from producer to consumer GEMMs (gemm_tc.h: Planes)
+  __nv_bfloat16 *vp, *v2p, *vlp, *v2lp;                // dropout(v), dropout(v2) [M][2048]; vl, v2l [M][320]
+  __nv_bfloat16 *cv_wp, *cv2_wp, *cv2_wtp;             // compress_v / compress_v2 weights [320][2048]; transposed [2048][320]
+  __nv_bfloat16 *vq1_wp, *vq1_wtp, *vq2_wp, *vq2_wtp;  // stacked Mutan W1 [2*512][320]; transposed [310][1024]
   size_t bytes;
 };
 
@@ -93,7 +97,8 @@ static int64_t lin_scratch_floats(int64_t B, int64_t N, int64_t C) {
   const int64_t M = B * N;
   const int64_t Cp = ((C + 31) / 32) * 32;
   // linear bwd: dZ + padded weights; Mutan bwd: stacked padded weights + dH1cat [M, R*512] + dH2cat [B, R*512]
-  const int64_t lin = M * 320 + 4 * B * 2048 + B * Cp + 2 * 2048 * 320 + C * 512;
+  // (bf16 modes: dZ planes in both orientations, 2 x [np = 2][M][320] bf16 = M * 640 floats)
+  const int64_t lin = M * 640 + 4 * B * 2048 + B * Cp + 2 * 2048 * 320 + C * 512;
   const int64_t mut = 2 * 5 * 512 * 1240 + M * 1024 + B * 5 * 512 + 65536;
   return (lin > mut ? lin : mut) + 4096;
 }
@@ -136,6 +141,13 @@ static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N, int64_t C) {
   w.vq2_w1p = c.take(2 * FPAD * 312); w.vq2_w2p = c.take(2 * FPAD * 312);
   w.ff_w1p = c.take(2 * FPAD * 2 * A); w.ff_w2p = c.take(2 * FPAD * 312);
   w.eq1p = c.take(D * 312); w.eq2p = c.take(D * 312); w.clsp = c.take(C * 512);
+  {  // plane buffers (sized for np = 2; bf16 elements = half floats)
+    auto takeh = [&](int64_t n) { return reinterpret_cast<__nv_bfloat16*>(c.take((n + 1) / 2)); };
+    w.vp = takeh(2 * M * D); w.v2p = takeh(2 * M * D); w.vlp = takeh(2 * M * HP); w.v2lp = takeh(2 * M * HP);
+    w.cv_wp = takeh(2 * HP * D); w.cv2_wp = takeh(2 * HP * D); w.cv2_wtp = takeh(2 * D * HP);
+    w.vq1_wp = takeh(2 * 2 * FPAD * HP); w.vq1_wtp = takeh(2 * H * 2 * FPAD);
+    w.vq2_wp = takeh(2 * 2 * FPAD * HP); w.vq2_wtp = takeh(2 * H * 2 * FPAD);
+  }
   w.bytes = c.off;
   return w;
 }
@@ -148,6 +160,7 @@ struct OdaWs {
   uint8_t* bits[32];
   int64_t bits_n[32];
   float *ff_w1p, *ff_w2p, *clsp;
+  __nv_bfloat16 *vp, *cv_wp;                           // bf16 modes: planes of dropout(v) and of compress_v's weight
   size_t bytes;
 };
 
@@ -172,6 +185,7 @@ static OdaWs carve_oda(void* base, int64_t B, int64_t N, int64_t C) {
       if (w.bits_n[i]) w.bits[i] = reinterpret_cast<uint8_t*>(c.take(w.bits_n[i] / 32 + 16));
   }
   w.ff_w1p = c.take(5 * FPAD * A); w.ff_w2p = c.take(5 * FPAD * 312); w.clsp = c.take(C * 512);
+  w.vp = reinterpret_cast<__nv_bfloat16*>(c.take(M * D)); w.cv_wp = reinterpret_cast<__nv_bfloat16*>(c.take(HP * D));
   w.bytes = c.off;
   return w;
 }
@@ -193,7 +207,7 @@ struct Ctx {
 // single or grouped linear forward; weight index widx[g] (bias = widx[g]+1)
 static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, int act, const float* const* X,
                    const int64_t* ldx, const int* widx, float* const* Y, const int64_t* ldy, const uint32_t* layer,
-                   const float* const* Wp = nullptr) {
+                   const float* const* Wp = nullptr, const LinExt* ext = nullptr) {
   vqa_linear_fwd_params lp = {};
   lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
   lp.p = c.pdrop(); lp.seed = c.p->seed; lp.seed_dev = c.p->seed_dev;
@@ -204,6 +218,7 @@ static int lin_fwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
     lp.Wp[g] = (Wp && c.packed) ? Wp[g] : nullptr;
   }
   lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
+  if (ext) return tc_linear_fwd(&lp, (cudaStream_t)c.stream, ext);      // bf16 modes: operand planes handed over
   return vqa_linear_fwd(&lp, c.stream);
 }
 
@@ -211,7 +226,8 @@ static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
                    const int64_t* ldx, const int* widx, const float* const* Y, const int64_t* ldy,
                    const float* const* dY, const int64_t* lddy, float* const* dX, const int64_t* lddx, int accumulate_x,
                    const uint32_t* layer, const float* const* Wp = nullptr,
-                   const float* pool_alpha = nullptr, const float* pool_dpooled = nullptr, int64_t pool_regions = 0) {
+                   const float* pool_alpha = nullptr, const float* pool_dpooled = nullptr, int64_t pool_regions = 0,
+                   const LinExt* ext = nullptr) {
   vqa_linear_bwd_params lp = {};
   lp.groups = groups; lp.M = M; lp.K = K; lp.N = N; lp.act = act; lp.math = c.p->math;
   lp.p = c.pdrop(); lp.seed = c.p->seed; lp.seed_dev = c.p->seed_dev; lp.accumulate_w = c.accumulate; lp.accumulate_x = accumulate_x;
@@ -226,12 +242,13 @@ static int lin_bwd(const Ctx& c, int groups, int64_t M, int64_t K, int64_t N, in
   }
   lp.workspace = c.lin_ws; lp.workspace_bytes = c.lin_ws_bytes;
   lp.pool_alpha = pool_alpha; lp.pool_dpooled = pool_dpooled; lp.pool_regions = pool_regions;
+  if (ext) return tc_linear_bwd(&lp, (cudaStream_t)c.stream, ext);
   return vqa_linear_bwd(&lp, c.stream);
 }
 
 static int mutan_fwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int64_t rows_per, const float* X1,
                      int64_t ldx1, const float* X2, int64_t ldx2, int l1, int l2, float* H1, float* H2, float* Y,
-                     int64_t ldy, const float* W1p = nullptr, const float* W2p = nullptr) {
+                     int64_t ldy, const float* W1p = nullptr, const float* W2p = nullptr, const MutanExt* ext = nullptr) {
   vqa_mutan_fwd_params mp = {};
   mp.R = R; mp.M = M; mp.K1 = K1; mp.K2 = K2; mp.F = F; mp.rows_per_h2 = rows_per; mp.math = c.p->math;
   mp.X1 = X1; mp.ldx1 = ldx1; mp.X2 = X2; mp.ldx2 = ldx2;
@@ -242,13 +259,15 @@ static int mutan_fwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int
   mp.H1 = H1; mp.H2 = H2; mp.Y = Y; mp.ldy = ldy;
   if (c.packed) { mp.W1p = W1p; mp.W2p = W2p; }
   mp.workspace = c.lin_ws; mp.workspace_bytes = c.lin_ws_bytes;
+  if (ext) return tc_mutan_fwd(&mp, (cudaStream_t)c.stream, ext);
   return vqa_mutan_fwd(&mp, c.stream);
 }
 
 static int mutan_bwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int64_t rows_per, const float* X1,
                      int64_t ldx1, const float* X2, int64_t ldx2, int l1, int l2, const float* H1, const float* H2,
                      const float* dY, int64_t lddy, float* dH2, float* dX1, int64_t lddx1, float* dX2, int64_t lddx2,
-                     int accumulate_x2, const float* W1p = nullptr, const float* W2p = nullptr) {
+                     int accumulate_x2, const float* W1p = nullptr, const float* W2p = nullptr,
+                     const MutanExt* ext = nullptr) {
   vqa_mutan_bwd_params mp = {};
   mp.R = R; mp.M = M; mp.K1 = K1; mp.K2 = K2; mp.F = F; mp.rows_per_h2 = rows_per; mp.math = c.p->math;
   mp.accumulate_w = c.accumulate; mp.accumulate_x1 = 0; mp.accumulate_x2 = accumulate_x2;
@@ -262,6 +281,7 @@ static int mutan_bwd(const Ctx& c, int R, int64_t M, int64_t K1, int64_t K2, int
   mp.dX1 = dX1; mp.lddx1 = lddx1; mp.dX2 = dX2; mp.lddx2 = lddx2;
   if (c.packed) { mp.W1p = W1p; mp.W2p = W2p; }
   mp.workspace = c.lin_ws; mp.workspace_bytes = c.lin_ws_bytes;
+  if (ext) return tc_mutan_bwd(&mp, (cudaStream_t)c.stream, ext);
   return vqa_mutan_bwd(&mp, c.stream);
 }
 
@@ -386,9 +406,32 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
   Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
   cudaEvent_t e_ql, e_gates;
-  if (p->train) {                                  // the mask compress_v needs right away
+  // bf16 math modes: the large GEMMs read bf16 operand planes (gemm_tc.h).  compress_v's input planes are made here
+  // with the dropout mask applied (Philox in registers: no keep-bit cache for this site, the planes ARE its stash).
+  const bool b16 = is_bf16_math(p->math) && M >= TC16_MIN_M;
+  const int np = p->math == VQA_MATH_BF16X3 ? 2 : 1;
+  LinExt x_cv, x_cv2;
+  MutanExt x_vq1, x_vq2;
+  if (b16) {
+    x_cv.Xp = Planes{w.vp, D, M * D}; x_cv.Wp = Planes{w.cv_wp, D, HP * D};
+    x_cv.Yp = w.vlp; x_cv.ldyp = HP; x_cv.yplane = M * HP;
+    x_cv2.Xp = Planes{w.v2p, D, M * D}; x_cv2.Wp = Planes{w.cv2_wp, D, HP * D};
+    x_cv2.Yp = w.v2lp; x_cv2.ldyp = HP; x_cv2.yplane = M * HP;
+    x_vq1.X1p = Planes{w.vlp, HP, M * HP}; x_vq1.W1p = Planes{w.vq1_wp, HP, 2 * FPAD * HP};
+    x_vq2.X1p = Planes{w.v2lp, HP, M * HP}; x_vq2.W1p = Planes{w.vq2_wp, HP, 2 * FPAD * HP};
+  }
+  if (p->train && !b16) {                          // the mask compress_v needs right away
     ProfScope ps_(stream, "dropout_bits");
     VQA_TRY(make_bits(p, w.bits, w.bits_n, stream, L_COMPRESS_V, true));
+  }
+  if (b16) {
+    ProfScope ps_(stream, "planes.v");
+    PackPlanesSeg sg = {};
+    sg.src = c.W[COMPRESS_V]; sg.rows = H; sg.rows_pad = HP; sg.K = D; sg.Kp = D; sg.dst = w.cv_wp; sg.plane = HP * D;
+    VQA_TRY(tc16::pack_planes(&sg, 1, np, ms));
+    const float* X[1] = {p->v}; int64_t ldx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V}; uint64_t base[1] = {0};
+    __nv_bfloat16* out[1] = {w.vp};
+    VQA_TRY(tc16::split_planes(X, ldx, 1, M, D, c.pdrop(), p->seed, p->seed_dev, layer, base, nullptr, out, D, M * D, np, ms));
   }
   Lanes::wait(ss, L->record(ms));                  // fork
   if (p->train) {                                  // every other site: first read after the main lane's e_ql wait
@@ -404,6 +447,21 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     pl.add(c.W[EQ1], w.eq1p, D, D, H); pl.add(c.W[EQ2], w.eq2p, D, D, H);
     pl.add(c.W[CLASSIF], w.clsp, p->C, p->C, F);
     VQA_TRY(vqa_pack_weights(pl.s, pl.n, ss));
+    if (b16) {      // operand planes of the remaining large-GEMM weights, both orientations, one launch
+      PackPlanesSeg sg[5] = {};
+      sg[0].src = c.W[COMPRESS_V2]; sg[0].rows = H; sg[0].rows_pad = HP; sg[0].K = D; sg[0].Kp = D;
+      sg[0].dst = w.cv2_wp; sg[0].plane = HP * D; sg[0].dstT = w.cv2_wtp; sg[0].Np = HP; sg[0].planeT = D * HP; sg[0].t_col0 = 0;
+      for (int r = 0; r < 2; ++r) {
+        PackPlanesSeg& a = sg[1 + r]; PackPlanesSeg& b = sg[3 + r];
+        a.src = c.W[VQ1_L1 + 2 * r]; b.src = c.W[VQ2_L1 + 2 * r];
+        a.rows = b.rows = F; a.rows_pad = b.rows_pad = FPAD; a.K = b.K = H; a.Kp = b.Kp = HP;
+        a.dst = w.vq1_wp + (int64_t)r * FPAD * HP; b.dst = w.vq2_wp + (int64_t)r * FPAD * HP;
+        a.plane = b.plane = 2 * FPAD * HP;
+        a.dstT = w.vq1_wtp; b.dstT = w.vq2_wtp; a.Np = b.Np = 2 * FPAD; a.planeT = b.planeT = H * 2 * FPAD;
+        a.t_col0 = b.t_col0 = (int64_t)r * FPAD;
+      }
+      VQA_TRY(tc16::pack_planes(sg, 5, np, ss));
+    }
   }
   {  // four 2400->310 question projections in one launch (config/CoR2.py:211,195,196,228)
     const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
@@ -421,10 +479,10 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // compress_v (config/CoR2.py:213)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, nullptr, b16 ? &x_cv : nullptr)); }
   }
   Lanes::wait(ms, e_ql);      // ql / qf ready
-  { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1, F, w.vq1_w1p, w.vq1_w2p)); }   // fusion_vq1 :214
+  { ProfScope ps_(stream, "fusion_vq1.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1, F, w.vq1_w1p, w.vq1_w2p, b16 ? &x_vq1 : nullptr)); }   // fusion_vq1 :214
   {  // att1 on raw v (:214)
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
@@ -445,9 +503,16 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // compress_v2 (:218)
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V2};
-    { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    if (b16) {      // planes of dropout(v2) for compress_v2's forward and weight-gradient GEMMs
+      ProfScope ps_(stream, "planes.v2");
+      uint64_t base[1] = {0};
+      const uint8_t* bits[1] = {p->train ? w.bits[L_COMPRESS_V2] : nullptr};
+      __nv_bfloat16* out[1] = {w.v2p};
+      VQA_TRY(tc16::split_planes(X, ldx, 1, M, D, c.pdrop(), p->seed, p->seed_dev, layer, base, bits, out, D, M * D, np, ms));
+    }
+    { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, nullptr, b16 ? &x_cv2 : nullptr)); }
   }
-  { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2, F, w.vq2_w1p, w.vq2_w2p)); }  // fusion_vq2 :219
+  { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2, F, w.vq2_w1p, w.vq2_w2p, b16 ? &x_vq2 : nullptr)); }  // fusion_vq2 :219
   {  // att2 on v2 (:219)
     vqa_region_softmax_pool_fwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
@@ -488,6 +553,15 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
   VQA_REQUIRE(L != nullptr, "vqa_cor2_bwd: cannot create the internal side stream");
   cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
   Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
+  const bool b16 = is_bf16_math(p->math) && M >= TC16_MIN_M;          // operand planes left by the forward (see vqa_cor2_fwd)
+  LinExt x_cv, x_cv2;
+  MutanExt x_vq1, x_vq2;
+  if (b16) {
+    x_cv.Xp = Planes{w.vp, D, M * D};
+    x_cv2.Xp = Planes{w.v2p, D, M * D}; x_cv2.WTp = Planes{w.cv2_wtp, HP, D * HP};
+    x_vq1.X1p = Planes{w.vlp, HP, M * HP}; x_vq1.W1Tp = Planes{w.vq1_wtp, 2 * FPAD, H * 2 * FPAD};
+    x_vq2.X1p = Planes{w.v2lp, HP, M * HP}; x_vq2.W1Tp = Planes{w.vq2_wtp, 2 * FPAD, H * 2 * FPAD};
+  }
   {  // linear_classif
     const float* X[1] = {w.xf}; int64_t ldx[1] = {XP}; int widx[1] = {CLASSIF}; const float* Y[1] = {p->logits};
     int64_t ldy[1] = {p->C}; const float* dY[1] = {bp->dlogits}; int64_t lddy[1] = {p->C};
@@ -522,13 +596,13 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     { ProfScope ps_(stream, "att2.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
   mark(3, ms);
-  { ProfScope ps_(stream, "fusion_vq2.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, F, w.d_f2_H2, w.dv2l, HP, w.dql, HP, 0, w.vq2_w1p, w.vq2_w2p)); }
+  { ProfScope ps_(stream, "fusion_vq2.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, F, w.d_f2_H2, w.dv2l, HP, w.dql, HP, 0, w.vq2_w1p, w.vq2_w2p, b16 ? &x_vq2 : nullptr)); }
   mark(4, ms);
   {  // compress_v2: v2 feeds both compress_v2 and att2's pooling; the dgrad store adds sum_g alpha2 * dpooled2
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; const float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {HP};
     float* dX[1] = {w.dv2}; int64_t lddx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V2};
-    { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, p->alpha2, w.dpooled2, N)); }
+    { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, p->alpha2, w.dpooled2, N, b16 ? &x_cv2 : nullptr)); }
   }
   mark(5, ms);
   // ---- att1 branch: the glimpse linears (side lane) initialise dpooled1, then the compound objects add to it
@@ -560,13 +634,13 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     { ProfScope ps_(stream, "att1.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
   mark(8, ms);
-  { ProfScope ps_(stream, "fusion_vq1.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, F, w.d_f1_H2, w.dvl, HP, w.dql, HP, 1, w.vq1_w1p, w.vq1_w2p)); }
+  { ProfScope ps_(stream, "fusion_vq1.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, F, w.d_f1_H2, w.dvl, HP, w.dql, HP, 1, w.vq1_w1p, w.vq1_w2p, b16 ? &x_vq1 : nullptr)); }
   mark(9, ms);
   Lanes::wait(ss, L->record(ms));                  // dql complete (fusion_vq2 + fusion_vq1)
   {  // compress_v: v is a graph input, no dgrad
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
+    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer, nullptr, nullptr, nullptr, 0, b16 ? &x_cv : nullptr)); }
   }
   mark(10, ms);
   {  // the four question projections
@@ -619,9 +693,22 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   VQA_REQUIRE(L != nullptr, "vqa_oda_fwd: cannot create the internal side stream");
   cudaStream_t ms = (cudaStream_t)stream, ss = L->side;
   Ctx cs = c; cs.stream = ss; cs.lin_ws = w.side_ws; cs.lin_ws_bytes = w.side_ws_bytes;
-  if (p->train) {
+  const bool b16 = is_bf16_math(p->math) && M >= TC16_MIN_M;       // bf16 modes: compress_v reads operand planes (see vqa_cor2_fwd)
+  const int np = p->math == VQA_MATH_BF16X3 ? 2 : 1;
+  LinExt x_cv;
+  if (b16) { x_cv.Xp = Planes{w.vp, D, M * D}; x_cv.Wp = Planes{w.cv_wp, D, HP * D}; }
+  if (p->train && !b16) {
     ProfScope ps_(stream, "dropout_bits");
     VQA_TRY(make_bits(p, w.bits, w.bits_n, stream, L_COMPRESS_V, true));
+  }
+  if (b16) {
+    ProfScope ps_(stream, "planes.v");
+    PackPlanesSeg sg = {};
+    sg.src = c.W[COMPRESS_V]; sg.rows = H; sg.rows_pad = HP; sg.K = D; sg.Kp = D; sg.dst = w.cv_wp; sg.plane = HP * D;
+    VQA_TRY(tc16::pack_planes(&sg, 1, np, ms));
+    const float* X[1] = {p->v}; int64_t ldx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V}; uint64_t base[1] = {0};
+    __nv_bfloat16* out[1] = {w.vp};
+    VQA_TRY(tc16::split_planes(X, ldx, 1, M, D, c.pdrop(), p->seed, p->seed_dev, layer, base, nullptr, out, D, M * D, np, ms));
   }
   Lanes::wait(ss, L->record(ms));               // fork
   if (p->train) {
@@ -638,7 +725,7 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
   {  // compress_v (config/ODA.py:211)
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    { ProfScope ps_(stream, "compress_v.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, nullptr, b16 ? &x_cv : nullptr)); }
   }
   {  // compress_q + linear_q (:214, :233)
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
@@ -707,7 +794,10 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
   {
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {H}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {H}; uint32_t layer[1] = {L_COMPRESS_V};
-    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
+    LinExt x_cv;
+    const bool b16 = is_bf16_math(p->math) && M >= TC16_MIN_M;
+    if (b16) x_cv.Xp = Planes{w.vp, D, M * D};
+    { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer, nullptr, nullptr, nullptr, 0, b16 ? &x_cv : nullptr)); }
   }
   mark(4);
   {

@@ -13,7 +13,7 @@ GOLDEN_CASES = ["oda_eval_b4", "oda_train_b4", "cor2_eval_b4", "cor2_train_b4", 
 # so structurally-zero gradients (conv_att biases, fusion_vq biases) compare as ~0 instead of noise/noise.
 FP32_TOL = 1e-4
 # precision names that claim the fp32-parity bound (1e-4): CUDA-core fp32 and the error-compensated tensor-core modes
-PARITY_MODES = ["fp32", "tf32x3"]
+PARITY_MODES = ["fp32", "tf32x3", "bf16x3"]
 
 
 def rel_err(new, ref, floor=0.0):

@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--model", default="CoR2")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--regions", type=int, default=36)
-    ap.add_argument("--precision", default="tf32x3")
+    ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--eval-mode", action="store_true")
     ap.add_argument("--steps", type=int, default=1)
     args = ap.parse_args()

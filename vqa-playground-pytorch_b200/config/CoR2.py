@@ -46,7 +46,7 @@ debug = False
 
 # additions (reference defaults)
 num_regions = 36
-precision = "tf32x3"       # fp32-parity arithmetic on tensor cores; "fp32" = CUDA-core FMA, "tf32" = single pass
+precision = "bf16x3"       # fp32-parity arithmetic on bf16 tensor cores (hi + lo operand planes); see _base.CoreModel
 
 method_name = os.path.splitext(os.path.basename(__file__))[0]
 if splitnum == 2:

@@ -11,8 +11,11 @@ class CoreModel(nn.Module):
 
     Extra constructor arguments, all defaulting to the reference's behaviour:
       num_regions  N (reference hard-codes 36: config/CoR2.py:203, config/ODA.py:202,222)
-      precision    GEMM arithmetic: 'tf32x3' (default: tcgen05 tensor cores, error-compensated 3xTF32, meets the
-                   1e-4 fp32-parity bound), 'fp32' (CUDA-core FMA, bitwise reproducible), 'tf32' (single pass)
+      precision    GEMM arithmetic (include/vqacore.h VQA_MATH_*).  fp32-parity modes (<= 1e-4 vs the reference):
+                   'bf16x3' (default: the large region-side GEMMs read bf16 hi + lo operand planes and issue three
+                   bf16 tcgen05 MMAs per product, the small ones run 3xTF32), 'tf32x3' (fp32 operands, 3xTF32
+                   everywhere), 'fp32' (CUDA-core FMA, bitwise reproducible).  Reduced precision (<= 2e-2):
+                   'bf16' (one bf16 plane for the large GEMMs, one TF32 pass for the small ones), 'tf32'.
       seq2vec      question encoder module; default passes sample['q_idxes'] through as the
                    2400-d embedding (blocks.QuestionPassThrough)
     """

@@ -425,7 +425,7 @@ def run_ours(args):
         total = sum(per_op.values())
         pk = peaks()
         breakdown = {k: round(v, 4) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])}
-        kernels = {k[2:]: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])[:6]}
+        kernels = {k[2:]: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])[:24]}
         roof = kernel_roofline(per_kernel, per_op, total, pk, args, B, N, C)
     if world > 1:
         dist.barrier()

@@ -321,6 +321,14 @@ typedef struct {
   const float* g1;         /* [B,D] */
   const float* g2;         /* [B,D] */
   float* v2;               /* [B,N,D] */
+  /* Optional (bf16 math modes): also write the bf16 operand planes of dropout(v2) that compress_v2's GEMMs read
+   * (VQA_MATH_BF16X3: 2 planes hi, lo; VQA_MATH_BF16: 1), [planes][B*N][D], planes v2_plane_stride elements apart;
+   * keep = bit ((b*N+j)*D + c) of v2_keep_bits (NULL: all kept, scale 1).  Saves a second pass over v2. */
+  void* v2_planes;         /* bf16, or NULL */
+  int v2_nplanes;
+  int64_t v2_plane_stride;
+  const uint8_t* v2_keep_bits;
+  float v2_keep_scale;
 } vqa_cor_compound_fwd_params;
 int vqa_cor_compound_fwd(const vqa_cor_compound_fwd_params* p, void* stream);
 
@@ -334,6 +342,15 @@ typedef struct {
   float* dg1; float* dg2;  /* [B,D] */
   float* dpooled;          /* [B,G,D]; glimpse-0 slice is ACCUMULATED into */
   float* dalpha0_ext;      /* [B] */
+  /* Optional: dv2 is handed over RAW by the producer of its largest term (compress_v2's dgrad GEMM, G = dZ.W) and
+   * finished while it is read here, instead of in that GEMM's epilogue (one pass less over [B,N,D]):
+   *   dv2_eff[b,j,c] = keep(b,j,c) * dv2_keep_scale * dv2[b,j,c] + sum_g dv2_pool_alpha[b,j,g] * dv2_pool_dpooled[b,g,c]
+   * keep = bit ((b*N+j)*D + c) of dv2_keep_bits (compress_v2's input-dropout mask, vqa_dropout_bits; NULL: all kept),
+   * the second term is the gradient of att2's pooling over the same v2 (NULL alpha: none). */
+  const uint8_t* dv2_keep_bits;
+  float dv2_keep_scale;
+  const float* dv2_pool_alpha;     /* [B,N,G] */
+  const float* dv2_pool_dpooled;   /* [B,G,D] */
 } vqa_cor_compound_bwd_params;
 int vqa_cor_compound_bwd(const vqa_cor_compound_bwd_params* p, void* stream);
 

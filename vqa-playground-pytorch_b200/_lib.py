@@ -101,12 +101,14 @@ class PoolBwd(C.Structure):
 
 class CompoundFwd(C.Structure):
     _fields_ = [("B", i64), ("N", i64), ("D", i64), ("x", fp), ("pooled", fp), ("alpha", fp), ("g1", fp), ("g2", fp),
-                ("v2", fp)]
+                ("v2", fp), ("v2_planes", fp), ("v2_nplanes", C.c_int), ("v2_plane_stride", i64), ("v2_keep_bits", fp),
+                ("v2_keep_scale", C.c_float)]
 
 
 class CompoundBwd(C.Structure):
     _fields_ = [("B", i64), ("N", i64), ("D", i64), ("x", fp), ("pooled", fp), ("alpha", fp), ("g1", fp), ("g2", fp),
-                ("dv2", fp), ("dg1", fp), ("dg2", fp), ("dpooled", fp), ("dalpha0_ext", fp)]
+                ("dv2", fp), ("dg1", fp), ("dg2", fp), ("dpooled", fp), ("dalpha0_ext", fp),
+                ("dv2_keep_bits", fp), ("dv2_keep_scale", C.c_float), ("dv2_pool_alpha", fp), ("dv2_pool_dpooled", fp)]
 
 
 class OdaFwd(C.Structure):

@@ -190,8 +190,13 @@ extern "C" int vqa_region_softmax_pool_fwd(const vqa_region_softmax_pool_fwd_par
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   {
     KProf kp_(st, "att_logits_softmax", "hbm", 4.0 * ((double)p->B * p->N * p->Ff + (double)p->B * p->N * G));
-    kern<<<(unsigned)p->B, ATT_THREADS, smem, st>>>(fs, p->N, p->Ff, p->Wc, p->bc, p->alpha);
+    const unsigned S = p->N >= 16 ? 4 : 1;
+    kern<<<dim3((unsigned)p->B, S), ATT_THREADS, smem, st>>>(fs, p->N, p->Ff, p->Wc, p->bc, p->alpha);
     VQA_TRY(check_launch("att_logits_softmax"));
+    if (S > 1) {
+      softmax_regions_kernel<<<(unsigned)p->B, 128, (size_t)p->N * G * sizeof(float), st>>>(p->N, p->alpha);
+      VQA_TRY(check_launch("softmax_regions"));
+    }
   }
   return launch_pool_fwd(p->B, p->N, p->D, p->x, p->alpha, p->pooled, st);
 }

@@ -63,7 +63,10 @@ __device__ __forceinline__ void softmax_regions_smem(float* z, int N) {
   }
 }
 
-// z[b,i,g] = sum_c Wc[g,c]*fuse~[b,i,c] + bc[g]; alpha = softmax_i z.   grid = B.
+// z[b,i,g] = sum_c Wc[g,c]*fuse~[b,i,c] + bc[g]; alpha = softmax_i z.   grid = (B, S).  S = 1: logits and softmax in
+// one CTA per sample.  S > 1: CTA (b, s) takes the rows i = s, s + S, ... and writes the raw logits; the softmax over
+// regions follows in softmax_regions_kernel (one CTA per sample keeps only ~14 warps per SM resident at B = 256 and
+// left the kernel latency-bound at 13 % of the HBM rate).
 // dynamic smem: G*Ff (weights) + N*G (logits).  One warp per region row; a lane owns quads of 4 consecutive
 // elements (one Philox call per quad when the row start is 4-aligned, two otherwise) and issues all of its
 // loads for the row before using them.
@@ -79,7 +82,8 @@ att_logits_softmax_kernel(FS fs, int64_t N, int64_t Ff, const float* __restrict_
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int QPL = 4;                       // quads per lane per pass: 32 lanes * 4 quads * 4 = 512 elements
-  for (int64_t i = warp; i < N; i += ATT_THREADS / 32) {
+  const int S = gridDim.y;
+  for (int64_t i = (int64_t)blockIdx.y + (int64_t)warp * S; i < N; i += (int64_t)(ATT_THREADS / 32) * S) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     for (int64_t c0 = 0; c0 < Ff; c0 += 32 * QPL * 4) {
       float f[QPL][4];
@@ -110,12 +114,17 @@ att_logits_softmax_kernel(FS fs, int64_t N, int64_t Ff, const float* __restrict_
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
     if (lane == 0) {
-      z_s[i * G + 0] = a0 + bc[0];
-      z_s[i * G + 1] = a1 + bc[1];
-      z_s[i * G + 2] = a2 + bc[2];
-      z_s[i * G + 3] = a3 + bc[3];
+      if (S > 1) {
+        *reinterpret_cast<float4*>(&alpha[(b * N + i) * G]) = make_float4(a0 + bc[0], a1 + bc[1], a2 + bc[2], a3 + bc[3]);
+      } else {
+        z_s[i * G + 0] = a0 + bc[0];
+        z_s[i * G + 1] = a1 + bc[1];
+        z_s[i * G + 2] = a2 + bc[2];
+        z_s[i * G + 3] = a3 + bc[3];
+      }
     }
   }
+  if (S > 1) return;
   __syncthreads();
   softmax_regions_smem(z_s, (int)N);
   __syncthreads();

@@ -77,15 +77,26 @@ static int operand_tmap(CUtensorMap* out, const float* ptr, bool mn_major, int64
   return make_tmap(out, ptr, k_extent, mn_extent, ld, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
-// y = act(y) in place over a [M, N] window of row stride ld; grid.z = group
+// y = act(y) in place over a [M, N] window of row stride ld; grid = (column chunks, row chunks, groups): no index
+// divisions, 128-bit accesses where the window allows them
 struct ActArgs { float* Y[MAXG]; int64_t ld[MAXG]; };
-__global__ void act_inplace_kernel(ActArgs a, int64_t M, int64_t N, int act) {
-  float* y = a.Y[blockIdx.z];
+__global__ void __launch_bounds__(256) act_inplace_kernel(ActArgs a, int64_t M, int64_t N, int act, int rows_per_cta) {
+  float* __restrict__ y = a.Y[blockIdx.z];
   const int64_t ld = a.ld[blockIdx.z];
-  const int64_t total = M * N;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = t / N, n = t - m * N;
-    y[m * ld + n] = act_apply(act, y[m * ld + n]);
+  const int64_t n = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (n >= N) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+  const bool vec = n + 4 <= N && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+  for (int64_t m = r0; m < r1; ++m) {
+    float* p = y + m * ld + n;
+    if (vec) {
+      float4 v = *reinterpret_cast<float4*>(p);
+      v.x = act_apply(act, v.x); v.y = act_apply(act, v.y); v.z = act_apply(act, v.z); v.w = act_apply(act, v.w);
+      *reinterpret_cast<float4*>(p) = v;
+    } else {
+      for (int e = 0; e < 4 && n + e < N; ++e) p[e] = act_apply(act, p[e]);
+    }
   }
 }
 
@@ -475,9 +486,9 @@ int tc_linear_fwd(const vqa_linear_fwd_params* p, cudaStream_t st, const LinExt*
   if (q.epi.atomic && p->act != VQA_ACT_NONE) {
     ActArgs a = {};
     for (int g = 0; g < MAXG; ++g) { const int s = g < p->groups ? g : 0; a.Y[g] = p->Y[s]; a.ld[g] = p->ldy[s]; }
-    int64_t blocks = cdiv(p->M * p->N, 256);
-    if (blocks > 1024) blocks = 1024;
-    act_inplace_kernel<<<dim3((unsigned)blocks, 1, (unsigned)p->groups), 256, 0, st>>>(a, p->M, p->N, p->act);
+    const int rows_per_cta = 8;
+    act_inplace_kernel<<<dim3((unsigned)cdiv(p->N, 1024), (unsigned)cdiv(p->M, rows_per_cta), (unsigned)p->groups), 256, 0, st>>>(
+        a, p->M, p->N, p->act, rows_per_cta);
     VQA_TRY(check_launch("tc_linear_fwd.act"));
   }
   return VQA_OK;
@@ -565,7 +576,7 @@ int tc_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st, const LinExt*
     if (!p->accumulate_w)
       for (int g = 0; g < p->groups; ++g)
         if (p->db[g]) cudaMemsetAsync(p->db[g], 0, (size_t)p->N * sizeof(float), st);
-    const int rows_per_cta = 64;
+    const int rows_per_cta = p->M <= 1024 ? 16 : 64;          // small M: more CTAs (the kernel is latency-bound there)
     dim3 grid((unsigned)cdiv(ldz, 32), (unsigned)cdiv(p->M, rows_per_cta), (unsigned)p->groups);
     KProf kp_(st, "dz_colsum", "hbm", 4.0 * (double)p->groups * p->M * p->N * (p->act != VQA_ACT_NONE ? 3 : 2));
     dz_colsum_kernel<<<grid, 256, 0, st>>>(a, p->M, p->N, ldz, p->act, rows_per_cta);
@@ -660,7 +671,7 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st, const MutanExt*
     VQA_TRY(pack_weights(p->W2, p->R, p->F, Fp, p->K2, w.w2pk, st));
   }
   const int bn = pick_bn(p->F);
-  {  // H2_r = X2 . W2_r^T + b2_r  (grouped over r)
+  if (!(ext && ext->h2_mode == 2)) {  // H2_r = X2 . W2_r^T + b2_r  (grouped over r)
     Params<EpiBiasAct> q = {};
     for (int g = 0; g < MAXG; ++g) {
       const int s = g < p->R ? g : 0;
@@ -674,6 +685,7 @@ int tc_mutan_fwd(const vqa_mutan_fwd_params* p, cudaStream_t st, const MutanExt*
     if (q.epi.atomic) cudaMemsetAsync(p->H2, 0, (size_t)p->R * Mh * p->F * sizeof(float), st);
     VQA_TRY(launch(q, p->R, x3, st, "tc_mutan_fwd.h2"));
   }
+  if (ext && ext->h2_mode == 1) return VQA_OK;
   if (big16) {      // the X1-side GEMMs on the bf16-plane kernel, its scratch behind this function's
     vqa_mutan_fwd_params q = *p;
     q.workspace = reinterpret_cast<char*>(p->workspace) + w.bytes;

@@ -43,8 +43,12 @@ struct LinExt {
   Planes WTp;                   // planes of W^T         [K][N_pad]    (dgrad)
   __nv_bfloat16* Yp = nullptr;  // forward: also write the planes of Y [M][ldyp]
   int64_t ldyp = 0, yplane = 0;
+  bool raw_dx = false;          // backward: dX = dZ.W as is — the caller's consumer applies the input-dropout mask (and
+                                // any pooling addend) while it reads dX (vqa_cor_compound_bwd's dv2_* fields)
 };
 struct MutanExt {
+  int h2_mode = 0;              // forward: 0 = H2 then the X1-side GEMMs; 1 = H2 = X2.W2^T + b2 only (it depends on the
+                                // question side alone: a plan runs it early on its side lane); 2 = H2 is already there
   Planes X1p;                   // [M][K1p]
   Planes W1p;                   // stacked [R*Fp][K1p]
   Planes W1Tp;                  // [K1][R*Fp]

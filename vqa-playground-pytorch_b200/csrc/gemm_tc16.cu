@@ -138,18 +138,22 @@ struct SplitArgs {
   const uint8_t* bits[MAXG];
   uint32_t layer[MAXG]; uint64_t base[MAXG];
 };
+// grid = (column chunks of 1024, row chunks, groups); a thread makes one quad of `rows_per_cta` consecutive rows
 __global__ void __launch_bounds__(256)
-split_planes_kernel(SplitArgs a, int64_t M, int64_t K, int64_t ldp, int64_t plane, int np, Drop d) {
-  const int g = blockIdx.y;
+split_planes_kernel(SplitArgs a, int64_t M, int64_t K, int64_t ldp, int64_t plane, int np, Drop d, int rows_per_cta) {
+  const int g = blockIdx.z;
   const float* __restrict__ x = a.X[g];
   const int64_t ldx = a.ldx[g];
   __nv_bfloat16* out = a.out[g];
   const uint8_t* __restrict__ bits = a.bits[g];
-  const int64_t q_per_row = ldp / 4, total = M * q_per_row;
   const uint64_t seed = d.on ? d.key() : 0;
   const bool vec = (ldx % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = t / q_per_row, k = (t - m * q_per_row) * 4;
+  const int64_t k = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (k >= ldp) return;
+  const int64_t m_begin = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t m_end = m_begin + rows_per_cta < M ? m_begin + rows_per_cta : M;
+#pragma unroll 4
+  for (int64_t m = m_begin; m < m_end; ++m) {
     float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (k + 4 <= K && vec) {
       const float4 v = ld_stream4(x + m * ldx + k);
@@ -191,10 +195,10 @@ int split_planes(const float* const* X, const int64_t* ldx, int groups, int64_t 
     a.layer[g] = layer ? layer[s] : 0; a.base[g] = base ? base[s] : 0;
   }
   Drop d = make_drop(pdrop, seed, 0, 0, 1, seed_dev);
-  int64_t blocks = cdiv(M * (ldp / 4), 256);
-  if (blocks > 8 * (int64_t)sm_count()) blocks = 8 * (int64_t)sm_count();
+  const int rows_per_cta = M >= 4096 ? 8 : 1;
   KProf kp_(st, "split_planes", "hbm", (double)groups * M * K * (4.0 + 2.0 * np));
-  split_planes_kernel<<<dim3((unsigned)blocks, (unsigned)groups), 256, 0, st>>>(a, M, K, ldp, plane, np, d);
+  split_planes_kernel<<<dim3((unsigned)cdiv(ldp, 1024), (unsigned)cdiv(M, rows_per_cta), (unsigned)groups), 256, 0, st>>>(
+      a, M, K, ldp, plane, np, d, rows_per_cta);
   return check_launch("split_planes");
 }
 
@@ -408,7 +412,8 @@ size_t tc16_linear_bwd_ws(int np, int groups, int64_t M, int64_t K, int64_t N) {
 }
 
 template <bool POOL>
-static int dgrad16_launch(const vqa_linear_bwd_params* p, const Planes* dzp, const Planes* wtp, int np, cudaStream_t st) {
+static int dgrad16_launch(const vqa_linear_bwd_params* p, const Planes* dzp, const Planes* wtp, int np, cudaStream_t st,
+                          bool raw = false) {
   using namespace tc16;
   Params<EpiDgradT<POOL>> q = {};
   const int bn = pick_bn(p->K);
@@ -420,8 +425,8 @@ static int dgrad16_launch(const vqa_linear_bwd_params* p, const Planes* dzp, con
   }
   q.M = (int)p->M; q.N = (int)p->K; q.K = (int)p->N; q.groups = p->groups; q.k_splits = 1; q.a_mn = 0; q.b_mn = 0;
   q.epi.accumulate = p->accumulate_x; q.epi.atomic = 0;
-  q.epi.drop_on = p->p > 0.0f;
-  q.epi.drop = make_drop(p->p, p->seed, 0, 0, 1, p->seed_dev);
+  q.epi.drop_on = p->p > 0.0f && !raw;
+  q.epi.drop = make_drop(raw ? 0.0f : p->p, p->seed, 0, 0, 1, p->seed_dev);
   for (int g = 0; g < MAXG; ++g) {
     const int s = g < p->groups ? g : 0;
     q.epi.gd.layer[g] = p->layer[s]; q.epi.gd.base[g] = p->drop_index_base[s];
@@ -522,6 +527,7 @@ int tc16_linear_bwd(const vqa_linear_bwd_params* p, cudaStream_t st, const LinEx
       }
       VQA_TRY(pack_planes(segs, p->groups, np, st));
     }
+    if (ext && ext->raw_dx) return dgrad16_launch<false>(p, dzp, wtp, np, st, true);
     return p->pool_alpha ? dgrad16_launch<true>(p, dzp, wtp, np, st) : dgrad16_launch<false>(p, dzp, wtp, np, st);
   }
   return VQA_OK;

@@ -468,6 +468,14 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
     int64_t ldy[4] = {HP, HP, HP, HP}; uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
     { ProfScope ps_(ss, "q_proj4.fwd"); VQA_TRY(lin_fwd(cs, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer)); }
+    if (b16) {     // the question halves H2 of both region-question fusions, off the main lane
+      ProfScope ps_(ss, "fusion_vq.h2");
+      MutanExt h1 = x_vq1, h2 = x_vq2;
+      h1.h2_mode = h2.h2_mode = 1;
+      VQA_TRY(mutan_fwd(cs, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.fuse1, F, w.vq1_w1p, w.vq1_w2p, &h1));
+      VQA_TRY(mutan_fwd(cs, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2, F, w.vq2_w1p, w.vq2_w2p, &h2));
+      x_vq1.h2_mode = x_vq2.h2_mode = 2;
+    }
     e_ql = L->record(ss);
   }
   {  // gates g1, g2 = sigmoid(310->2048) (config/CoR2.py:195-196)
@@ -498,18 +506,15 @@ extern "C" int vqa_cor2_fwd(const vqa_model_fwd_params* p, void* stream) {
     vqa_cor_compound_fwd_params cp = {};
     cp.B = B; cp.N = N; cp.D = D; cp.x = p->v; cp.pooled = w.pooled1; cp.alpha = p->alpha1; cp.g1 = w.g1; cp.g2 = w.g2;
     cp.v2 = p->v2;
+    if (b16) {     // the operand planes of dropout(v2) for compress_v2's forward and weight-gradient GEMMs, same pass
+      cp.v2_planes = w.v2p; cp.v2_nplanes = np; cp.v2_plane_stride = M * D;
+      cp.v2_keep_bits = p->train ? w.bits[L_COMPRESS_V2] : nullptr; cp.v2_keep_scale = 1.0f / (1.0f - P_DROP);
+    }
     { ProfScope ps_(stream, "compound.fwd"); VQA_TRY(vqa_cor_compound_fwd(&cp, stream)); }
   }
   {  // compress_v2 (:218)
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V2};
-    if (b16) {      // planes of dropout(v2) for compress_v2's forward and weight-gradient GEMMs
-      ProfScope ps_(stream, "planes.v2");
-      uint64_t base[1] = {0};
-      const uint8_t* bits[1] = {p->train ? w.bits[L_COMPRESS_V2] : nullptr};
-      __nv_bfloat16* out[1] = {w.v2p};
-      VQA_TRY(tc16::split_planes(X, ldx, 1, M, D, c.pdrop(), p->seed, p->seed_dev, layer, base, bits, out, D, M * D, np, ms));
-    }
     { ProfScope ps_(stream, "compress_v2.fwd"); VQA_TRY(lin_fwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, layer, nullptr, b16 ? &x_cv2 : nullptr)); }
   }
   { ProfScope ps_(stream, "fusion_vq2.fwd"); VQA_TRY(mutan_fwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.fuse2, F, w.vq2_w1p, w.vq2_w2p, b16 ? &x_vq2 : nullptr)); }  // fusion_vq2 :219
@@ -559,6 +564,7 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
   if (b16) {
     x_cv.Xp = Planes{w.vp, D, M * D};
     x_cv2.Xp = Planes{w.v2p, D, M * D}; x_cv2.WTp = Planes{w.cv2_wtp, HP, D * HP};
+    x_cv2.raw_dx = true;       // dv2 is finished (mask + att2 pooling gradient) by compound.bwd while it reads it
     x_vq1.X1p = Planes{w.vlp, HP, M * HP}; x_vq1.W1Tp = Planes{w.vq1_wtp, 2 * FPAD, H * 2 * FPAD};
     x_vq2.X1p = Planes{w.v2lp, HP, M * HP}; x_vq2.W1Tp = Planes{w.vq2_wtp, 2 * FPAD, H * 2 * FPAD};
   }
@@ -611,6 +617,10 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     vqa_cor_compound_bwd_params cp = {};
     cp.B = B; cp.N = N; cp.D = D; cp.x = p->v; cp.pooled = w.pooled1; cp.alpha = p->alpha1; cp.g1 = w.g1; cp.g2 = w.g2;
     cp.dv2 = w.dv2; cp.dg1 = w.dg1; cp.dg2 = w.dg2; cp.dpooled = w.dpooled1; cp.dalpha0_ext = w.dalpha_ext;
+    if (b16) {                 // w.dv2 holds the raw dZ.W of compress_v2's dgrad
+      cp.dv2_keep_bits = p->train ? w.bits[L_COMPRESS_V2] : nullptr; cp.dv2_keep_scale = 1.0f / (1.0f - P_DROP);
+      cp.dv2_pool_alpha = p->alpha2; cp.dv2_pool_dpooled = w.dpooled2;
+    }
     { ProfScope ps_(stream, "compound.bwd"); VQA_TRY(vqa_cor_compound_bwd(&cp, stream)); }
   }
   {  // gates

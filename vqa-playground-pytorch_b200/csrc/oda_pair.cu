@@ -349,8 +349,8 @@ extern "C" int vqa_oda_pair_attn_fwd(const vqa_oda_pair_attn_fwd_params* p, void
     VQA_TRY(check_launch("oda_wsum"));
     FuseOdaEval fs{p->vl, p->ql, p->N, p->H};
     const size_t smem = (size_t)(G * p->H + p->N * G) * sizeof(float);
-    att_logits_softmax_kernel<FuseOdaEval><<<(unsigned)p->B, ATT_THREADS, smem, st>>>(fs, p->N, p->H, p->wsum, p->bc,
-                                                                                     p->alpha);
+    att_logits_softmax_kernel<FuseOdaEval><<<dim3((unsigned)p->B, 1), ATT_THREADS, smem, st>>>(fs, p->N, p->H, p->wsum,
+                                                                                               p->bc, p->alpha);
     VQA_TRY(check_launch("oda_logits_eval"));
   } else {
     Drop d = make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev);

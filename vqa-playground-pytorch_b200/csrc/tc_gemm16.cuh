@@ -14,7 +14,8 @@
 //   warps 2-9   epilogue: the accumulator is DOUBLE-BUFFERED in TMEM (2 x ACC_COLS columns), so the epilogue of tile t
 //               runs under the main loop of tile t+1.  It moves 32 accumulator columns at a time through a
 //               double-buffered shared-memory slab (tcgen05.ld -> st.shared -> one named barrier -> functor), with the
-//               same functors as tc_gemm.cuh (tc_epilogues.cuh).
+//               same functors as tc_gemm.cuh (tc_epilogues.cuh).  (Warp-private slabs without the barrier were
+//               measured 5-10 % slower on every epilogue-bound launch: profiles/r2_experiments.md.)
 // Operands may be K-major ([rows, K] row-major) or MN-major ([K, rows] row-major, the transposed view used by
 // wgrad/dgrad); an MN-major B needs BN % 64 == 0.  Descriptor layouts follow cute/arch/mma_sm100_desc.hpp and
 // cute/atom/mma_traits_sm100.hpp (make_umma_desc, 16-bit SWIZZLE_128B canonical layouts).

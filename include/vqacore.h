@@ -410,6 +410,15 @@ typedef struct {
   float* dlogits;        /* [B,C] or NULL */
 } vqa_kld_logsoftmax_params;
 int vqa_kld_logsoftmax_fwd_bwd(const vqa_kld_logsoftmax_params* p, void* stream);
+/* Input pipeline: region features stored and shipped as bf16 (pre-packed shards: half the host->device bytes of the
+ * reference's fp32 h5 features, datasets.py:517-549, :905-970) are widened to the fp32 tensor the plans read.  Exact. */
+int vqa_cast_bf16_f32(int64_t n, const void* src_bf16, float* dst, void* stream);
+/* Prediction tail of the eval loop (train.py:146-169, `output.data.cpu().max(1)`): pred[b] = index of the first maximum
+ * of logits[b, :] (OpenEnded), or of the candidates mc_idx[b, 0..n_mc) (MultipleChoice, train.py:153-164: -1 entries are
+ * padding; pred = -1 when a row has no candidate).  best ([B] or NULL) receives the winning logit.  The B x C logits
+ * never leave the device: only B indices do. */
+int vqa_argmax_rows(int64_t B, int64_t C, const float* logits, const int64_t* mc_idx, int64_t n_mc, int64_t* pred,
+                    float* best, void* stream);
 /* out[0] = sum(rows[0..n)) with a fixed reduction order; y = x * scale[0] with the scalar read on the device
  * (the incoming autograd gradient of the scalar loss) — the two pieces that keep the loss off ATen. */
 int vqa_sum_rows(int64_t n, const float* rows, float* out, void* stream);

@@ -224,6 +224,58 @@ def cor2_forward(sd, v, q, drop=no_drop, num_regions=36, ties=None):
     return x, alpha_dict
 
 
+def cor_layers(steps):
+    """Dropout call sites of a CoR chain with `steps` attention steps, in forward-call order (steps = 2: COR2_LAYERS)."""
+    out = COR2_LAYERS[:17]
+    for s in range(3, steps + 1):
+        out += ["compress_q_%d" % (2 * s - 3), "expand_q_%d" % (2 * s - 3), "compress_q_%d" % (2 * s - 2),
+                "expand_q_%d" % (2 * s - 2), "compress_v%d" % s, "att%d.conv_att" % s]
+        out += ["att%d.list_linear_v_fusion.%d" % (s, g) for g in range(G)]
+    return out + COR2_LAYERS[17:]
+
+
+def cor_forward(sd, v, q, drop=no_drop, num_regions=36, steps=3):
+    """The chain of reasoning with `steps` attention steps.  UNPINNED for steps > 2: the reference ships only the
+    two-step config/CoR2.py (the 3-step model is known from the `alpha3` / `v3_feature` keys of
+    visu.py:2491-2495 and CoR_Visulization.py:107-109).  Built from the reference's OWN blocks composed once more:
+    every further step s calls decare_cat(previous objects, v, q) (config/CoR2.py:191-199) with its own gates, takes
+    the alpha_{s-1}[0]-weighted sum over i (:215-216), compresses, fuses with the question and attends (:218-219)."""
+    L = {n: i for i, n in enumerate(cor_layers(steps))}
+    N = num_regions
+    v = v.contiguous().view(-1, N, D_DIM)
+    b = v.size(0)
+    ql = my_linear(q, sd["compress_q.linear.weight"], sd["compress_q.linear.bias"], 0.5, "relu", drop, L["compress_q"])
+    x, prev, feats, alphas, objects = v, v, [], [], []
+    for s in range(1, steps + 1):
+        if s > 1:
+            k1, k2 = 2 * s - 3, 2 * s - 2
+            f1 = prev.view(-1, N, 1, D_DIM).expand(b, N, N, D_DIM)             # block1: the previous step's objects
+            f2 = v.view(-1, 1, N, D_DIM).expand(b, N, N, D_DIM)                # block2: v
+            g = []
+            for k in (k1, k2):
+                h = my_linear(q, sd["compress_q_%d.linear.weight" % k], sd["compress_q_%d.linear.bias" % k], 0.5, "relu",
+                              drop, L["compress_q_%d" % k])
+                g.append(my_linear(h, sd["expand_q_%d.linear.weight" % k], sd["expand_q_%d.linear.bias" % k], 0.5,
+                                   "sigmoid", drop, L["expand_q_%d" % k]))
+            cat = f1 * g[0].view(b, 1, 1, D_DIM) + f2 * g[1].view(b, 1, 1, D_DIM)
+            x = (alphas[-1][:, :, 0].contiguous().view(b, N, 1, 1) * cat).sum(1)
+            objects.append(x)
+        name = "compress_v" if s == 1 else "compress_v%d" % s
+        xl = my_conv1d(x, sd[name + ".conv.weight"], sd[name + ".conv.bias"], 0.5, "relu", drop, L[name])
+        att, alpha, _ = my_att(sd, "att%d" % s, x, mutan_fusion(sd, "fusion_vq%d" % s, xl, ql, 2), drop, L)
+        feats.append(att)
+        alphas.append(alpha)
+        prev = x
+    alpha_dict = {"alpha%d" % (s + 1): torch.split(a, 1, dim=2) for s, a in enumerate(alphas)}
+    alpha_dict["feature"] = objects[0][:, [0, 1], :]
+    for s, o in enumerate(objects[1:], start=3):
+        alpha_dict["v%d_feature" % s] = o[:, [0, 1], :]
+    q_final = my_linear(q, sd["linear_q.linear.weight"], sd["linear_q.linear.bias"], 0.5, "relu", drop, L["linear_q"])
+    xf = mutan_fusion(sd, "fusion_final", torch.cat(feats, dim=1), q_final, 2)
+    return my_linear(xf, sd["linear_classif.linear.weight"], sd["linear_classif.linear.bias"], 0.5, None, drop,
+                     L["linear_classif"]), alpha_dict
+
+
 def kld_loss(logits, target):
     """train.py:536-544: KLDivLoss(size_average=False)(log_softmax(x), a) = sum a*(log a - log p)."""
     return F.kl_div(F.log_softmax(logits, dim=1), target, reduction="sum")

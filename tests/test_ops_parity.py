@@ -102,3 +102,74 @@ def test_mutan_backward_fused_gradient_operands(cuda):
     grads = torch.autograd.grad(y, leaves, dy)
     for got, want in zip(grads, ref_grads):
         assert rel_err(got, want) < 1e-4
+
+
+def test_eval_tail_argmax_and_answer_mapping(cuda):
+    """ops.argmax_rows / engine.predict_answers against the reference's `output.data.cpu().max(1)` and its
+    MultipleChoice scan (train.py:146-169), ties included (first maximum wins on both sides)."""
+    from oracle import reasoning_core as rc
+    from vqa_playground_pytorch_b200 import ops
+    from vqa_playground_pytorch_b200.config import ODA
+    from vqa_playground_pytorch_b200.engine import predict_answers
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(37, 3000, device="cuda", generator=g)
+    x[5, 100] = x[5, 2000] = 9.0                      # a tie: index 100 wins
+    x[6] = 0.0                                        # all equal: index 0
+    pred, best = ops.argmax_rows(x, return_best=True)
+    want_v, want_i = x.cpu().max(1)
+    assert torch.equal(pred.cpu(), want_i) and torch.equal(best.cpu(), want_v)
+    mc = torch.randint(0, 3000, (37, 18), device="cuda", generator=g)
+    mc[:, 15:] = -1
+    mc[3] = -1                                        # no candidate at all
+    pm = ops.argmax_rows(x, mc).cpu()
+    xc, mcc = x.cpu(), mc.cpu()
+    for j in range(37):                               # the reference's scan (train.py:156-164)
+        cand = [e for e in mcc[j].tolist() if e != -1]
+        p, prob = -1, 0.0
+        for k in range(3000):
+            if k in cand and (p == -1 or prob < xc[j, k]):
+                p, prob = k, xc[j, k]
+        assert pm[j].item() == p, j
+
+    class Vocab:
+        def idx2word(self, i):
+            return "ans%d" % i
+    C = 50
+    m = ODA.Model(None, C)
+    m.load_state_dict(rc.synth_state_dict("ODA", C, seed=3))
+    m = m.cuda().train()
+    v, q, _ = (t.cuda() for t in rc.synth_inputs(6, 36, C, seed=1))
+    sample = {"v": v, "q_idxes": q, "q_id": torch.arange(100, 106)}
+    items = predict_answers(m, sample, Vocab())
+    assert m.training                                  # mode restored
+    m.eval()
+    with torch.no_grad():
+        ref = m(sample).cpu().max(1)[1]
+    assert items == [{"question_id": 100 + j, "answer": "ans%d" % int(ref[j])} for j in range(6)]
+
+
+def test_bf16_feature_shards_through_the_prefetcher(cuda):
+    """engine.pack_feature_shard + HostPrefetcher: features shipped as bf16 and widened on the device give exactly the
+    step the fp32 copies of the same (bf16-representable) values give — plain and widened into a graph's static buffers."""
+    from oracle import reasoning_core as rc
+    from vqa_playground_pytorch_b200 import ops
+    from vqa_playground_pytorch_b200.config import ODA
+    from vqa_playground_pytorch_b200.engine import GraphedStep, HostPrefetcher, pack_feature_shard
+    C = 40
+    m = ODA.Model(None, C)
+    m.load_state_dict(rc.synth_state_dict("ODA", C, seed=3))
+    m = m.cuda().eval()
+    batches = []
+    for i in range(3):
+        v, q, a = rc.synth_inputs(4, 36, C, seed=20 + i)
+        batches.append({"v": v.to(torch.bfloat16).float(), "q_idxes": q, "a": a})
+    shard = pack_feature_shard(batches)
+    assert shard[0]["v"].dtype == torch.bfloat16 and shard[0]["v"].is_pinned()
+    want = [ops.kld_loss(m({k: t.cuda() for k, t in b.items()}), b["a"].cuda()).item() for b in batches]
+    pf = HostPrefetcher(shard, "cuda:0")
+    got = [ops.kld_loss(m(s), s["a"]).item() for s in pf]
+    assert pf.bytes_per_batch == sum(t.numel() * t.element_size() for t in shard[0].values())
+    assert got == want
+    step = GraphedStep(m, {k: t.cuda() for k, t in batches[0].items()}, warmup=1)
+    got2 = [step(s).item() for s in HostPrefetcher(shard, "cuda:0", widen_into=step.static)]
+    assert all(abs(x - y) <= 1e-5 * abs(y) for x, y in zip(got2, want))

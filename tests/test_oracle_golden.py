@@ -58,3 +58,16 @@ def test_oracle_matches_live_reference(model, C, seed):
     _, m = ref_import.build_model(model, C)
     ref_keys = [(k, tuple(p.shape)) for k, p in m.state_dict().items() if not k.startswith("seq2vec")]
     assert ref_keys == rc.param_shapes(model, C)
+
+
+def test_n_step_chain_oracle_reduces_to_the_pinned_two_step_model():
+    """oracle.cor_forward (the reference's blocks composed for any number of steps; UNPINNED beyond two) with steps = 2
+    is the pinned cor2_forward, bit for bit, in eval and in train mode."""
+    sd = rc.synth_state_dict("CoR2", 120, seed=2)
+    v, q, _ = rc.synth_inputs(3, 36, 120, seed=8)
+    for drop in (rc.no_drop, rc.PhiloxDrop(17)):
+        y2, a2 = rc.cor_forward(sd, v, q, drop, 36, 2)
+        y, a = rc.cor2_forward(sd, v, q, drop, 36)
+        assert torch.equal(y2, y) and set(a2) == set(a)
+        assert all(torch.equal(x, z) for x, z in zip(a2["alpha2"], a["alpha2"])) and torch.equal(a2["feature"], a["feature"])
+    assert rc.cor_layers(2) == rc.COR2_LAYERS

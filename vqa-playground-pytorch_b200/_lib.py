@@ -175,6 +175,8 @@ SYMBOLS = {
     "vqa_cor_compound_fwd": _OP(CompoundFwd), "vqa_cor_compound_bwd": _OP(CompoundBwd),
     "vqa_oda_pair_attn_fwd": _OP(OdaFwd), "vqa_oda_pair_attn_bwd": _OP(OdaBwd),
     "vqa_kld_logsoftmax_fwd_bwd": _OP(KldParams),
+    "vqa_cast_bf16_f32": (C.c_int, [i64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vqa_argmax_rows": (C.c_int, [i64, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vqa_sum_rows": (C.c_int, [i64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vqa_scale_by_device_scalar": (C.c_int, [i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vqa_cor2_workspace_bytes": (C.c_size_t, [i64, i64, i64]),

@@ -29,10 +29,14 @@ class _DropSite:
     counter word, assigned by the owning Model in forward-call order (include/vqacore.h)."""
     layer_id = 0
     math = "fp32"
+    fixed_seed = None          # tests: pin the Philox key of this site (CoreModel.fixed_seed sets it on every site)
 
     def _drop_args(self):
         p = float(self.p) if (self.p and self.training) else 0.0
-        return p, (ops.next_seed() if p > 0.0 else 0), self.layer_id
+        seed = 0
+        if p > 0.0:
+            seed = self.fixed_seed if self.fixed_seed is not None else ops.next_seed()
+        return p, seed, self.layer_id
 
 
 class MyConv1d(nn.Module, _DropSite):
@@ -133,12 +137,17 @@ class MyATT(nn.Module):
             [MyLinear(inputs_dim, int(att_dim / glimpses), p=0.5, af=af) for _ in range(glimpses)])
         self.af = af
 
-    def forward(self, inputs, fuse):
+    def forward_with_pooled(self, inputs, fuse):
+        """(x_v [B, att_dim], x_att [B,N,G], pooled [B,G,D]); `pooled` (the reference's `tmp`, config/CoR2.py:146) is what
+        a following compound-object step needs (its glimpse 0 is sum_i alpha_i x_i)."""
         ca = self.conv_att
         p, seed, layer = ca._drop_args()
         pooled, x_att = ops.RegionSoftmaxPoolFn.apply(inputs, fuse, ca.conv.weight, ca.conv.bias, p, seed, layer)
         list_v = [self.list_linear_v_fusion[g](pooled[:, g, :]) for g in range(self.glimpses)]
-        x_v = torch.cat(list_v, 1)
+        return torch.cat(list_v, 1), x_att, pooled
+
+    def forward(self, inputs, fuse):
+        x_v, x_att, _ = self.forward_with_pooled(inputs, fuse)
         return x_v, torch.split(x_att, 1, dim=2)
 
 

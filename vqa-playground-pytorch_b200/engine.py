@@ -33,16 +33,63 @@ def train_step(model, sample, optimizer=None, scheduler=None, engine=None, clip_
     return output, loss
 
 
+@torch.no_grad()
+def predict_answers(model, sample, a_vocab=None, eval_metric="OpenEnded"):
+    """The body of the reference's eval loop for one batch (train.py:125-169): forward in eval mode, answer index per
+    question on the GPU (ops.argmax_rows; MultipleChoice restricts it to sample['a_mc_idx'], train.py:153-164), ONE
+    device->host copy of the B indices, then the id -> answer mapping.  Returns the list of
+    {'question_id', 'answer'} items train.py:166-169 appends (answer = the index when no a_vocab is given), ready for
+    official_test.test_local."""
+    if eval_metric not in ("OpenEnded", "MultipleChoice"):
+        raise ValueError("<train.py> %s is not allowed" % eval_metric)
+    was_training = model.training
+    model.eval()
+    try:
+        output = model(sample)
+    finally:
+        model.train(was_training)
+    mc = sample.get("a_mc_idx") if eval_metric == "MultipleChoice" else None
+    pred = ops.argmax_rows(output, mc).cpu().tolist()
+    q_id = sample.get("q_id")
+    q_ids = q_id.cpu().tolist() if torch.is_tensor(q_id) else (list(q_id) if q_id is not None else list(range(len(pred))))
+    word = a_vocab.idx2word if a_vocab is not None else (lambda i: i)
+    return [{"question_id": q_ids[j], "answer": word(int(pred[j]))} for j in range(len(pred))]
+
+
+def pack_feature_shard(samples, keys=("v", "q_idxes", "a"), feature_key="v"):
+    """Pre-packed input shard: the reference builds every sample in Python from h5py / redis
+    (datasets.py:517-549, :905-970: `torch.Tensor(feature[idx])` per item, fp32) and copies it with a synchronous
+    `.cuda()`.  Here a list of batches (dicts of CPU tensors) becomes PINNED host memory once, with the region
+    features stored as bf16 — half the bytes over PCIe, widened exactly on the device (ops.cast_bf16_to_f32).
+    A feature store that keeps bf16 on disk loses nothing: the model then sees exactly the stored values."""
+    out = []
+    for smp in samples:
+        d = {}
+        for k in keys:
+            t = smp[k]
+            if k == feature_key and t.dtype == torch.float32:
+                t = t.to(torch.bfloat16)
+            d[k] = t.contiguous().pin_memory()
+        out.append(d)
+    return out
+
+
 class HostPrefetcher:
     """Iterates over host batches (dicts of PINNED tensors) yielding device dicts; the copy of batch i+1 runs
-    on a side stream while batch i is being computed.  Two device staging slots, reused."""
+    on a side stream while batch i is being computed.  Two device staging slots, reused.  bf16 host tensors
+    (pack_feature_shard) are copied as bf16 and widened to fp32 on the device, on the copy stream as well."""
 
-    def __init__(self, host_batches, device, keys=("v", "q_idxes", "a")):
+    def __init__(self, host_batches, device, keys=("v", "q_idxes", "a"), widen_into=None):
+        """widen_into: dict of preallocated fp32 device tensors (e.g. GraphedStep.static): bf16 features are widened
+        straight into them on the consumer's stream when the batch is handed out, instead of into a staging copy that
+        the consumer would have to copy again."""
         self.batches = host_batches
         self.device = torch.device(device)
         self.keys = keys
+        self.widen_into = widen_into
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slots = [None, None]
+        self.stage = [None, None]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
         self.bytes_per_batch = 0
@@ -52,10 +99,18 @@ class HostPrefetcher:
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.consumed[slot])        # previous user of the slot has finished
             if self.slots[slot] is None:
-                self.slots[slot] = {k: torch.empty_like(host[k], device=self.device) for k in self.keys}
+                self.slots[slot] = {k: torch.empty(host[k].shape, device=self.device, dtype=torch.float32 if
+                                                   host[k].dtype == torch.bfloat16 else host[k].dtype) for k in self.keys}
+                self.stage[slot] = {k: torch.empty_like(host[k], device=self.device) for k in self.keys
+                                    if host[k].dtype == torch.bfloat16}
             nbytes = 0
             for k in self.keys:
-                self.slots[slot][k].copy_(host[k], non_blocking=True)
+                if host[k].dtype == torch.bfloat16:
+                    self.stage[slot][k].copy_(host[k], non_blocking=True)
+                    if self.widen_into is None or k not in self.widen_into:
+                        ops.cast_bf16_to_f32(self.stage[slot][k], out=self.slots[slot][k])
+                else:
+                    self.slots[slot][k].copy_(host[k], non_blocking=True)
                 nbytes += host[k].numel() * host[k].element_size()
             self.bytes_per_batch = nbytes
             self.ready[slot].record(self.copy_stream)
@@ -73,7 +128,13 @@ class HostPrefetcher:
             if i + 1 < n:
                 self._issue(i + 1, slot ^ 1)
             cur.wait_event(self.ready[slot])
-            yield self.slots[slot]
+            out = self.slots[slot]
+            if self.widen_into is not None and self.stage[slot]:
+                out = dict(out)
+                for k, st in self.stage[slot].items():
+                    if k in self.widen_into:
+                        out[k] = ops.cast_bf16_to_f32(st, out=self.widen_into[k])
+            yield out
             self.consumed[slot].record(cur)
 
 

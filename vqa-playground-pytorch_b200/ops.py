@@ -462,6 +462,36 @@ def kld_loss(logits, target):
     return KldLossFn.apply(logits, target)
 
 
+def cast_bf16_to_f32(src, out=None):
+    """fp32 copy of a bf16 CUDA tensor on the current stream (vqa_cast_bf16_f32; exact)."""
+    if not (isinstance(src, torch.Tensor) and src.is_cuda and src.dtype == torch.bfloat16):
+        raise ValueError("cast_bf16_to_f32: expected a bfloat16 CUDA tensor")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    _lib.check(_lib.lib().vqa_cast_bf16_f32(src.numel(), src.data_ptr(), out.data_ptr(), _stream()), "vqa_cast_bf16_f32")
+    return out
+
+
+def argmax_rows(logits, mc_idx=None, return_best=False):
+    """pred[b] = first argmax of logits[b, :] (or of the candidate columns mc_idx[b, :], -1 = padding) on the GPU
+    (vqa_argmax_rows) — the `output.data.cpu().max(1)` of the reference's eval loop (train.py:146-164) without moving
+    the [B, num_ans] logits to the host."""
+    x = _chk(logits.detach(), "logits", 2)
+    B, Cc = x.shape
+    pred = torch.empty((B,), device=x.device, dtype=torch.int64)
+    best = torch.empty((B,), device=x.device, dtype=torch.float32) if return_best else None
+    mc, n_mc = None, 0
+    if mc_idx is not None:
+        mc = mc_idx.to(device=x.device, dtype=torch.int64).contiguous()
+        if mc.dim() != 2 or mc.shape[0] != B:
+            raise ValueError("a_mc_idx must be [B, n_candidates]")
+        n_mc = mc.shape[1]
+    _lib.check(_lib.lib().vqa_argmax_rows(B, Cc, x.data_ptr(), _p(mc), n_mc, pred.data_ptr(), _p(best), _stream()),
+               "vqa_argmax_rows")
+    return (pred, best) if return_best else pred
+
+
 # =========================================================================== whole-model plans
 _MODEL = {
     "CoR2": ("vqa_cor2_workspace_bytes", "vqa_cor2_fwd", "vqa_cor2_bwd"),

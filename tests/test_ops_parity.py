@@ -170,6 +170,9 @@ def test_bf16_feature_shards_through_the_prefetcher(cuda):
     got = [ops.kld_loss(m(s), s["a"]).item() for s in pf]
     assert pf.bytes_per_batch == sum(t.numel() * t.element_size() for t in shard[0].values())
     assert got == want
+    m = ODA.Model(None, C)                  # a fresh model: autograd caches per-parameter streams at first use
+    m.load_state_dict(rc.synth_state_dict("ODA", C, seed=3))
+    m = m.cuda().eval()
     step = GraphedStep(m, {k: t.cuda() for k, t in batches[0].items()}, warmup=1)
     got2 = [step(s).item() for s in HostPrefetcher(shard, "cuda:0", widen_into=step.static)]
     assert all(abs(x - y) <= 1e-5 * abs(y) for x, y in zip(got2, want))

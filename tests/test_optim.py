@@ -117,8 +117,11 @@ def test_optimizer_state_dict_round_trip_and_torch_layout(cuda):
     o2.load_state_dict(sd_opt)
     assert o2.step_count == 2 and o2.param_groups[0]["lr"] == 1e-3
     run(m2, o2, batches[2], 3)
-    for p, r in zip(m2.core_parameters(), m1.core_parameters()):      # same state, same gradients up to atomic ordering
-        assert (p.detach() - r.detach()).abs().max().item() <= 1e-3 * 1e-3          # << one update (lr = 1e-3)
+    # same state, same gradients up to the ordering of atomic additions; Adam turns gradient noise into a fraction of lr
+    for (n, p), r in zip(m2.named_parameters(), m1.core_parameters()):
+        if n.endswith("conv_att.conv.bias"):          # analytically zero gradient: its update is sign(noise) * lr
+            continue
+        assert (p.detach() - r.detach()).abs().max().item() <= 0.05 * 1e-3, n          # << one update (lr = 1e-3)
     # torch.optim.Adam accepts the same dict, and its own state_dict loads here
     twins = [p.detach().clone().requires_grad_() for p in m2.core_parameters()]
     stock = torch.optim.Adam(twins, lr=1e-3)
@@ -139,7 +142,7 @@ def test_graph_captured_optimizer_step_matches_the_reference_order(cuda):
     from vqa_playground_pytorch_b200 import ops
     from vqa_playground_pytorch_b200.engine import GraphedStep
     from vqa_playground_pytorch_b200.optim import FusedClipAdam
-    gamma = 0.5 ** (1 / 50.0)                                # a fast decay makes an ordering mistake visible
+    gamma = 0.5 ** (1 / 5.0)                                 # a fast decay makes an ordering mistake visible
     g = torch.Generator(device="cuda").manual_seed(4)
     batches = [_batch(g, 4, 50) for _ in range(4)]
     m1, s1 = _small_oda()
@@ -166,9 +169,11 @@ def test_graph_captured_optimizer_step_matches_the_reference_order(cuda):
         torch.nn.utils.clip_grad_norm_(m2.core_parameters(), 0.25)
         ref.step()
     # The two sides compute their gradients separately (atomic ordering differs at the 1e-7 level) and Adam turns
-    # noise-level gradients into O(lr) updates, so the bound is in units of lr: 0.2 % of the four updates.  Stepping the
-    # scheduler AFTER the optimizer instead would change every update by 1 - gamma = 1.4 %, seven times the bound.
-    for p, r in zip(m1.core_parameters(), m2.core_parameters()):
-        assert (p.detach() - r.detach()).abs().max().item() <= 0.002 * 1e-3 * 4
+    # noise-level gradients into a fraction of lr, so the bound is in units of lr: 5 % of one update.  Stepping the
+    # scheduler AFTER the optimizer instead would change every update by 1 - gamma = 13 % (0.4 lr over the four steps).
+    for (n, p), r in zip(m1.named_parameters(), m2.core_parameters()):
+        if n.endswith("conv_att.conv.bias"):          # analytically zero gradient: its update is sign(noise) * lr
+            continue
+        assert (p.detach() - r.detach()).abs().max().item() <= 0.05 * 1e-3, n
     fresh = FusedClipAdam(s1, lr=1e-3, clip_grad=0.25, device_clock=True, lr_gamma=gamma)     # epoch reset
     assert fresh.steps_done() == 0 and fresh.lr_dev.item() == 1e-3 and not fresh.exp_avg.any()

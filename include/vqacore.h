@@ -361,8 +361,12 @@ int vqa_cor_compound_bwd(const vqa_cor_compound_bwd_params* p, void* stream);
  *   z[b,i,g] = bc[g] + sum_{j,k} W[g,j*H+k] * dropout(vq)[b,i,j*H+k],  vq = (vl[b,i,k]-vl[b,j,k])*ql[b,k]
  * The [B,N,N*H] tensor is never formed.  train = 0: factorised form
  * (z = sum_k ql*vl[i]*Wsum[k] + const_i, Wsum = sum_j W[g,j,:]); train = 1: every (i,j,k) term is
- * produced in registers with its Philox mask (index ((b*N+i)*N+j)*H+k).
+ * produced in registers with its keep flag (Philox index ((b*N+i)*N+j)*H+k).  Train mode needs a scratch buffer of
+ * vqa_oda_pair_attn_workspace_bytes(B,N,H): the 1-bit-per-element keep cache of the dropped tensor
+ * (vqa_dropout_bits layout, drawn ONCE per step) followed by the forward's partial logits.  The forward fills it,
+ * the backward reads the keep bits back: pass the SAME buffer to both calls.
  */
+size_t vqa_oda_pair_attn_workspace_bytes(int64_t B, int64_t N, int64_t H);
 typedef struct {
   int64_t B, N, H, D;
   int train;
@@ -375,6 +379,10 @@ typedef struct {
   float* wsum;           /* workspace [G,H] (eval) */
   float* alpha;          /* [B,N,G] */
   float* pooled;         /* [B,G,D] */
+  void* workspace;       /* train: vqa_oda_pair_attn_workspace_bytes(B,N,H) bytes, 256-byte aligned */
+  size_t workspace_bytes;
+  int keep_bits_ready;   /* nonzero: the keep bits at the head of the workspace are already drawn (a whole-model plan
+                            makes them in its batched vqa_dropout_bits_batch launch); zero: this call draws them */
 } vqa_oda_pair_attn_fwd_params;
 int vqa_oda_pair_attn_fwd(const vqa_oda_pair_attn_fwd_params* p, void* stream);
 
@@ -393,6 +401,8 @@ typedef struct {
   float* dW; float* dbc;
   float* dvl;                 /* [B,N,H] */
   float* dql;                 /* [B,H] */
+  const void* workspace;      /* train: the buffer the forward filled */
+  size_t workspace_bytes;
 } vqa_oda_pair_attn_bwd_params;
 int vqa_oda_pair_attn_bwd(const vqa_oda_pair_attn_bwd_params* p, void* stream);
 

@@ -113,14 +113,15 @@ class CompoundBwd(C.Structure):
 
 class OdaFwd(C.Structure):
     _fields_ = [("B", i64), ("N", i64), ("H", i64), ("D", i64), ("train", C.c_int), ("drop", Dropout),
-                ("vl", fp), ("ql", fp), ("W", fp), ("bc", fp), ("x", fp), ("wsum", fp), ("alpha", fp), ("pooled", fp)]
+                ("vl", fp), ("ql", fp), ("W", fp), ("bc", fp), ("x", fp), ("wsum", fp), ("alpha", fp), ("pooled", fp),
+                ("workspace", fp), ("workspace_bytes", C.c_size_t), ("keep_bits_ready", C.c_int)]
 
 
 class OdaBwd(C.Structure):
     _fields_ = [("B", i64), ("N", i64), ("H", i64), ("D", i64), ("train", C.c_int), ("drop", Dropout),
                 ("accumulate_w", C.c_int), ("vl", fp), ("ql", fp), ("W", fp), ("x", fp), ("alpha", fp), ("wsum", fp),
                 ("dpooled", fp), ("dalpha", fp), ("dz", fp), ("dwsum", fp), ("dW", fp), ("dbc", fp), ("dvl", fp),
-                ("dql", fp)]
+                ("dql", fp), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
 
 
 class KldParams(C.Structure):
@@ -182,6 +183,7 @@ SYMBOLS = {
     "vqa_cor2_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "vqa_cor2_fwd": _OP(ModelFwd), "vqa_cor2_bwd": _OP(ModelBwd),
     "vqa_oda_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
+    "vqa_oda_pair_attn_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "vqa_oda_fwd": _OP(ModelFwd), "vqa_oda_bwd": _OP(ModelBwd),
     "vqa_stash_info": (C.c_int, [C.c_int, C.c_char_p, i64, i64, i64, C.POINTER(C.c_size_t), C.POINTER(i64),
                                  C.POINTER(i64), C.POINTER(i64)]),

@@ -161,6 +161,7 @@ struct OdaWs {
   int64_t bits_n[32];
   float *ff_w1p, *ff_w2p, *clsp;
   __nv_bfloat16 *vp, *cv_wp;                           // bf16 modes: planes of dropout(v) and of compress_v's weight
+  void* pair_ws; size_t pair_ws_bytes;                 // pairwise attention scratch: keep bits of the [B,N,N*H] site + partial logits
   size_t bytes;
 };
 
@@ -183,6 +184,10 @@ static OdaWs carve_oda(void* base, int64_t B, int64_t N, int64_t C) {
     for (int g = 0; g < G; ++g) w.bits_n[L_ATT_G + g] = B * D;
     for (int i = 0; i < 32; ++i)
       if (w.bits_n[i]) w.bits[i] = reinterpret_cast<uint8_t*>(c.take(w.bits_n[i] / 32 + 16));
+    // the pairwise site's keep bits sit at the head of the pair kernels' own scratch (vqa_oda_pair_attn_workspace_bytes)
+    w.pair_ws_bytes = vqa_oda_pair_attn_workspace_bytes(B, N, H);
+    w.pair_ws = c.take((int64_t)(w.pair_ws_bytes / sizeof(float)) + 64);
+    w.bits_n[L_ATT_CONV] = M * N * H; w.bits[L_ATT_CONV] = reinterpret_cast<uint8_t*>(w.pair_ws);
   }
   w.ff_w1p = c.take(5 * FPAD * A); w.ff_w2p = c.take(5 * FPAD * 312); w.clsp = c.take(C * 512);
   w.vp = reinterpret_cast<__nv_bfloat16*>(c.take(M * D)); w.cv_wp = reinterpret_cast<__nv_bfloat16*>(c.take(HP * D));
@@ -749,6 +754,7 @@ extern "C" int vqa_oda_fwd(const vqa_model_fwd_params* p, void* stream) {
     ap.drop.p = c.pdrop(); ap.drop.layer = L_ATT_CONV; ap.drop.seed = p->seed; ap.drop.seed_dev = p->seed_dev;
     ap.vl = w.vl; ap.ql = w.ql; ap.W = c.W[ATT_CONV]; ap.bc = c.W[ATT_CONV + 1]; ap.x = p->v; ap.wsum = w.wsum;
     ap.alpha = p->alpha1; ap.pooled = w.pooled;
+    ap.workspace = w.pair_ws; ap.workspace_bytes = w.pair_ws_bytes; ap.keep_bits_ready = 1;   // drawn by make_bits above
     { ProfScope ps_(stream, "oda_pair_attn.fwd"); VQA_TRY(vqa_oda_pair_attn_fwd(&ap, stream)); }
   }
   { ProfScope ps_(stream, "att.glimpse.fwd"); VQA_TRY(glimpse_fwd(c, B, w.pooled, ATT_G, w.vf, A, 0, L_ATT_G)); }
@@ -798,6 +804,7 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
     ap.vl = w.vl; ap.ql = w.ql; ap.W = c.W[ATT_CONV]; ap.x = p->v; ap.alpha = p->alpha1; ap.wsum = w.wsum;
     ap.dpooled = w.dpooled; ap.dalpha = w.dalpha; ap.dz = w.dz; ap.dwsum = w.dwsum;
     ap.dW = c.grad(ATT_CONV); ap.dbc = c.grad(ATT_CONV + 1); ap.dvl = w.dvl; ap.dql = w.dql;
+    ap.workspace = w.pair_ws; ap.workspace_bytes = w.pair_ws_bytes;
     { ProfScope ps_(stream, "oda_pair_attn.bwd"); VQA_TRY(vqa_oda_pair_attn_bwd(&ap, stream)); }
   }
   mark(3);

@@ -30,119 +30,210 @@ __global__ void oda_dw_broadcast_kernel(int64_t N, int64_t H, const float* __res
 }
 
 // ---- train mode ------------------------------------------------------------------------------
-// The [B,N,N*H] tensor of the reference (config/ODA.py:222) is indexed by (b, i, e) with e = j*H + k.
-// z[b,i,g] = bc[g] + scale * sum_e keep(b,i,e) W[g,e] (vl[b,i,k]-vl[b,j,k]) ql[b,k].
-//
-// "e-mapping" kernels: a thread owns EPT = 8 consecutive e of one sample — their W[g,e], vl[b,j,k], ql[b,k] stay
-// in registers — and loops over all regions i, drawing the 8 keep-bytes of (b,i,e..e+7) with one Philox call
-// (N*H is a multiple of 8, so the 8 elements never straddle a 16-element Philox group).  W is read once per
-// (sample, e) instead of once per (sample, i, e): 100x less L2 traffic at N = 100.
-constexpr int ODA_EPT = 8;
-constexpr int ODA_THREADS = 256;
+// The [B,N,N*H] tensor of the reference (config/ODA.py:222) is indexed by (b, i, e) with e = j*H + k:
+//   z[b,i,g] = bc[g] + scale * sum_e keep(b,i,e) W[g,e] ql[b,k] (vl[b,i,k] - vl[b,j,k]).
+// Every kernel below is bound by the instruction issue rate (4 FMAs per element for the G = 4 glimpses, nothing to
+// stream: one sample is N*H floats), so the design minimises instructions per (b,i,j,k) element:
+//  * the keep flags come from the step's 1-bit-per-element cache (vqa_dropout_bits layout: bit n of the stream =
+//    element n), made by ONE Philox pass per step — the forward and the backward both read it instead of drawing
+//    the 16-byte Philox groups again, which were two thirds of the old kernels' instructions;
+//  * "e-mapping": a thread owns a chunk of CW consecutive k of one region j — W[g,e], vl[b,j,k] stay in registers —
+//    and walks over the regions i, whose rows vl[b,i,:] are staged once per CTA in shared memory (one 128-bit
+//    broadcast read per 4 elements);
+//  * a CTA owns ALL regions j of a k-range, so the sum over j that dvl[b,i,k] needs completes inside the CTA through a
+//    double-buffered shared-memory tile (one barrier per row) — the old second backward kernel, which regenerated
+//    every mask and re-read W from shared memory four times per element, is gone.
+constexpr int PAIR_MAX_THREADS = 512;
+constexpr int PF_CW = 16;          // forward: elements per thread and row
+constexpr int PF_RB = 8;           // forward: rows per cross-lane reduction batch (PF_RB * G = 32 values = one per lane)
+constexpr int PB_CW = 8;           // backward: elements per thread and row (twice the per-element state of the forward)
 
-// v[e] = row[kk[e]], e < 8.  kk holds consecutive feature indices unless the chunk wraps into the next region (or runs
-// past the end); consecutive and 8-byte aligned (even start, even row length) -> four 8-byte loads instead of eight
-// 4-byte ones: lanes sit 32 bytes apart, so every load instruction costs 8 L1 wavefronts whatever its width.
-__device__ __forceinline__ void load_row8(const float* __restrict__ row, const int (&kk)[8], bool contiguous,
-                                          float (&v)[8]) {
-  if (contiguous) {
-    const float2* p = reinterpret_cast<const float2*>(row + kk[0]);
+struct PairGeom { int CC, P, threads; };
+// chunk ranges: CC chunks of CW features per CTA, P CTAs per sample, CC * N threads (rounded up to a warp)
+static PairGeom pair_geom(int64_t N, int64_t H, int CW) {
+  const int NC = (int)cdiv(H, CW);
+  int CC = (int)(PAIR_MAX_THREADS / N);
+  if (CC < 1) CC = 1;
+  if (CC > NC) CC = NC;
+  const int P = (NC + CC - 1) / CC;
+  CC = (NC + P - 1) / P;
+  return PairGeom{CC, P, (int)(((int64_t)CC * N + 31) / 32 * 32)};
+}
+
+// ---- keep-bit windows through a thread-private cp.async ring -----------------------------------------
+// A thread needs, for every region row i, the <= 32 keep bits that start at bit n0(i) = bit0 + i*N*H of the stream: two
+// consecutive 32-bit words (the cache keeps one spare word past its end).  The words are fetched RD - 1 rows ahead
+// with cp.async into a shared-memory ring slot that only this thread reads (no barrier, no registers held while the
+// load is in flight) — waiting on the global load at its use was 40 % of the first version's stall samples.
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+template <int RD>
+struct KeepRing {
+  uint2* slot;                    // this thread's slot of ring row 0; rows are `stride` uint2 apart
+  int stride;
+  const uint32_t* words;
+  uint64_t n_issue, n_use;        // bit position of the next row to fetch / to hand out
+  uint32_t row_bits_lo;           // row length (bits) mod 2^32: enough for the 5-bit shift
+  uint64_t row_bits;
+  int issued, used;
+  __device__ __forceinline__ KeepRing(uint2* slot_, int stride_, const uint32_t* words_, uint64_t bit0, uint64_t row_bits_)
+      : slot(slot_), stride(stride_), words(words_), n_issue(bit0), n_use(bit0), row_bits_lo((uint32_t)row_bits_),
+        row_bits(row_bits_), issued(0), used(0) {}
+  __device__ __forceinline__ void issue() {
+    uint32_t* d = reinterpret_cast<uint32_t*>(slot + (issued & (RD - 1)) * stride);
+    cp_async4(d, words + (n_issue >> 5));
+    cp_async4(d + 1, words + (n_issue >> 5) + 1);
+    n_issue += row_bits;
+    ++issued;
+  }
+  // call once per row, in order: prefetches row i + RD - 1 and returns the window of row i
+  __device__ __forceinline__ uint32_t next(int nrows) {
+    if (issued < nrows) issue();
+    cp_async_commit();
+    cp_async_wait<RD - 1>();
+    const uint2 wv = slot[(used & (RD - 1)) * stride];
+    const uint32_t kb = __funnelshift_r(wv.x, wv.y, (uint32_t)n_use & 31u);
+    n_use += row_bits;
+    ++used;
+    return kb;
+  }
+  __device__ __forceinline__ void prime(int nrows) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 t = __ldg(p + e);
-      v[2 * e] = t.x; v[2 * e + 1] = t.y;
+    for (int r = 0; r < RD - 1; ++r) {
+      if (r < nrows) issue();
+      cp_async_commit();
     }
-  } else {
+  }
+};
+
+// v[0] of lane l <- sum over the 32 lanes of v[l] (butterfly that halves the live values at every step: 31 shuffles)
+__device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = __ldg(row + kk[e]);
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int x = 0; x < s; ++x) {
+      const float send = up ? v[x] : v[x + s];
+      const float keep = up ? v[x + s] : v[x];
+      v[x] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
   }
 }
 
-// keep flags (1.0 / 0.0) of 8 consecutive indices starting at idx.  Fast path idx % 8 == 0: one Philox call.
-__device__ __forceinline__ void keep8(const Drop& d, uint64_t seed, uint64_t idx, float (&keep)[8]) {
-  const uint4 r = philox_group(seed, d.layer, idx >> 4);
-  if ((idx & 7) == 0) {
-    const uint32_t lo = (idx & 8) ? r.z : r.x, hi = (idx & 8) ? r.w : r.y;
+// vl[b, :, kbase .. kbase+KT) -> Vs [N][KT] (zero past H), several loads in flight per thread
+__device__ __forceinline__ void stage_rows(float* Vs, const float* __restrict__ vb, int N, int H, int KT, int kbase) {
+  const int total = N * KT;
+  for (int x0 = threadIdx.x; x0 < total; x0 += 4 * blockDim.x) {
+    float v[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      keep[e] = ((lo >> (8 * e)) & 0xFFu) >= d.thr ? 1.0f : 0.0f;
-      keep[4 + e] = ((hi >> (8 * e)) & 0xFFu) >= d.thr ? 1.0f : 0.0f;
+    for (int u = 0; u < 4; ++u) {
+      const int x = x0 + u * blockDim.x;
+      const int i = x / KT, k = kbase + (x - i * KT);
+      v[u] = (x < total && k < H) ? __ldg(vb + (int64_t)i * H + k) : 0.0f;
     }
-    return;
-  }
-  const uint4 r1 = philox_group(seed, d.layer, (idx >> 4) + 1);     // unaligned rows (N*H not a multiple of 8)
-  const uint32_t wd[8] = {r.x, r.y, r.z, r.w, r1.x, r1.y, r1.z, r1.w};
-  const uint32_t off = (uint32_t)idx & 15u;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const uint32_t pos = off + e;
-    keep[e] = ((wd[pos >> 2] >> (8u * (pos & 3u))) & 0xFFu) >= d.thr ? 1.0f : 0.0f;
+    for (int u = 0; u < 4; ++u) {
+      const int x = x0 + u * blockDim.x;
+      if (x < total) Vs[x] = v[u];
+    }
   }
 }
 
-// grid = (cdiv(NH/8, 256), B).  z must hold bc[g] on entry (oda_init_logits_kernel); partial sums are added.
-__global__ void __launch_bounds__(ODA_THREADS)
-oda_pair_logits_train_kernel(int64_t N, int64_t H, Drop d, const float* __restrict__ vl, const float* __restrict__ ql,
-                             const float* __restrict__ W, float* __restrict__ z) {
-  extern __shared__ float part[];                       // [warps][N][G]
-  const int64_t b = blockIdx.y;
-  const int64_t NH = N * H;
-  const int64_t e0 = ((int64_t)blockIdx.x * ODA_THREADS + threadIdx.x) * ODA_EPT;
-  const bool active = e0 < NH;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint64_t seed = d.key();
-  const float* vb = vl + b * NH;
-  float w[G][ODA_EPT], vj[ODA_EPT], qk[ODA_EPT];
-  int kk[ODA_EPT];
-  if (active) {
-    int64_t j = e0 / H, k = e0 - j * H;
+// Forward.  grid = (P, B), threads = CC * N rounded up; thread t = (chunk cl = t / N, region j = t % N).
+// zpart[b][p][i][g] = this CTA's share of the logit (k-range p); oda_softmax_partials_kernel adds the shares in a
+// fixed order (deterministic) with the bias and normalises.
+// dynamic smem: Vs [N][KT] (KT = CC * PF_CW) | zred [warps][cdiv(N, 8)][32] | keep ring [PF_RD][threads] uint2
+constexpr int PF_RD = 8;
+__global__ void __launch_bounds__(PAIR_MAX_THREADS)
+oda_pair_fwd_train_kernel(int N, int H, int CC, float scale, const uint32_t* __restrict__ bits,
+                          const float* __restrict__ vl, const float* __restrict__ ql, const float* __restrict__ W,
+                          float* __restrict__ zpart) {
+  extern __shared__ __align__(16) float pair_smem[];
+  const int KT = CC * PF_CW;
+  const int NB = (N + PF_RB - 1) / PF_RB;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+  float* Vs = pair_smem;
+  float* zred = pair_smem + (size_t)N * KT;
+  uint2* ring = reinterpret_cast<uint2*>(zred + (size_t)nwarps * NB * 32);
+  const int b = blockIdx.y, P = gridDim.x;
+  const int64_t NH = (int64_t)N * H;
+  const int kbase = blockIdx.x * KT;
+  const float* vb = vl + (int64_t)b * NH;
+  const int cl = t / N, j = t - cl * N;
+  const int k0 = kbase + cl * PF_CW;
+  const bool active = cl < CC && k0 < H;
+  // idle threads read (and ignore: their weights are zero) the bits and rows of chunk 0 / region 0
+  KeepRing<PF_RD> keep(ring + t, (int)blockDim.x, bits, (uint64_t)b * N * NH + (active ? (uint64_t)j * H + k0 : 0),
+                       (uint64_t)NH);
+  keep.prime(N);
+  stage_rows(Vs, vb, N, H, KT, kbase);
+  float wq[G][PF_CW], vj[PF_CW];
 #pragma unroll
-    for (int e = 0; e < ODA_EPT; ++e) {
-      const bool in = e0 + e < NH;                      // ragged tail when N*H is not a multiple of 8
-      kk[e] = in ? (int)k : 0;
-      vj[e] = in ? vb[j * H + k] : 0.0f;
-      qk[e] = in ? ql[b * H + k] * d.scale : 0.0f;
+  for (int e = 0; e < PF_CW; ++e) {
+    const int k = k0 + e;
+    const bool in = active && k < H;
+    const float q = in ? __ldg(ql + (int64_t)b * H + k) * scale : 0.0f;
+    vj[e] = in ? __ldg(vb + (int64_t)j * H + k) : 0.0f;
 #pragma unroll
-      for (int g = 0; g < G; ++g) w[g][e] = in ? W[g * NH + e0 + e] : 0.0f;
-      if (++k == H) { k = 0; ++j; }
-    }
-  }
-  // the 8 features are consecutive in every row (no wrap, no ragged tail) and 8-byte aligned there
-  const bool contig = active && e0 + ODA_EPT <= NH && kk[ODA_EPT - 1] == kk[0] + ODA_EPT - 1 && (kk[0] & 1) == 0 &&
-                      (H & 1) == 0 && (reinterpret_cast<uintptr_t>(vl) & 7) == 0;
-  for (int64_t i = 0; i < N; ++i) {
-    float acc[G] = {0.f, 0.f, 0.f, 0.f};
-    if (active) {
-      float keep[ODA_EPT], vi8[ODA_EPT];
-      keep8(d, seed, d.base + (uint64_t)((b * N + i) * NH + e0), keep);
-      load_row8(vb + i * H, kk, contig, vi8);
-#pragma unroll
-      for (int e = 0; e < ODA_EPT; ++e) {          // branch-free: a 50 % mask would diverge on every element
-        const float delta = (vi8[e] - vj[e]) * (qk[e] * keep[e]);
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] = fmaf(w[g][e], delta, acc[g]);
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g) acc[g] = warp_sum(acc[g]);
-    if (lane == 0) {
-#pragma unroll
-      for (int g = 0; g < G; ++g) part[(warp * N + i) * G + g] = acc[g];
-    }
+    for (int g = 0; g < G; ++g) wq[g][e] = in ? __ldg(W + g * NH + (int64_t)j * H + k) * q : 0.0f;
   }
   __syncthreads();
-  for (int64_t t = threadIdx.x; t < N * G; t += ODA_THREADS) {
-    float s = 0.0f;
+  const float* vrow = Vs + (active ? cl * PF_CW : 0);
+  for (int ib = 0; ib < NB; ++ib) {
+    float za[PF_RB * G];
 #pragma unroll
-    for (int wv = 0; wv < ODA_THREADS / 32; ++wv) s += part[wv * N * G + t];
-    atomicAdd(&z[b * N * G + t], s);
+    for (int x = 0; x < PF_RB * G; ++x) za[x] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < PF_RB; ++r) {
+      const int i = ib * PF_RB + r;
+      if (i < N) {
+        const uint32_t kb = keep.next(N);
+        const float4* vi = reinterpret_cast<const float4*>(vrow + i * KT);
+#pragma unroll
+        for (int q4 = 0; q4 < PF_CW / 4; ++q4) {
+          const float4 x4 = vi[q4];
+          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = q4 * 4 + u;
+            const float d = (kb & (1u << e)) ? xv[u] - vj[e] : 0.0f;
+#pragma unroll
+            for (int g = 0; g < G; ++g) za[r * G + g] = fmaf(wq[g][e], d, za[r * G + g]);
+          }
+        }
+      }
+    }
+    warp_transpose_sum32(za, lane);
+    zred[(warp * NB + ib) * 32 + lane] = za[0];
+  }
+  __syncthreads();
+  for (int x = t; x < N * G; x += blockDim.x) {       // x = i*G + g = (ib, lane) = (x / 32, x % 32)
+    float s = 0.0f;
+    for (int wv = 0; wv < nwarps; ++wv) s += zred[(wv * NB + (x >> 5)) * 32 + (x & 31)];
+    zpart[((int64_t)b * P + blockIdx.x) * N * G + x] = s;
   }
 }
 
-// z[b,i,g] = bc[g]
-__global__ void oda_init_logits_kernel(int64_t total, const float* __restrict__ bc, float* __restrict__ z) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < total) z[t] = bc[t % G];
+// alpha[b,:,g] = softmax_i(bc[g] + sum_p zpart[b][p][i][g]).  grid = B, dynamic smem N*G floats
+__global__ void oda_softmax_partials_kernel(int N, int P, const float* __restrict__ zpart, const float* __restrict__ bc,
+                                            float* __restrict__ alpha) {
+  extern __shared__ float z_s[];
+  const int64_t b = blockIdx.x;
+  for (int t = threadIdx.x; t < N * G; t += blockDim.x) {
+    float s = bc[t % G];
+    for (int p = 0; p < P; ++p) s += zpart[(b * P + p) * N * G + t];
+    z_s[t] = s;
+  }
+  __syncthreads();
+  softmax_regions_smem(z_s, N);
+  __syncthreads();
+  for (int t = threadIdx.x; t < N * G; t += blockDim.x) alpha[b * N * G + t] = z_s[t];
 }
 
 // dz = alpha (.) (dalpha - <alpha, dalpha>), dbc += sum dz.  grid = B
@@ -165,164 +256,142 @@ __global__ void softmax_regions_bwd_kernel(int64_t N, const float* __restrict__ 
   if (lane == 0 && dbc) atomicAdd(&dbc[warp], tot);
 }
 
-// Backward, e-mapping (thread owns 8 consecutive e = fixed (j,k) pairs, loops over the samples of its chunk and
-// over i).  With u(b,i,e) = scale * keep * sum_g dz[b,i,g] W[g,e]:
-//   dvl[b,j,k]  = -ql[b,k] * sum_i u              (this thread is the only writer of (b,j,k): plain store)
-//   dql[b,k]   += sum_i u * (vl[b,i,k]-vl[b,j,k])  (atomic: other j share k)
-//   dW[g,e]    += scale * sum_{b,i} dz[b,i,g] keep (vl[b,i,k]-vl[b,j,k]) ql[b,k]   (registers over the chunk, then atomic)
-// grid = (cdiv(NH/8, 128), cdiv(B, ODA_BCHUNK))
-constexpr int ODA_BCHUNK = 8;
-__global__ void __launch_bounds__(128)
-oda_pair_bwd_train_e_kernel(int64_t B, int64_t N, int64_t H, Drop d, const float* __restrict__ vl,
-                            const float* __restrict__ ql, const float* __restrict__ W, const float* __restrict__ dz,
-                            float* __restrict__ dW, float* __restrict__ dvl, float* __restrict__ dql) {
-  const int64_t NH = N * H;
-  const int64_t e0 = ((int64_t)blockIdx.x * 128 + threadIdx.x) * ODA_EPT;
-  if (e0 >= NH) return;
-  const uint64_t seed = d.key();
-  float w[G][ODA_EPT], dwacc[G][ODA_EPT];
-  int jj[ODA_EPT], kk[ODA_EPT];
-  {
-    int64_t j = e0 / H, k = e0 - j * H;
-#pragma unroll
-    for (int e = 0; e < ODA_EPT; ++e) {
-      const bool in = e0 + e < NH;
-      jj[e] = in ? (int)j : 0; kk[e] = in ? (int)k : 0;
-#pragma unroll
-      for (int g = 0; g < G; ++g) { w[g][e] = in ? W[g * NH + e0 + e] : 0.0f; dwacc[g][e] = 0.0f; }
-      if (++k == H) { k = 0; ++j; }
-    }
-  }
-  const bool contig = e0 + ODA_EPT <= NH && kk[ODA_EPT - 1] == kk[0] + ODA_EPT - 1 && (kk[0] & 1) == 0 && (H & 1) == 0 &&
-                      (reinterpret_cast<uintptr_t>(vl) & 7) == 0;
-  const int64_t b0 = (int64_t)blockIdx.y * ODA_BCHUNK;
-  const int64_t b1 = b0 + ODA_BCHUNK < B ? b0 + ODA_BCHUNK : B;
-  for (int64_t b = b0; b < b1; ++b) {
-    const float* vb = vl + b * NH;
-    float vj[ODA_EPT], qk[ODA_EPT], minus[ODA_EPT], dq[ODA_EPT];
-#pragma unroll
-    for (int e = 0; e < ODA_EPT; ++e) {
-      vj[e] = vb[(int64_t)jj[e] * H + kk[e]];
-      qk[e] = ql[b * H + kk[e]];
-      minus[e] = 0.0f; dq[e] = 0.0f;
-    }
-#pragma unroll 2                                   // two regions in flight: their Philox chains interleave (8 warps per SM)
-    for (int64_t i = 0; i < N; ++i) {
-      float keep[ODA_EPT];
-      keep8(d, seed, d.base + (uint64_t)((b * N + i) * NH + e0), keep);
-      const float4 z4 = __ldg(reinterpret_cast<const float4*>(dz + (b * N + i) * G));
-      const float zg[G] = {z4.x * d.scale, z4.y * d.scale, z4.z * d.scale, z4.w * d.scale};
-      float vi8[ODA_EPT];
-      load_row8(vb + i * H, kk, contig, vi8);
-#pragma unroll
-      for (int e = 0; e < ODA_EPT; ++e) {          // branch-free
-        const float diff = (vi8[e] - vj[e]) * keep[e];
-        const float u = (zg[0] * w[0][e] + zg[1] * w[1][e] + zg[2] * w[2][e] + zg[3] * w[3][e]) * keep[e];
-        minus[e] += u;
-        dq[e] = fmaf(u, diff, dq[e]);
-        const float dl = diff * qk[e];
-#pragma unroll
-        for (int g = 0; g < G; ++g) dwacc[g][e] = fmaf(zg[g], dl, dwacc[g][e]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < ODA_EPT; ++e) {
-      if (e0 + e < NH) {
-        dvl[b * NH + e0 + e] = -minus[e] * qk[e];
-        atomicAdd(&dql[b * H + kk[e]], dq[e]);
-      }
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < ODA_EPT; ++e)
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      if (e0 + e < NH) atomicAdd(&dW[g * NH + e0 + e], dwacc[g][e]);
-}
+// Backward.  Same mapping as the forward with PB_CW = 8 elements per thread.  With keep = the element's keep flag,
+// delta = vl[b,i,k] - vl[b,j,k], D[g,e] = sum_i dz[b,i,g] keep delta and u(i,e) = keep sum_g dz[b,i,g] W[g,e]:
+//   dW[g,e]    += scale ql[b,k] D[g,e]                                   (atomic: summed over the samples)
+//   dql[b,k]    = scale sum_{j,g} W[g,e] D[g,e]                          (column sum over j inside the CTA)
+//   dvl[b,x,k]  = scale ql[b,k] (sum_j u(x,(j,k)) - sum_i u(i,(x,k)))    ("plus": sum over j per row x through the
+//                 shared tile; "minus": the thread's own running sum over i)
+// The tile is stored TRANSPOSED, tile[column k][region j] with row stride TSC = 16 mod 32 words: the writers (lanes =
+// consecutive j) store conflict-free words, the column sums read float4 runs of j (4 lanes per column, two shuffles).
+// grid = (P, B).  dynamic smem: Vs [N][KT] | dvs [N][KT] | tile [2][KT][TSC] | dzs [N][G] | keep ring [PB_RD][threads]
+constexpr int PB_RD = 4;
+// tile row stride: >= roundup(N, 16) (so that TSC/16 float4 reads per lane cover a column) and = 16 mod 32
+__host__ __device__ inline int pair_tsc(int N) { return ((N + 3) / 4 * 4 + 15) / 32 * 32 + 16; }
 
-// Backward, (i,k)-mapping: thread (i, 16-column slot) loops over j and adds the "+" term
-//   dvl[b,i,k] += ql[b,k] * sum_j u(b,i,(j,k))
-// to the value the e-kernel stored (it is the only "+" writer of (b,i,k)).  W rows of a block of ODA_JB regions j
-// are staged in shared memory and shared by the ODA_IC rows i of the CTA.  A thread reads the 16 features
-// k0 .. k0+15 of its slot; the row is stored slot-interleaved, feature k at (k % 16) * KS + k / 16, so that the
-// lanes of a warp (consecutive slots) read consecutive words — the plain layout put them 16 words apart, a 16-way
-// bank conflict on every read.  grid = (cdiv(N, ODA_IC), B); threads = ODA_IC * cdiv(H,16) rounded up to a warp.
-// KSC: slots per row as a compile-time constant (20 for the models' H = 310) so that every shared-memory offset of
-// the inner loop is an immediate; 0 = computed from H at run time.
-constexpr int ODA_IC = 16, ODA_JB = 8;
-template <int KSC>
-__global__ void __launch_bounds__(320, 2)
-oda_pair_bwd_train_plus_kernel(int64_t N, int64_t H, Drop d, const float* __restrict__ ql,
-                                               const float* __restrict__ W, const float* __restrict__ dz,
-                                               float* __restrict__ dvl) {
-  extern __shared__ float w_s[];                        // [G][ODA_JB][Hp], Hp = 16 * KS
-  const int64_t NH = N * H;
-  const int KS = KSC > 0 ? KSC : (int)((H + 15) / 16);
-  const int Hp = 16 * KS;
-  const int64_t b = blockIdx.y;
-  const int ii = threadIdx.x / KS, ks = threadIdx.x % KS;
-  const int64_t i = (int64_t)blockIdx.x * ODA_IC + ii;
-  const bool active = ii < ODA_IC && i < N;
-  const int k0 = ks * 16;
-  const int nk = (int)(H - k0 < 16 ? H - k0 : 16);
-  const uint64_t seed = d.key();
-  float zg[G] = {0.f, 0.f, 0.f, 0.f};
-  if (active) {
-    const float4 z4 = __ldg(reinterpret_cast<const float4*>(dz + (b * N + i) * G));
-    zg[0] = z4.x * d.scale; zg[1] = z4.y * d.scale; zg[2] = z4.z * d.scale; zg[3] = z4.w * d.scale;
+template <int TSC>
+__global__ void __launch_bounds__(PAIR_MAX_THREADS)
+oda_pair_bwd_train_kernel(int N, int H, int CC, float scale, const uint32_t* __restrict__ bits,
+                          const float* __restrict__ vl, const float* __restrict__ ql, const float* __restrict__ W,
+                          const float* __restrict__ dz, float* __restrict__ dW, float* __restrict__ dvl,
+                          float* __restrict__ dql) {
+  extern __shared__ __align__(16) float pair_smem[];
+  const int KT = CC * PB_CW;
+  const int KTT = (blockDim.x + N - 1) / N * PB_CW;     // tile columns: every thread has a slot (idle chunks write zeros)
+  float* Vs = pair_smem;
+  float* dvs = Vs + (size_t)N * KT;
+  float* tile = dvs + (size_t)N * KT;
+  float* dzs = tile + (size_t)2 * KTT * TSC;
+  uint2* ring = reinterpret_cast<uint2*>(dzs + (size_t)N * G);
+  const int b = blockIdx.y;
+  const int64_t NH = (int64_t)N * H;
+  const int kbase = blockIdx.x * KT;
+  const int t = threadIdx.x;
+  const float* vb = vl + (int64_t)b * NH;
+  const int cl = t / N, j = t - cl * N;
+  const int k0 = kbase + cl * PB_CW;
+  const bool owner = cl < CC;
+  const bool active = owner && k0 < H;
+  KeepRing<PB_RD> keep(ring + t, (int)blockDim.x, bits, (uint64_t)b * N * NH + (active ? (uint64_t)j * H + k0 : 0),
+                       (uint64_t)NH);
+  keep.prime(N);
+  stage_rows(Vs, vb, N, H, KT, kbase);
+  for (int x = t; x < N * G; x += blockDim.x) dzs[x] = __ldg(dz + (int64_t)b * N * G + x);
+  for (int x = t; x < 2 * KTT * TSC; x += blockDim.x) tile[x] = 0.0f;      // the pad columns j >= N stay zero
+  float w[G][PB_CW], D[G][PB_CW], vj[PB_CW], minus[PB_CW];
+#pragma unroll
+  for (int e = 0; e < PB_CW; ++e) {
+    const int k = k0 + e;
+    const bool in = active && k < H;
+    vj[e] = in ? __ldg(vb + (int64_t)j * H + k) : 0.0f;
+    minus[e] = 0.0f;
+#pragma unroll
+    for (int g = 0; g < G; ++g) { w[g][e] = in ? __ldg(W + g * NH + (int64_t)j * H + k) : 0.0f; D[g][e] = 0.0f; }
   }
-  float plus[16];
+  __syncthreads();
+  const float* vrow = Vs + (active ? cl * PB_CW : 0);
+  float* tcol = tile + (size_t)cl * PB_CW * TSC + j;
+  const int toggle = KTT * TSC;
+  // column-sum role: 4 consecutive lanes share a column; lane sl takes the float4 runs sl, sl+4, ... (TSC/16 of them:
+  // the runs past N are zero padding)
+  const int col = t >> 2, sl = t & 3;
+  const int cstep = blockDim.x >> 2, colend = (KT + cstep - 1) / cstep * cstep;
+  for (int i = 0; i < N; ++i) {
+    const uint32_t kb = keep.next(N);
+    const float4 z4 = *reinterpret_cast<const float4*>(dzs + i * G);
+    const float zg[G] = {z4.x, z4.y, z4.z, z4.w};
+    const float4* vi = reinterpret_cast<const float4*>(vrow + i * KT);
+    const int boff = (i & 1) * toggle;
+    float um[PB_CW];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) plus[e] = 0.0f;
-  for (int64_t jb = 0; jb < N; jb += ODA_JB) {
-    const int64_t nj = N - jb < ODA_JB ? N - jb : ODA_JB;
-    __syncthreads();
-    // (loops instead of one flat index: the flat form spent three 64-bit divisions per staged element — two thirds of
-    // the kernel's instructions)
-    for (int gj = 0; gj < G * (int)nj; ++gj) {
-      const int g = gj / (int)nj, jl = gj - g * (int)nj;
-      const float* src = W + g * NH + (jb + jl) * H;
-      float* dst = w_s + (g * ODA_JB + jl) * Hp;
-      for (int k = threadIdx.x; k < (int)H; k += blockDim.x) dst[(k & 15) * KS + (k >> 4)] = __ldg(src + k);
-    }
-    __syncthreads();
-    if (!active) continue;
-    for (int64_t jl = 0; jl < nj; ++jl) {
-      const uint64_t idx0 = d.base + (uint64_t)((b * N + i) * NH + (jb + jl) * H + k0);
-      const uint4 r0 = philox_group(seed, d.layer, idx0 >> 4);
-      const uint32_t off = (uint32_t)idx0 & 15u;
-      uint4 r1 = r0;
-      if (off) r1 = philox_group(seed, d.layer, (idx0 >> 4) + 1);
-      // the 16 keep-bytes start at byte `off` of the 32-byte pair (r0, r1): rotate by whole words with predicated
-      // moves (static register indexing), then funnel-shift the remaining 0..3 bytes
-      uint32_t a[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-      if (off & 4u) {
+    for (int q4 = 0; q4 < PB_CW / 4; ++q4) {
+      const float4 x4 = vi[q4];
+      const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-        for (int t = 0; t < 7; ++t) a[t] = a[t + 1];
-      }
-      if (off & 8u) {
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const int e = q4 * 4 + u4;
+        const bool kp = (kb & (1u << e)) != 0;
+        const float dm = kp ? xv[u4] - vj[e] : 0.0f;
+        float u = zg[0] * w[0][e];
 #pragma unroll
-        for (int t = 0; t < 6; ++t) a[t] = a[t + 2];
-      }
-      const uint32_t sh = 8u * (off & 3u);
-      uint32_t by[4];
+        for (int g = 1; g < G; ++g) u = fmaf(zg[g], w[g][e], u);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) by[t] = __funnelshift_r(a[t], a[t + 1], sh);
-      const float* wrow = w_s + jl * Hp + ks;
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float m = (e < nk && ((by[e >> 2] >> (8 * (e & 3))) & 0xFFu) >= d.thr) ? 1.0f : 0.0f;
-        const float u = e < nk ? zg[0] * wrow[e * KS] + zg[1] * wrow[ODA_JB * Hp + e * KS] +
-                                     zg[2] * wrow[2 * ODA_JB * Hp + e * KS] + zg[3] * wrow[3 * ODA_JB * Hp + e * KS]
-                               : 0.0f;
-        plus[e] = fmaf(m, u, plus[e]);
+        for (int g = 0; g < G; ++g) D[g][e] = fmaf(zg[g], dm, D[g][e]);
+        um[e] = kp ? u : 0.0f;
+        minus[e] += um[e];
       }
     }
-  }
-  if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (e < nk) dvl[(b * N + i) * H + k0 + e] += plus[e] * ql[b * H + k0 + e];
+    for (int e = 0; e < PB_CW; ++e) tcol[boff + e * TSC] = um[e];
+    __syncthreads();
+    // plus term of row i: sums over j of the tile columns.  The other buffer is rewritten only after the next barrier,
+    // which every thread reaches after it has finished these reads.
+    for (int c = col; c < colend; c += cstep) {       // colend is a multiple of cstep: uniform trip count
+      float s = 0.0f;
+      if (c < KT) {
+        const float4* src = reinterpret_cast<const float4*>(tile + boff + (size_t)c * TSC) + sl;
+#pragma unroll
+        for (int q = 0; q < TSC / 16; ++q) {
+          const float4 a = src[q * 4];
+          s += (a.x + a.y) + (a.z + a.w);
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (sl == 0 && c < KT) dvs[i * KT + c] = s;
+    }
+  }
+  __syncthreads();
+  // per-sample tail: dW (atomics over the samples), the dql shares into tile buffer 0, minus into dvs
+  {
+#pragma unroll
+    for (int e = 0; e < PB_CW; ++e) {
+      const int k = k0 + e;
+      float qp = 0.0f;
+      if (active && k < H) {
+        const float qk = __ldg(ql + (int64_t)b * H + k) * scale;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          atomicAdd(dW + g * NH + (int64_t)j * H + k, qk * D[g][e]);
+          qp = fmaf(w[g][e], D[g][e], qp);
+        }
+      }
+      tcol[e * TSC] = qp * scale;
+      if (owner) dvs[j * KT + cl * PB_CW + e] -= minus[e];
+    }
+  }
+  __syncthreads();
+  for (int c = t; c < KT; c += blockDim.x) {
+    const int k = kbase + c;
+    if (k < H) {
+      float s = 0.0f;
+      for (int jj = 0; jj < N; ++jj) s += tile[(size_t)c * TSC + jj];
+      dql[(int64_t)b * H + k] = s;
+    }
+  }
+  for (int x = t; x < N * KT; x += blockDim.x) {
+    const int i = x / KT, k = kbase + (x - i * KT);
+    if (k < H) dvl[((int64_t)b * N + i) * H + k] = scale * __ldg(ql + (int64_t)b * H + k) * dvs[x];
   }
 }
 
@@ -333,6 +402,27 @@ using namespace vqa;
 static int oda_check(int64_t B, int64_t N, int64_t H, int64_t D, const char* who) {
   VQA_REQUIRE(B >= 0 && N >= 1 && H >= 1 && D >= 4 && D % 4 == 0, "%s: bad shape B=%lld N=%lld H=%lld D=%lld", who,
               (long long)B, (long long)N, (long long)H, (long long)D);
+  return VQA_OK;
+}
+
+// train-mode scratch: [keep bits of the dropped [B,N,N*H] tensor | forward's partial logits [B][P][N][G]]
+static size_t pair_bits_bytes(int64_t B, int64_t N, int64_t H) {
+  return (((size_t)cdiv(B * N * N * H, 16) * 2 + 8) + 255) & ~(size_t)255;
+}
+extern "C" size_t vqa_oda_pair_attn_workspace_bytes(int64_t B, int64_t N, int64_t H) {
+  if (B < 0 || N < 1 || H < 1) return 0;
+  const PairGeom gf = pair_geom(N, H, PF_CW);
+  return pair_bits_bytes(B, N, H) + (size_t)B * gf.P * N * G * sizeof(float);
+}
+
+template <class K>
+static int allow_smem(K kern, size_t smem, const char* who) {
+  if (smem > 227 * 1024) { set_error("%s: needs %zu bytes of shared memory (N too large)", who, smem); return VQA_EINVAL; }
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: cannot reserve %zu bytes of shared memory", who, smem);
+    return VQA_ECUDA;
+  }
   return VQA_OK;
 }
 
@@ -353,18 +443,32 @@ extern "C" int vqa_oda_pair_attn_fwd(const vqa_oda_pair_attn_fwd_params* p, void
                                                                                                p->bc, p->alpha);
     VQA_TRY(check_launch("oda_logits_eval"));
   } else {
-    Drop d = make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev);
-    const int64_t NH = p->N * p->H;
-    oda_init_logits_kernel<<<(unsigned)cdiv(p->B * p->N * G, 256), 256, 0, st>>>(p->B * p->N * G, p->bc, p->alpha);
-    VQA_TRY(check_launch("oda_init_logits"));
-    dim3 grid((unsigned)cdiv(cdiv(NH, ODA_EPT), ODA_THREADS), (unsigned)p->B);
-    const size_t smem = (size_t)(ODA_THREADS / 32) * p->N * G * sizeof(float);
-    VQA_REQUIRE(smem <= 48 * 1024, "vqa_oda_pair_attn_fwd: N=%lld too large", (long long)p->N);
-    KProf kp_(st, "oda_pair_logits_train", "flop", (double)p->B * p->N * p->N * p->H * (2.0 * G + 2.0));
-    oda_pair_logits_train_kernel<<<grid, ODA_THREADS, smem, st>>>(p->N, p->H, d, p->vl, p->ql, p->W, p->alpha);
-    VQA_TRY(check_launch("oda_pair_logits_train"));
-    softmax_regions_kernel<<<(unsigned)p->B, 128, (size_t)p->N * G * sizeof(float), st>>>(p->N, p->alpha);
-    VQA_TRY(check_launch("softmax_regions"));
+    VQA_REQUIRE(p->N <= 144, "vqa_oda_pair_attn_fwd: train mode supports up to 144 regions, got N=%lld", (long long)p->N);
+    const size_t need = vqa_oda_pair_attn_workspace_bytes(p->B, p->N, p->H);
+    if (!p->workspace || p->workspace_bytes < need) {
+      set_error("vqa_oda_pair_attn_fwd: train mode needs a workspace of %zu bytes (vqa_oda_pair_attn_workspace_bytes), got %zu",
+                need, p->workspace ? p->workspace_bytes : (size_t)0);
+      return VQA_EWORKSPACE;
+    }
+    const int64_t total = p->B * p->N * p->N * p->H;
+    uint8_t* bits = reinterpret_cast<uint8_t*>(p->workspace);
+    float* zpart = reinterpret_cast<float*>(bits + pair_bits_bytes(p->B, p->N, p->H));
+    if (!p->keep_bits_ready)      // a whole-model plan makes them in its batched keep-bit launch instead
+      VQA_TRY(vqa_dropout_bits(p->drop.p, p->drop.seed, p->drop.seed_dev, p->drop.layer, (uint64_t)total, bits, stream));
+    const PairGeom gm = pair_geom(p->N, p->H, PF_CW);
+    const size_t smem = ((size_t)p->N * gm.CC * PF_CW + (size_t)(gm.threads / 32) * cdiv(p->N, PF_RB) * 32) * sizeof(float) +
+                        (size_t)PF_RD * gm.threads * sizeof(uint2);
+    VQA_TRY(allow_smem(oda_pair_fwd_train_kernel, smem, "vqa_oda_pair_attn_fwd"));
+    {
+      KProf kp_(st, "oda_pair_fwd_train", "flop", (double)p->B * p->N * p->N * p->H * (2.0 * G + 2.0));
+      oda_pair_fwd_train_kernel<<<dim3((unsigned)gm.P, (unsigned)p->B), gm.threads, smem, st>>>(
+          (int)p->N, (int)p->H, gm.CC, 1.0f / (1.0f - p->drop.p), reinterpret_cast<const uint32_t*>(bits), p->vl, p->ql,
+          p->W, zpart);
+      VQA_TRY(check_launch("oda_pair_fwd_train"));
+    }
+    oda_softmax_partials_kernel<<<(unsigned)p->B, 128, (size_t)p->N * G * sizeof(float), st>>>((int)p->N, gm.P, zpart,
+                                                                                             p->bc, p->alpha);
+    VQA_TRY(check_launch("oda_softmax_partials"));
   }
   return launch_pool_fwd(p->B, p->N, p->D, p->x, p->alpha, p->pooled, st);
 }
@@ -393,29 +497,28 @@ extern "C" int vqa_oda_pair_attn_bwd(const vqa_oda_pair_attn_bwd_params* p, void
     oda_dw_broadcast_kernel<<<(unsigned)cdiv(G * NH, 256), 256, 0, st>>>(p->N, p->H, p->dwsum, p->dW, p->accumulate_w);
     return check_launch("oda_dw_broadcast");
   }
-  Drop d = make_drop(p->drop.p, p->drop.seed, p->drop.layer, 0, 1, p->drop.seed_dev);
+  const size_t need = vqa_oda_pair_attn_workspace_bytes(p->B, p->N, p->H);
+  if (!p->workspace || p->workspace_bytes < need) {
+    set_error("vqa_oda_pair_attn_bwd: train mode needs the forward's workspace (%zu bytes), got %zu", need,
+              p->workspace ? p->workspace_bytes : (size_t)0);
+    return VQA_EWORKSPACE;
+  }
   softmax_regions_bwd_kernel<<<(unsigned)p->B, 128, 0, st>>>(p->N, p->alpha, p->dalpha, p->dz, p->dbc);
   VQA_TRY(check_launch("softmax_regions_bwd"));
   if (!p->accumulate_w) cudaMemsetAsync(p->dW, 0, (size_t)G * NH * sizeof(float), st);
-  cudaMemsetAsync(p->dql, 0, (size_t)p->B * p->H * sizeof(float), st);
-  {
-    dim3 grid((unsigned)cdiv(cdiv(NH, ODA_EPT), 128), (unsigned)cdiv(p->B, ODA_BCHUNK));
-    KProf kp_(st, "oda_pair_bwd_train_e", "flop", (double)p->B * p->N * p->N * p->H * (4.0 * G + 4.0));
-    oda_pair_bwd_train_e_kernel<<<grid, 128, 0, st>>>(p->B, p->N, p->H, d, p->vl, p->ql, p->W, p->dz, p->dW, p->dvl,
-                                                      p->dql);
-    VQA_TRY(check_launch("oda_pair_bwd_train_e"));
-  }
-  {
-    const int KS = (int)((p->H + 15) / 16);
-    const int threads = ((ODA_IC * KS + 31) / 32) * 32;
-    VQA_REQUIRE(threads <= 1024, "vqa_oda_pair_attn_bwd: H=%lld too large", (long long)p->H);
-    const size_t smem = (size_t)G * ODA_JB * 16 * KS * sizeof(float);        // slot-interleaved rows of 16 * KS words
-    auto kern = KS == 20 ? oda_pair_bwd_train_plus_kernel<20> : oda_pair_bwd_train_plus_kernel<0>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((unsigned)cdiv(p->N, ODA_IC), (unsigned)p->B);
-    KProf kp_(st, "oda_pair_bwd_train_plus", "flop", (double)p->B * p->N * p->N * p->H * (2.0 * G + 1.0));
-    kern<<<grid, threads, smem, st>>>(p->N, p->H, d, p->ql, p->W, p->dz, p->dvl);
-    VQA_TRY(check_launch("oda_pair_bwd_train_plus"));
-  }
-  return VQA_OK;
+  const PairGeom gm = pair_geom(p->N, p->H, PB_CW);
+  const int KT = gm.CC * PB_CW, TSC = pair_tsc((int)p->N);
+  const int KTT = (int)cdiv(gm.threads, p->N) * PB_CW;
+  const size_t smem = ((size_t)2 * p->N * KT + (size_t)2 * KTT * TSC + (size_t)p->N * G) * sizeof(float) +
+                      (size_t)PB_RD * gm.threads * sizeof(uint2);
+  auto kern = TSC == 16 ? oda_pair_bwd_train_kernel<16> : TSC == 48 ? oda_pair_bwd_train_kernel<48>
+            : TSC == 80 ? oda_pair_bwd_train_kernel<80> : TSC == 112 ? oda_pair_bwd_train_kernel<112>
+            : TSC == 144 ? oda_pair_bwd_train_kernel<144> : nullptr;
+  VQA_REQUIRE(kern != nullptr, "vqa_oda_pair_attn_bwd: train mode supports up to 144 regions, got N=%lld", (long long)p->N);
+  VQA_TRY(allow_smem(kern, smem, "vqa_oda_pair_attn_bwd"));
+  KProf kp_(st, "oda_pair_bwd_train", "flop", (double)p->B * p->N * p->N * p->H * (4.0 * G + 4.0));
+  kern<<<dim3((unsigned)gm.P, (unsigned)p->B), gm.threads, smem, st>>>(
+      (int)p->N, (int)p->H, gm.CC, 1.0f / (1.0f - p->drop.p), reinterpret_cast<const uint32_t*>(p->workspace), p->vl,
+      p->ql, p->W, p->dz, p->dW, p->dvl, p->dql);
+  return check_launch("oda_pair_bwd_train");
 }

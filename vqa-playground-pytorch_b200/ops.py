@@ -369,15 +369,19 @@ class OdaPairAttnFn(torch.autograd.Function):
         pr.drop.p, pr.drop.layer, pr.drop.seed = float(p), int(layer), int(seed)
         pr.vl, pr.ql, pr.W, pr.bc, pr.x = vlc.data_ptr(), qlc.data_ptr(), w2.data_ptr(), bc.data_ptr(), xc.data_ptr()
         pr.wsum, pr.alpha, pr.pooled = wsum.data_ptr(), alpha.data_ptr(), pooled.data_ptr()
+        # train mode: keep-bit cache of the dropped [B,N,N*H] tensor + partial logits, filled here, read by backward
+        nws = int(_lib.lib().vqa_oda_pair_attn_workspace_bytes(B, N, Hd)) if p > 0.0 else 0
+        ws = torch.empty((max(nws, 1),), device=dev, dtype=torch.uint8)
+        pr.workspace, pr.workspace_bytes, pr.keep_bits_ready = ws.data_ptr(), nws, 0
         _lib.check(_lib.lib().vqa_oda_pair_attn_fwd(C.byref(pr), _stream()), "vqa_oda_pair_attn_fwd")
-        ctx.save_for_backward(xc, vlc, qlc, w2, alpha, wsum)
+        ctx.save_for_backward(xc, vlc, qlc, w2, alpha, wsum, ws)
         ctx.meta = (p, seed, layer, w.shape)
         ctx.mark_non_differentiable(alpha)
         return pooled, alpha
 
     @staticmethod
     def backward(ctx, dpooled, _dalpha):
-        xc, vlc, qlc, w2, alpha, wsum = ctx.saved_tensors
+        xc, vlc, qlc, w2, alpha, wsum, ws = ctx.saved_tensors
         p, seed, layer, wshape = ctx.meta
         B, N, Dd = xc.shape
         Hd = vlc.shape[2]
@@ -395,6 +399,7 @@ class OdaPairAttnFn(torch.autograd.Function):
                                                        alpha.data_ptr(), wsum.data_ptr())
         pr.dpooled, pr.dalpha, pr.dz, pr.dwsum = dpooled.data_ptr(), dalpha.data_ptr(), dz.data_ptr(), dwsum.data_ptr()
         pr.dW, pr.dbc, pr.dvl, pr.dql = dW.data_ptr(), dbc.data_ptr(), dvl.data_ptr(), dql.data_ptr()
+        pr.workspace, pr.workspace_bytes = ws.data_ptr(), (ws.numel() if p > 0.0 else 0)
         _lib.check(_lib.lib().vqa_oda_pair_attn_bwd(C.byref(pr), _stream()), "vqa_oda_pair_attn_bwd")
         return None, dvl, dql, dW.reshape(wshape), dbc, None, None, None
 

@@ -76,8 +76,11 @@ def pack_feature_shard(samples, keys=("v", "q_idxes", "a"), feature_key="v"):
 
 class HostPrefetcher:
     """Iterates over host batches (dicts of PINNED tensors) yielding device dicts; the copy of batch i+1 runs
-    on a side stream while batch i is being computed.  Two device staging slots, reused.  bf16 host tensors
-    (pack_feature_shard) are copied as bf16 and widened to fp32 on the device, on the copy stream as well."""
+    on a side stream while batch i is being computed.  Two device staging slots, allocated ONCE per prefetcher and
+    reused by every pass (`reset(batches)` starts another pass: building a new prefetcher per epoch would make the
+    caching allocator cudaMalloc fresh buffers for the new copy stream, a device-wide synchronisation that cost 1 ms
+    per step in the first version of the bench).  bf16 host tensors (pack_feature_shard) are copied as bf16 and
+    widened to fp32 on the device."""
 
     def __init__(self, host_batches, device, keys=("v", "q_idxes", "a"), widen_into=None):
         """widen_into: dict of preallocated fp32 device tensors (e.g. GraphedStep.static): bf16 features are widened
@@ -94,20 +97,32 @@ class HostPrefetcher:
         self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
         self.bytes_per_batch = 0
 
+    def reset(self, host_batches):
+        """Another pass over (other) host batches of the same shapes with the same device buffers."""
+        self.batches = host_batches
+        return self
+
+    def _allocate(self, slot, host):
+        # on the CONSUMER's stream pool: the buffers live as long as the prefetcher and every cross-stream use is
+        # ordered by the ready / consumed events
+        widened = lambda k: self.widen_into is not None and k in self.widen_into
+        self.slots[slot] = {k: torch.empty(host[k].shape, device=self.device, dtype=torch.float32 if
+                                           host[k].dtype == torch.bfloat16 else host[k].dtype)
+                            for k in self.keys if not (host[k].dtype == torch.bfloat16 and widened(k))}
+        self.stage[slot] = {k: torch.empty(host[k].shape, device=self.device, dtype=torch.bfloat16)
+                            for k in self.keys if host[k].dtype == torch.bfloat16}
+
     def _issue(self, i, slot):
         host = self.batches[i]
+        if self.slots[slot] is None:
+            self._allocate(slot, host)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.consumed[slot])        # previous user of the slot has finished
-            if self.slots[slot] is None:
-                self.slots[slot] = {k: torch.empty(host[k].shape, device=self.device, dtype=torch.float32 if
-                                                   host[k].dtype == torch.bfloat16 else host[k].dtype) for k in self.keys}
-                self.stage[slot] = {k: torch.empty_like(host[k], device=self.device) for k in self.keys
-                                    if host[k].dtype == torch.bfloat16}
             nbytes = 0
             for k in self.keys:
                 if host[k].dtype == torch.bfloat16:
                     self.stage[slot][k].copy_(host[k], non_blocking=True)
-                    if self.widen_into is None or k not in self.widen_into:
+                    if k in self.slots[slot]:
                         ops.cast_bf16_to_f32(self.stage[slot][k], out=self.slots[slot][k])
                 else:
                     self.slots[slot][k].copy_(host[k], non_blocking=True)
@@ -128,12 +143,10 @@ class HostPrefetcher:
             if i + 1 < n:
                 self._issue(i + 1, slot ^ 1)
             cur.wait_event(self.ready[slot])
-            out = self.slots[slot]
-            if self.widen_into is not None and self.stage[slot]:
-                out = dict(out)
-                for k, st in self.stage[slot].items():
-                    if k in self.widen_into:
-                        out[k] = ops.cast_bf16_to_f32(st, out=self.widen_into[k])
+            out = dict(self.slots[slot])
+            for k, st in self.stage[slot].items():
+                if k not in out:
+                    out[k] = ops.cast_bf16_to_f32(st, out=self.widen_into[k])
             yield out
             self.consumed[slot].record(cur)
 

@@ -50,7 +50,7 @@ enum {
   VQA_EWORKSPACE = -4   /* workspace too small */
 };
 
-enum { VQA_ACT_NONE = 0, VQA_ACT_RELU = 1, VQA_ACT_SIGMOID = 2 };
+enum { VQA_ACT_NONE = 0, VQA_ACT_RELU = 1, VQA_ACT_SIGMOID = 2, VQA_ACT_TANH = 3 /* GRU candidate state only */ };
 
 /* GEMM arithmetic.  Every mode but FP32_SIMT runs on the tcgen05 tensor cores with fp32 accumulation in
  * TMEM and NEVER falls back to the CUDA-core GEMM: what a mode cannot run is VQA_EINVAL.
@@ -423,6 +423,65 @@ int vqa_kld_logsoftmax_fwd_bwd(const vqa_kld_logsoftmax_params* p, void* stream)
 /* Input pipeline: region features stored and shipped as bf16 (pre-packed shards: half the host->device bytes of the
  * reference's fp32 h5 features, datasets.py:517-549, :905-970) are widened to the fp32 tensor the plans read.  Exact. */
 int vqa_cast_bf16_f32(int64_t n, const void* src_bf16, float* dst, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * SkipThoughts question encoder (putils/__init__.py:878-985): nn.Embedding(V, 620, padding_idx=0) ->
+ * BayesianGRU(620 -> 2400) -> the hidden state at each question's last non-PAD token.  The dense contractions are the
+ * grouped linears above (the three input projections of ALL time steps in one launch, the three recurrent projections
+ * of a step in one launch, one wgrad over all steps at the end); these entry points are what sits between them.
+ *
+ * SequentialDropout (putils/__init__.py:503-539): ONE mask per sequence and call site, shared by every time step.
+ * masks[m][b][f] = keep ? 1/(1-p) : 0 with keep from the Philox contract above, layer = layer0 + m, element index
+ * b*dim + f.  p = 0 writes ones. */
+int vqa_seq_dropout_masks(float p, uint64_t seed, const uint64_t* seed_dev, uint32_t layer0, int64_t B, int64_t dim,
+                          int nmasks, float* out /* [nmasks][B][dim] */, void* stream);
+/* out[g][(t*B + b)][f] = emb[idx[b][t]][f] * masks[g][b][f], g < 3 (drop_ir / drop_ii / drop_in of
+ * BayesianGRUCell.forward :624-626); rows are TIME-major so that a step's slice is contiguous.  masks NULL = eval. */
+int vqa_gru_embed_fwd(int64_t B, int64_t T, int64_t I, const int64_t* idx /* [B][T] */, const float* emb /* [V][I] */,
+                      const float* masks /* [3][B][I] or NULL */, float* out /* [3][T*B][I] */, void* stream);
+/* demb[idx[b][t]][f] += sum_g dX[g][(t*B+b)][f] * masks[g][b][f]; the PAD row 0 receives nothing (padding_idx=0). */
+int vqa_gru_embed_bwd(int64_t B, int64_t T, int64_t I, const int64_t* idx, const float* masks, const float* dX,
+                      float* demb, void* stream);
+/* One step of BayesianGRUCell.forward (:630-636) after its six projections:
+ *   r = sigmoid(gi_r + gh_r), i = sigmoid(gi_i + gh_i), n = act(gi_n + r*gh_n), h = (1-i)*n + i*h_prev
+ * plus the masked copies hm_g = h * hmask_g the next step's recurrent projections read (drop_hr/hi/hn).
+ * gh and h_prev are NULL together at the first step (h_prev = 0, the hidden projections have no bias). */
+typedef struct {
+  int64_t B, H;
+  int act;                 /* VQA_ACT_RELU | VQA_ACT_TANH (SkipThoughts(af=...), config/CoR2.py:166-167) */
+  const float* gi[3];      /* [B,H] each: input projections r, i, n of this step */
+  const float* gh[3];      /* [B,H] each: recurrent projections, or NULL */
+  const float* h_prev;     /* [B,H] or NULL */
+  const float* hmask[3];   /* [B,H] sequence-tied masks or NULL (eval) */
+  float* h;                /* [B,H] */
+  float* r; float* i; float* n;   /* [B,H] stash for the backward (NULL to skip) */
+  float* hm[3];            /* [B,H] masked copies for the next step (NULL to skip) */
+} vqa_gru_gate_fwd_params;
+int vqa_gru_gate_fwd(const vqa_gru_gate_fwd_params* p, void* stream);
+/* Backward of one step.  dh = dh_partial + sum_g dhm[g]*hmask[g] + (last_pos[b] == t ? dx_last[b] : 0);
+ * outputs da[0..2] = gradients of the pre-activations (= of gi_r, gi_i, gi_n and of gh_r, gh_i), dgh_n (of gh_n) and
+ * dh_partial_out = dh * i (the direct path to h_prev). */
+typedef struct {
+  int64_t B, H;
+  int act;
+  int64_t t;
+  const float* dh_partial;   /* [B,H] or NULL */
+  const float* dhm[3];       /* [B,H] gradients of the NEXT step's masked inputs, or NULL */
+  const float* hmask[3];
+  const float* dx_last;      /* [B,H] gradient of the encoder output, or NULL */
+  const int64_t* last_pos;   /* [B] */
+  const float* r; const float* i; const float* n;
+  const float* gh_n;         /* [B,H] or NULL (first step) */
+  const float* h_prev;       /* [B,H] or NULL */
+  float* da[3];
+  float* dgh_n;
+  float* dh_partial_out;
+} vqa_gru_gate_bwd_params;
+int vqa_gru_gate_bwd(const vqa_gru_gate_bwd_params* p, void* stream);
+/* last_pos[b] = (#tokens != 0 of question b) - 1, -1 wrapping to T-1 like `mask[i][lengths[i] - 1]` (:729-731);
+ * out[b] = hs[last_pos[b]][b] for the time-major hidden states hs [T][B][H]. */
+int vqa_gru_last_pos(int64_t B, int64_t T, const int64_t* idx, int64_t* last_pos, void* stream);
+int vqa_gru_select_last(int64_t B, int64_t H, const float* hs, const int64_t* last_pos, float* out, void* stream);
+
 /* Prediction tail of the eval loop (train.py:146-169, `output.data.cpu().max(1)`): pred[b] = index of the first maximum
  * of logits[b, :] (OpenEnded), or of the candidates mc_idx[b, 0..n_mc) (MultipleChoice, train.py:153-164: -1 entries are
  * padding; pred = -1 when a row has no candidate).  best ([B] or NULL) receives the winning logit.  The B x C logits
@@ -473,6 +532,9 @@ typedef struct {
    * stream that produced the group, so that a data-parallel caller can all-reduce a bucket of the flat buffer
    * while the rest of the backward is still running.  NULL entries are skipped. */
   void* group_events[VQA_MAX_GRAD_GROUPS];
+  float* dq;                 /* optional [B,2400]: gradient of the loss w.r.t. the question embedding, for a trainable
+                                question encoder in front of the core (seq2vec, config/CoR2.py:205); NULL skips the
+                                extra dgrads of the 2400->310 question projections */
 } vqa_model_bwd_params;
 /* ------------------------------------------------------------------------------------------
  * Optimizer step over the flat gradient buffer: global-norm clipping + Adam in two launches.

@@ -129,6 +129,17 @@ class KldParams(C.Structure):
                 ("loss_rows", fp), ("dlogits", fp)]
 
 
+class GruGateFwd(C.Structure):
+    _fields_ = [("B", i64), ("H", i64), ("act", C.c_int), ("gi", fp * 3), ("gh", fp * 3), ("h_prev", fp),
+                ("hmask", fp * 3), ("h", fp), ("r", fp), ("i", fp), ("n", fp), ("hm", fp * 3)]
+
+
+class GruGateBwd(C.Structure):
+    _fields_ = [("B", i64), ("H", i64), ("act", C.c_int), ("t", i64), ("dh_partial", fp), ("dhm", fp * 3),
+                ("hmask", fp * 3), ("dx_last", fp), ("last_pos", fp), ("r", fp), ("i", fp), ("n", fp), ("gh_n", fp),
+                ("h_prev", fp), ("da", fp * 3), ("dgh_n", fp), ("dh_partial_out", fp)]
+
+
 class ModelFwd(C.Structure):
     _fields_ = [("B", i64), ("N", i64), ("C", i64), ("train", C.c_int), ("math", C.c_int), ("seed", C.c_uint64),
                 ("seed_dev", fp), ("v", fp), ("q", fp), ("params", C.POINTER(fp)), ("logits", fp), ("alpha1", fp), ("alpha2", fp),
@@ -137,7 +148,7 @@ class ModelFwd(C.Structure):
 
 class ModelBwd(C.Structure):
     _fields_ = [("fwd", ModelFwd), ("dlogits", fp), ("grads", C.POINTER(fp)), ("accumulate", C.c_int),
-                ("grads_flat", fp), ("grads_flat_bytes", C.c_size_t), ("group_events", fp * 16)]
+                ("grads_flat", fp), ("grads_flat_bytes", C.c_size_t), ("group_events", fp * 16), ("dq", fp)]
 
 
 STRUCTS = {
@@ -146,7 +157,8 @@ STRUCTS = {
     "vqa_region_softmax_pool_fwd_params": PoolFwd, "vqa_region_softmax_pool_bwd_params": PoolBwd,
     "vqa_cor_compound_fwd_params": CompoundFwd, "vqa_cor_compound_bwd_params": CompoundBwd,
     "vqa_oda_pair_attn_fwd_params": OdaFwd, "vqa_oda_pair_attn_bwd_params": OdaBwd,
-    "vqa_kld_logsoftmax_params": KldParams, "vqa_model_fwd_params": ModelFwd, "vqa_model_bwd_params": ModelBwd,
+    "vqa_kld_logsoftmax_params": KldParams, "vqa_gru_gate_fwd_params": GruGateFwd, "vqa_gru_gate_bwd_params": GruGateBwd,
+    "vqa_model_fwd_params": ModelFwd, "vqa_model_bwd_params": ModelBwd,
 }
 
 # every symbol include/vqacore.h declares: name -> (restype, argtypes)
@@ -176,6 +188,13 @@ SYMBOLS = {
     "vqa_cor_compound_fwd": _OP(CompoundFwd), "vqa_cor_compound_bwd": _OP(CompoundBwd),
     "vqa_oda_pair_attn_fwd": _OP(OdaFwd), "vqa_oda_pair_attn_bwd": _OP(OdaBwd),
     "vqa_kld_logsoftmax_fwd_bwd": _OP(KldParams),
+    "vqa_seq_dropout_masks": (C.c_int, [C.c_float, C.c_uint64, C.c_void_p, C.c_uint32, i64, i64, C.c_int, C.c_void_p,
+                                        C.c_void_p]),
+    "vqa_gru_embed_fwd": (C.c_int, [i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vqa_gru_embed_bwd": (C.c_int, [i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vqa_gru_gate_fwd": _OP(GruGateFwd), "vqa_gru_gate_bwd": _OP(GruGateBwd),
+    "vqa_gru_last_pos": (C.c_int, [i64, i64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vqa_gru_select_last": (C.c_int, [i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vqa_cast_bf16_f32": (C.c_int, [i64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vqa_argmax_rows": (C.c_int, [i64, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vqa_sum_rows": (C.c_int, [i64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -159,3 +159,71 @@ class QuestionPassThrough(nn.Module):
 
     def forward(self, q):
         return q
+
+
+# ----------------------------------------------------------------------------------------- question encoder
+class BayesianGRUCell(nn.Module):
+    """Parameter container of putils.BayesianGRUCell (putils/__init__.py:604-637 over AbstractGRUCell :566-583): six
+    nn.Linear children with the reference's names (weight_ir/ii/in with bias, weight_hr/hi/hn without), so the
+    state_dict keys `gru_cell.weight_*.{weight,bias}` that SkipThoughts.load_bayesiangru_state_dict fills are the same."""
+
+    def __init__(self, input_size, hidden_size, bias_ih=True, bias_hh=False, dropout=0.25, af='tanh'):
+        super().__init__()
+        if bias_hh or not bias_ih:
+            raise NotImplementedError("BayesianGRUCell: the SkipThoughts form (bias_ih=True, bias_hh=False) is implemented")
+        self.input_size, self.hidden_size, self.dropout, self.af = input_size, hidden_size, dropout, af
+        self.weight_ir = nn.Linear(input_size, hidden_size, bias=True)
+        self.weight_ii = nn.Linear(input_size, hidden_size, bias=True)
+        self.weight_in = nn.Linear(input_size, hidden_size, bias=True)
+        self.weight_hr = nn.Linear(hidden_size, hidden_size, bias=False)
+        self.weight_hi = nn.Linear(hidden_size, hidden_size, bias=False)
+        self.weight_hn = nn.Linear(hidden_size, hidden_size, bias=False)
+
+    def set_dropout(self, dropout):
+        self.dropout = dropout
+
+
+class BayesianGRU(nn.Module):
+    """putils.BayesianGRU (putils/__init__.py:660-741) with return_last=True: the hidden state at each sequence's last
+    non-PAD position.  `forward(emb_or_idx, ...)` is not exposed step by step: SkipThoughts below runs the whole
+    encoder as one autograd node (ops.BayesianGruFn)."""
+
+    def __init__(self, input_size, hidden_size, bias_ih=True, bias_hh=False, dropout=0.25, return_last=True, af='tanh'):
+        super().__init__()
+        if return_last is not True:
+            raise NotImplementedError("BayesianGRU: return_last=True (the form config/CoR2.py and config/ODA.py use)")
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.dropout, self.return_last, self.af = dropout, return_last, af
+        self.gru_cell = BayesianGRUCell(input_size, hidden_size, bias_ih, bias_hh, dropout=dropout, af=af)
+
+    def set_dropout(self, dropout):
+        self.dropout = dropout
+        self.gru_cell.set_dropout(dropout)
+
+
+class SkipThoughts(nn.Module):
+    """putils.SkipThoughts (putils/__init__.py:878-985) without the downloads: nn.Embedding(len(vocab), 620,
+    padding_idx=0) + BayesianGRU(620, 2400, dropout=0.25); state_dict keys `embedding.weight`,
+    `gru.gru_cell.weight_*` as in the reference, so a reference checkpoint's `seq2vec.*` entries load unchanged.
+    The pretrained uni-skip tables are not shipped (no network): weights keep their default init unless loaded.
+    forward(q_idxes [B, T] int64, 0 = PAD) -> [B, 2400]."""
+
+    def __init__(self, vocab_list, data_dir=None, gru='BayesianGRU', return_last=True, af='tanh', precision="bf16x3"):
+        super().__init__()
+        if gru != 'BayesianGRU':
+            raise ValueError
+        self.vocab_list, self.data_dir, self.af, self.math = vocab_list, data_dir, af, precision
+        self.embedding = nn.Embedding(num_embeddings=len(vocab_list), embedding_dim=620, padding_idx=0)
+        self.gru = BayesianGRU(input_size=620, hidden_size=2400, dropout=0.25, return_last=return_last, af=af)
+        self.fixed_seed = None
+
+    def forward(self, x, return_hidden=False):
+        c = self.gru.gru_cell
+        p = float(self.gru.dropout) if self.training else 0.0
+        seed = 0
+        if p > 0.0:
+            seed = self.fixed_seed if self.fixed_seed is not None else ops.next_seed()
+        out = ops.BayesianGruFn.apply(x, self.embedding.weight, c.weight_ir.weight, c.weight_ir.bias, c.weight_ii.weight,
+                                      c.weight_ii.bias, c.weight_in.weight, c.weight_in.bias, c.weight_hr.weight,
+                                      c.weight_hi.weight, c.weight_hn.weight, p, seed, self.af, self.math)
+        return out

@@ -82,6 +82,7 @@ struct Cor2Ws {
       *dhq2, *dalpha_ext, *dpooled1, *dalpha1, *dz1, *dfuse1, *dvl, *d_f1_H2;
   float* lin_ws; size_t lin_ws_bytes;
   float* side_ws; size_t side_ws_bytes;   // scratch of the ops that run on the side lane
+  float* dq_parts;                        // [4][B][Q]: per-projection shares of the question-embedding gradient
   uint8_t* bits[32];           // packed dropout keep-bits of every dropout site, by layer id (train mode)
   int64_t bits_n[32];          // element count of each site
   float *vq1_w1p, *vq1_w2p, *vq2_w1p, *vq2_w2p, *ff_w1p, *ff_w2p, *eq1p, *eq2p, *clsp;   // vqa_pack_weights copies
@@ -127,6 +128,7 @@ static Cor2Ws carve_cor2(void* base, int64_t B, int64_t N, int64_t C) {
   w.dfuse1 = c.take(M * F); w.dvl = c.take(M * HP); w.d_f1_H2 = c.take(2 * B * F);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
   w.side_ws_bytes = (size_t)(8 * B * 2048 + 65536) * sizeof(float); w.side_ws = c.take(8 * B * 2048 + 65536);
+  w.dq_parts = c.take(4 * B * Q);
   {
     using namespace cor2;
     for (int i = 0; i < 32; ++i) { w.bits[i] = nullptr; w.bits_n[i] = 0; }
@@ -157,6 +159,7 @@ struct OdaWs {
   float *dxf, *dvf, *dqf, *d_ff_H2, *dpooled, *dalpha, *dz, *dwsum, *dvl, *dql;
   float* lin_ws; size_t lin_ws_bytes;
   float* side_ws; size_t side_ws_bytes;
+  float* dq_parts;                                     // [2][B][Q]
   uint8_t* bits[32];
   int64_t bits_n[32];
   float *ff_w1p, *ff_w2p, *clsp;
@@ -177,6 +180,7 @@ static OdaWs carve_oda(void* base, int64_t B, int64_t N, int64_t C) {
   w.dvl = c.take(M * H); w.dql = c.take(B * H);
   w.lin_ws_bytes = (size_t)lin_scratch_floats(B, N, C) * sizeof(float); w.lin_ws = c.take(lin_scratch_floats(B, N, C));
   w.side_ws_bytes = (size_t)(8 * B * 2048 + 65536) * sizeof(float); w.side_ws = c.take(8 * B * 2048 + 65536);
+  w.dq_parts = c.take(2 * B * Q);
   {
     using namespace oda;
     for (int i = 0; i < 32; ++i) { w.bits[i] = nullptr; w.bits_n[i] = 0; }
@@ -193,6 +197,22 @@ static OdaWs carve_oda(void* base, int64_t B, int64_t N, int64_t C) {
   w.vp = reinterpret_cast<__nv_bfloat16*>(c.take(M * D)); w.cv_wp = reinterpret_cast<__nv_bfloat16*>(c.take(HP * D));
   w.bytes = c.off;
   return w;
+}
+
+// dst[i] = sum_{k < parts} src[k*n + i]   (the question-embedding gradient: one share per 2400->310 projection)
+__global__ void sum_parts_kernel(int64_t n, int parts, const float* __restrict__ src, float* __restrict__ dst) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 s = *reinterpret_cast<const float4*>(src + i);
+  for (int k = 1; k < parts; ++k) {
+    const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)k * n + i);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dst + i) = s;
+}
+static int sum_parts(int64_t n, int parts, const float* src, float* dst, cudaStream_t st) {
+  sum_parts_kernel<<<(unsigned)cdiv(n / 4, 256), 256, 0, st>>>(n, parts, src, dst);
+  return check_launch("sum_parts");
 }
 
 // ---- small builders ---------------------------------------------------------------------------------
@@ -663,7 +683,10 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; const float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
     int64_t ldy[4] = {HP, HP, HP, HP}; const float* dY[4] = {w.dql, w.dhq1, w.dhq2, w.dqf}; int64_t lddy[4] = {HP, HP, HP, HP};
     uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
-    { ProfScope ps_(ss, "q_proj4.bwd"); VQA_TRY(lin_bwd(cs, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
+    float* dX[4] = {w.dq_parts, w.dq_parts + B * Q, w.dq_parts + 2 * B * Q, w.dq_parts + 3 * B * Q};
+    int64_t lddx[4] = {Q, Q, Q, Q};
+    { ProfScope ps_(ss, "q_proj4.bwd"); VQA_TRY(lin_bwd(cs, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, bp->dq ? dX : nullptr, bp->dq ? lddx : nullptr, 0, layer)); }
+    if (bp->dq) VQA_TRY(sum_parts(B * Q, 4, w.dq_parts, bp->dq, ss));
   }
   mark(11, ss);
   Lanes::wait(ms, L->record(ss));                  // join
@@ -821,7 +844,10 @@ extern "C" int vqa_oda_bwd(const vqa_model_bwd_params* bp, void* stream) {
     const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {COMPRESS_Q, LINEAR_Q};
     const float* Y[2] = {w.ql, w.qf}; int64_t ldy[2] = {H, HP}; const float* dY[2] = {w.dql, w.dqf};
     int64_t lddy[2] = {H, HP}; uint32_t layer[2] = {L_COMPRESS_Q, L_LINEAR_Q};
-    { ProfScope ps_(stream, "q_proj2.bwd"); VQA_TRY(lin_bwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer)); }
+    float* dX[2] = {w.dq_parts, w.dq_parts + B * Q};
+    int64_t lddx[2] = {Q, Q};
+    { ProfScope ps_(stream, "q_proj2.bwd"); VQA_TRY(lin_bwd(c, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, bp->dq ? dX : nullptr, bp->dq ? lddx : nullptr, 0, layer)); }
+    if (bp->dq) VQA_TRY(sum_parts(B * Q, 2, w.dq_parts, bp->dq, (cudaStream_t)stream));
   }
   mark(5);
   return VQA_OK;

@@ -404,6 +404,129 @@ class OdaPairAttnFn(torch.autograd.Function):
         return None, dvl, dql, dW.reshape(wshape), dbc, None, None, None
 
 
+# =========================================================================== SkipThoughts question encoder
+GRU_INPUT_MASK_LAYER, GRU_HIDDEN_MASK_LAYER = 64, 67     # Philox layer ids of drop_ir/ii/in and drop_hr/hi/hn
+
+
+def seq_dropout_masks(p, seed, layer0, B, dim, nmasks, device):
+    """[nmasks, B, dim] sequence-tied dropout multipliers (0 or 1/(1-p)) — SequentialDropout, putils/__init__.py:503-539."""
+    out = torch.empty((nmasks, B, dim), device=device, dtype=torch.float32)
+    _lib.check(_lib.lib().vqa_seq_dropout_masks(float(p), int(seed), None, int(layer0), B, dim, nmasks, out.data_ptr(),
+                                                _stream()), "vqa_seq_dropout_masks")
+    return out
+
+
+def _gru_act(af):
+    if af not in ("relu", "tanh"):
+        raise ValueError("BayesianGRU: af must be 'relu' or 'tanh', got %r" % (af,))
+    return 1 if af == "relu" else 3
+
+
+class BayesianGruFn(torch.autograd.Function):
+    """SkipThoughts.forward (putils/__init__.py:975-982): embedding -> BayesianGRU over T tokens -> hidden state at the
+    last non-PAD token.  One autograd node; every kernel inside is libvqacore's: the three input projections of all
+    time steps are ONE grouped tensor-core linear over [T*B, 620], each step is one grouped linear for the three
+    recurrent projections plus one fused gate kernel, the backward walks the steps in reverse with dgrad-only linears
+    and finishes with ONE wgrad over all steps per weight."""
+
+    @staticmethod
+    def forward(ctx, idx, emb_w, w_ir, b_ir, w_ii, b_ii, w_in, b_in, w_hr, w_hi, w_hn, p, seed, af, math):
+        if not (isinstance(idx, torch.Tensor) and idx.is_cuda and idx.dtype == torch.int64 and idx.dim() == 2):
+            raise ValueError("q_idxes: expected a [B, T] int64 CUDA tensor of token ids")
+        idx = idx.contiguous()
+        B, T = idx.shape
+        emb_w = _chk(emb_w, "embedding.weight", 2)
+        I, H = emb_w.shape[1], w_hr.shape[0]
+        wi = [_chk(w, "weight_i*", 2) for w in (w_ir, w_ii, w_in)]
+        bi = [_chk(b, "bias_i*", 1) for b in (b_ir, b_ii, b_in)]
+        wh = [_chk(w, "weight_h*", 2) for w in (w_hr, w_hi, w_hn)]
+        dev, L, act = idx.device, _lib.lib(), _gru_act(af)
+        train = p > 0.0
+        imask = seq_dropout_masks(p, seed, GRU_INPUT_MASK_LAYER, B, I, 3, dev) if train else None
+        hmask = seq_dropout_masks(p, seed, GRU_HIDDEN_MASK_LAYER, B, H, 3, dev) if train else None
+        X = torch.empty((3, T * B, I), device=dev, dtype=torch.float32)
+        _lib.check(L.vqa_gru_embed_fwd(B, T, I, idx.data_ptr(), emb_w.data_ptr(), _p(imask), X.data_ptr(), _stream()),
+                   "vqa_gru_embed_fwd")
+        gi = linear_forward([X[0], X[1], X[2]], wi, bi, 0, 0.0, 0, [0, 0, 0], math)        # 3 x [T*B, H]
+        hs = torch.empty((T, B, H), device=dev, dtype=torch.float32)
+        r, i, n, ghn = (torch.empty_like(hs) for _ in range(4))
+        hm = torch.empty((3, T, B, H), device=dev, dtype=torch.float32)
+        gh_r, gh_i = torch.empty((B, H), device=dev), torch.empty((B, H), device=dev)
+        for t in range(T):
+            pr = _lib.GruGateFwd()
+            pr.B, pr.H, pr.act = B, H, act
+            if t > 0:
+                linear_forward([hm[0, t - 1], hm[1, t - 1], hm[2, t - 1]], wh, [None] * 3, 0, 0.0, 0, [0, 0, 0], math,
+                               outs=[gh_r, gh_i, ghn[t]])
+                pr.gh[0], pr.gh[1], pr.gh[2] = gh_r.data_ptr(), gh_i.data_ptr(), ghn[t].data_ptr()
+                pr.h_prev = hs[t - 1].data_ptr()
+            for g in range(3):
+                pr.gi[g] = gi[g][t * B:(t + 1) * B].data_ptr()
+                pr.hmask[g] = hmask[g].data_ptr() if train else None
+                pr.hm[g] = hm[g, t].data_ptr()
+            pr.h, pr.r, pr.i, pr.n = hs[t].data_ptr(), r[t].data_ptr(), i[t].data_ptr(), n[t].data_ptr()
+            _lib.check(L.vqa_gru_gate_fwd(C.byref(pr), _stream()), "vqa_gru_gate_fwd")
+        last_pos = torch.empty((B,), device=dev, dtype=torch.int64)
+        _lib.check(L.vqa_gru_last_pos(B, T, idx.data_ptr(), last_pos.data_ptr(), _stream()), "vqa_gru_last_pos")
+        out = torch.empty((B, H), device=dev, dtype=torch.float32)
+        _lib.check(L.vqa_gru_select_last(B, H, hs.data_ptr(), last_pos.data_ptr(), out.data_ptr(), _stream()),
+                   "vqa_gru_select_last")
+        ctx.save_for_backward(idx, X, hs, r, i, n, ghn, hm, last_pos, *wi, *wh)
+        ctx.masks = (imask, hmask)
+        ctx.meta = (act, math, emb_w.shape, ctx.needs_input_grad[1])
+        ctx.all_hiddens = hs
+        return out
+
+    @staticmethod
+    def backward(ctx, dx):
+        idx, X, hs, r, i, n, ghn, hm, last_pos, w_ir, w_ii, w_in, w_hr, w_hi, w_hn = ctx.saved_tensors
+        imask, hmask = ctx.masks
+        act, math, emb_shape, need_emb = ctx.meta
+        B, T = idx.shape
+        I, H = X.shape[2], hs.shape[2]
+        dev, L = idx.device, _lib.lib()
+        dx = dx.contiguous()
+        wi, wh = [w_ir, w_ii, w_in], [w_hr, w_hi, w_hn]
+        dA = torch.empty((3, T, B, H), device=dev, dtype=torch.float32)        # d(pre-activations) = d gi_* (= d gh_r, d gh_i)
+        dghn = torch.zeros((T, B, H), device=dev, dtype=torch.float32)         # d gh_n
+        dh_part = [torch.empty((B, H), device=dev), torch.empty((B, H), device=dev)]
+        dhm, have_part = None, False
+        for t in range(T - 1, -1, -1):
+            pr = _lib.GruGateBwd()
+            pr.B, pr.H, pr.act, pr.t = B, H, act, t
+            pr.dh_partial = dh_part[(t + 1) & 1].data_ptr() if have_part else None
+            for g in range(3):
+                pr.dhm[g] = dhm[g].data_ptr() if dhm is not None else None
+                pr.hmask[g] = hmask[g].data_ptr() if hmask is not None else None
+                pr.da[g] = dA[g, t].data_ptr()
+            pr.dx_last, pr.last_pos = dx.data_ptr(), last_pos.data_ptr()
+            pr.r, pr.i, pr.n = r[t].data_ptr(), i[t].data_ptr(), n[t].data_ptr()
+            pr.gh_n = ghn[t].data_ptr() if t > 0 else None
+            pr.h_prev = hs[t - 1].data_ptr() if t > 0 else None
+            pr.dgh_n, pr.dh_partial_out = dghn[t].data_ptr(), dh_part[t & 1].data_ptr()
+            _lib.check(L.vqa_gru_gate_bwd(C.byref(pr), _stream()), "vqa_gru_gate_bwd")
+            have_part = True
+            if t > 0:       # gradients of the masked copies of h_{t-1}: dgrad only, the wgrad of all steps follows below
+                _, _, dhm = linear_backward([hm[0, t - 1], hm[1, t - 1], hm[2, t - 1]], wh, [None] * 3,
+                                            [dA[0, t], dA[1, t], dghn[t]], 0, 0.0, 0, [0, 0, 0], True, math,
+                                            dws=[None] * 3, dbs=[None] * 3)
+        dwh = [torch.zeros_like(w) for w in wh]
+        if T > 1:
+            linear_backward([hm[g, :T - 1].reshape(-1, H) for g in range(3)], wh, [None] * 3,
+                            [dA[0, 1:].reshape(-1, H), dA[1, 1:].reshape(-1, H), dghn[1:].reshape(-1, H)], 0, 0.0, 0,
+                            [0, 0, 0], False, math, dws=dwh, dbs=[None] * 3)
+        dX = torch.empty((3, T * B, I), device=dev, dtype=torch.float32) if need_emb else None
+        dwi, dbi, _ = linear_backward([X[0], X[1], X[2]], wi, [None] * 3, [dA[g].reshape(-1, H) for g in range(3)], 0,
+                                      0.0, 0, [0, 0, 0], need_emb, math,
+                                      dxs=[dX[0], dX[1], dX[2]] if need_emb else [None] * 3)
+        demb = None
+        if need_emb:
+            demb = torch.zeros(emb_shape, device=dev, dtype=torch.float32)
+            _lib.check(L.vqa_gru_embed_bwd(B, T, I, idx.data_ptr(), _p(imask), dX.data_ptr(), demb.data_ptr(), _stream()),
+                       "vqa_gru_embed_bwd")
+        return (None, demb, dwi[0], dbi[0], dwi[1], dbi[1], dwi[2], dbi[2], dwh[0], dwh[1], dwh[2], None, None, None, None)
+
+
 # =========================================================================== loss
 class KldLogSoftmaxFn(torch.autograd.Function):
     """KLDivLoss(size_average=False)(log_softmax(x,1), a) — train.py:536-544."""
@@ -590,8 +713,10 @@ class ModelCoreFn(torch.autograd.Function):
         pr.grads_flat, pr.grads_flat_bytes = flat.data_ptr(), flat.numel() * 4
         for k, ev in enumerate(getattr(sink, "group_events", None) or ()):
             pr.group_events[k] = ev.cuda_event      # recorded by the plan as gradient group k completes
+        dq = torch.empty_like(qc) if ctx.needs_input_grad[2] else None     # a trainable question encoder in front
+        pr.dq = _p(dq)
         _lib.check(getattr(L, bwd)(C.byref(pr), _stream()), bwd)
         if sink is not None:
             sink.after_backward()
         ctx.keep = None
-        return (None, None, None, None, None, None, None, None, None, None, *ret)
+        return (None, None, dq, None, None, None, None, None, None, None, *ret)

@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--no-overlap", action="store_true",
                     help="N>1: run the gradient all-reduce after the graph replay instead of capturing it, bucket by "
                          "bucket, inside the backward")
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1 gradient all-reduce: libvqacore's NVLink peer-memory kernel (peer), NCCL, or auto = peer "
+                         "when symmetric memory can be set up")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -288,7 +291,7 @@ def workload_config(args, C, batch=None):
             "precision": args.precision, "parallelism": "dp%d" % args.gpus,
             "allreduce": getattr(args, "allreduce", None) or (
                 "none (1 GPU)" if args.gpus == 1 else
-                "bucketed NCCL all-reduce captured inside the step graph, overlapped with the backward"),
+                "bucketed all-reduce captured inside the step graph, overlapped with the backward"),
             "l2": "inputs rotate over 4 distinct batches and each step touches >0.6 GB of activations (> 126 MB L2)",
             "input_format": "region features stored as bf16 shards (values bf16-representable in both arms); e2e ships them "
                             "as bf16 over PCIe from pinned memory and widens them on the device"}
@@ -316,7 +319,7 @@ def run_ours(args):
     model = cf.Model(None, C, num_regions=N, precision=args.precision).to(dev)
     model.train(not args.eval_mode)
     ops.manual_seed(1234 + rank)
-    engine = DataParallelEngine(model)
+    engine = DataParallelEngine(model, allreduce=args.transport)
     engine.broadcast_parameters()
 
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -345,8 +348,10 @@ def run_ours(args):
             torch.cuda.synchronize()
             overlap = False
             graphed = GraphedStep(model, example, engine, capture_collectives=False)
-        args.allreduce = ("bucketed NCCL all-reduce captured inside the step graph, overlapped with the backward" if overlap
-                          else "bucketed NCCL all-reduce after the graph replay") if world > 1 else "none (1 GPU)"
+        what = ("libvqacore peer-memory all-reduce over NVLink (vqa_peer_allreduce_f32, no shared memory: runs next to "
+                "the backward's GEMMs)" if engine.transport == "peer" else "NCCL all-reduce")
+        args.allreduce = ("bucketed %s captured inside the step graph, overlapped with the backward" % what if overlap
+                          else "bucketed %s after the graph replay" % what) if world > 1 else "none (1 GPU)"
 
     def step(v, q, a):
         if graphed is None:
@@ -376,6 +381,8 @@ def run_ours(args):
     if graphed is not None:
         launches = graphed.launches_per_replay * args.steps
     ms = e0.elapsed_time(e1)
+    if engine.peer_error():
+        raise RuntimeError("a peer all-reduce gave up waiting for another rank: the timed steps are invalid")
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

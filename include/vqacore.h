@@ -424,6 +424,30 @@ int vqa_kld_logsoftmax_fwd_bwd(const vqa_kld_logsoftmax_params* p, void* stream)
  * reference's fp32 h5 features, datasets.py:517-549, :905-970) are widened to the fp32 tensor the plans read.  Exact. */
 int vqa_cast_bf16_f32(int64_t n, const void* src_bf16, float* dst, void* stream);
 /* ------------------------------------------------------------------------------------------
+ * Gradient all-reduce over NVLink peer memory: the ONE collective of data-parallel training (replaces the
+ * gradient gather of nn.DataParallel, train.py:517).  buffers[r] / signals[r] are rank r's gradient buffer and signal
+ * buffer AS MAPPED IN THE CALLING PROCESS (symmetric allocations exchanged once by the host side, e.g. CUDA IPC or
+ * torch symmetric memory); every rank calls this with the same offset / count in the same order on its own stream.
+ * In place: on return (stream order) buffers[rank][offset .. offset+count) holds the sum over the ranks, bit-identical
+ * on every rank (each element is summed by one rank in rank order and broadcast).  The signal buffer
+ * (vqa_peer_allreduce_signal_bytes() bytes per rank) must be zeroed once before the first call.  The kernel takes no
+ * shared memory: it runs next to the persistent GEMMs of the backward instead of displacing them.
+ * spin_limit_ms > 0: a rank that waits longer than that for a peer sets word [last] of its signal buffer to 1 and
+ * gives up instead of hanging (the result is then invalid); 0 = wait forever. */
+#define VQA_AR_MAX_WORLD 8
+#define VQA_AR_MAX_CTAS 160
+typedef struct {
+  int world, rank;
+  void* buffers[VQA_AR_MAX_WORLD];
+  void* signals[VQA_AR_MAX_WORLD];
+  int64_t offset, count;     /* in floats, multiples of 4 */
+  int max_ctas;              /* 0 = default (128); every rank must pass the same value */
+  int spin_limit_ms;
+} vqa_peer_allreduce_params;
+size_t vqa_peer_allreduce_signal_bytes(void);
+int vqa_peer_allreduce_f32(const vqa_peer_allreduce_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * SkipThoughts question encoder (putils/__init__.py:878-985): nn.Embedding(V, 620, padding_idx=0) ->
  * BayesianGRU(620 -> 2400) -> the hidden state at each question's last non-PAD token.  The dense contractions are the
  * grouped linears above (the three input projections of ALL time steps in one launch, the three recurrent projections
@@ -549,6 +573,7 @@ typedef struct {
  */
 typedef struct { float* param; int64_t offset; int64_t numel; } vqa_param_segment;
 #define VQA_MAX_PARAM_SEGMENTS 64
+#define VQA_CLIP_SCRATCH_FLOATS 1024
 typedef struct {
   int nsegs;
   const vqa_param_segment* segs;   /* host array */
@@ -560,7 +585,8 @@ typedef struct {
   int64_t step;                    /* 1 for the first update */
   float max_norm;                  /* clip_grad_norm_'s max_norm; <= 0 disables clipping */
   int write_clipped_grads;         /* 1: grads_flat *= clip as clip_grad_norm_ does in place; 0: leave them */
-  float* scratch;                  /* 1 float of device memory (holds ||g||^2 on return) when clipping */
+  float* scratch;                  /* VQA_CLIP_SCRATCH_FLOATS floats of device memory when clipping: [0] holds ||g||^2 on
+                                      return, the rest the per-block partials of its fixed-order reduction */
   /* Optional device-resident optimizer clock, for a step captured in a CUDA graph (every replay must be the same
    * launch): when step_dev is non-NULL the call first enqueues *step_dev += 1 (and *lr_dev *= lr_gamma when lr_dev is
    * non-NULL and lr_gamma > 0 — ExponentialLR stepped BEFORE the optimizer, train.py:75-76, :296), then the update

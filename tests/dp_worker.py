@@ -42,6 +42,30 @@ def main():
         m.load_state_dict(sd)
         return m.to(dev).train(train)
 
+    # ---- 0. the transport itself: a bucket reduced by the engine's all-reduce equals the NCCL sum, and the peer
+    # kernel leaves BIT-identical results on every rank
+    m = fresh(False)
+    eng = DataParallelEngine(m)
+    want_transport = os.environ.get("VQA_ALLREDUCE", "auto")
+    if want_transport in ("peer", "nccl"):
+        assert eng.transport == want_transport, (eng.transport, want_transport)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    for rep in range(3):
+        eng.flat.copy_(torch.randn(eng.flat.shape, device=dev, generator=g))
+        ref = eng.flat.clone()
+        dist.all_reduce(ref)
+        eng.reduce_all(overlapped=False)
+        eng.wait()
+        torch.cuda.synchronize()
+        assert not eng.peer_error(), "a peer all-reduce timed out"
+        err = (eng.flat - ref).abs().max().item() / ref.abs().max().item()
+        assert err <= 1e-6, ("engine all-reduce differs from NCCL", err, eng.transport)
+        if eng.transport == "peer":
+            both = [torch.empty_like(eng.flat) for _ in range(world)]
+            dist.all_gather(both, eng.flat)
+            assert all(torch.equal(both[0], t) for t in both[1:]), "peer all-reduce results differ between ranks"
+    transport = eng.transport
+
     # ---- 1. gradient equality, eval mode (dropout masks are indexed per rank, so train mode has no 1-GPU twin)
     m = fresh(False)
     eng = DataParallelEngine(m)
@@ -79,7 +103,7 @@ def main():
     dist.all_gather(keys, m.seed_device)
     assert len({int(k.item()) for k in keys}) == world, "ranks drew the same dropout key"
     if rank == 0:
-        print("DP_OK worst gradient error %.2e (%s)" % worst, flush=True)
+        print("DP_OK transport %s, worst gradient error %.2e (%s)" % ((transport,) + worst), flush=True)
     torch.cuda.synchronize()
     dist.barrier()
     sys.stdout.flush()

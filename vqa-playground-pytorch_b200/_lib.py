@@ -129,6 +129,11 @@ class KldParams(C.Structure):
                 ("loss_rows", fp), ("dlogits", fp)]
 
 
+class PeerAllreduce(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("buffers", fp * 8), ("signals", fp * 8), ("offset", i64),
+                ("count", i64), ("max_ctas", C.c_int), ("spin_limit_ms", C.c_int)]
+
+
 class GruGateFwd(C.Structure):
     _fields_ = [("B", i64), ("H", i64), ("act", C.c_int), ("gi", fp * 3), ("gh", fp * 3), ("h_prev", fp),
                 ("hmask", fp * 3), ("h", fp), ("r", fp), ("i", fp), ("n", fp), ("hm", fp * 3)]
@@ -157,7 +162,7 @@ STRUCTS = {
     "vqa_region_softmax_pool_fwd_params": PoolFwd, "vqa_region_softmax_pool_bwd_params": PoolBwd,
     "vqa_cor_compound_fwd_params": CompoundFwd, "vqa_cor_compound_bwd_params": CompoundBwd,
     "vqa_oda_pair_attn_fwd_params": OdaFwd, "vqa_oda_pair_attn_bwd_params": OdaBwd,
-    "vqa_kld_logsoftmax_params": KldParams, "vqa_gru_gate_fwd_params": GruGateFwd, "vqa_gru_gate_bwd_params": GruGateBwd,
+    "vqa_kld_logsoftmax_params": KldParams, "vqa_peer_allreduce_params": PeerAllreduce, "vqa_gru_gate_fwd_params": GruGateFwd, "vqa_gru_gate_bwd_params": GruGateBwd,
     "vqa_model_fwd_params": ModelFwd, "vqa_model_bwd_params": ModelBwd,
 }
 
@@ -188,6 +193,8 @@ SYMBOLS = {
     "vqa_cor_compound_fwd": _OP(CompoundFwd), "vqa_cor_compound_bwd": _OP(CompoundBwd),
     "vqa_oda_pair_attn_fwd": _OP(OdaFwd), "vqa_oda_pair_attn_bwd": _OP(OdaBwd),
     "vqa_kld_logsoftmax_fwd_bwd": _OP(KldParams),
+    "vqa_peer_allreduce_signal_bytes": (C.c_size_t, []),
+    "vqa_peer_allreduce_f32": _OP(PeerAllreduce),
     "vqa_seq_dropout_masks": (C.c_int, [C.c_float, C.c_uint64, C.c_void_p, C.c_uint32, i64, i64, C.c_int, C.c_void_p,
                                         C.c_void_p]),
     "vqa_gru_embed_fwd": (C.c_int, [i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -147,6 +147,7 @@ extern "C" size_t vqa_sizeof(const char* name) {
   VQA_SZ(vqa_oda_pair_attn_fwd_params);
   VQA_SZ(vqa_oda_pair_attn_bwd_params);
   VQA_SZ(vqa_kld_logsoftmax_params);
+  VQA_SZ(vqa_peer_allreduce_params);
   VQA_SZ(vqa_gru_gate_fwd_params);
   VQA_SZ(vqa_gru_gate_bwd_params);
   VQA_SZ(vqa_model_fwd_params);

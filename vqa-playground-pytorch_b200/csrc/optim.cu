@@ -8,8 +8,12 @@ namespace vqa {
 
 constexpr int OPT_THREADS = 256;
 
-// out[0] += sum of squares of g[0..n)   (out zeroed by the caller's memset; block tree + one atomic per block)
-__global__ void __launch_bounds__(OPT_THREADS) sumsq_kernel(int64_t n, const float* __restrict__ g, float* __restrict__ out) {
+// Sum of squares of g[0..n) with a FIXED reduction order (bit-identical on every data-parallel rank and every run:
+// a float atomicAdd per block made the clip coefficient, and after one step the parameters, differ in the last bit
+// between ranks).  Stage 1: block b writes its partial to part[1 + b].  Stage 2 (sumsq_final_kernel, one warp-tree
+// over the <= OPT_MAX_PARTIALS partials): part[0] = total.
+constexpr int OPT_MAX_PARTIALS = VQA_CLIP_SCRATCH_FLOATS - 1;
+__global__ void __launch_bounds__(OPT_THREADS) sumsq_kernel(int64_t n, const float* __restrict__ g, float* __restrict__ part) {
   __shared__ float red[OPT_THREADS / 32];
   float s = 0.0f;
   const int64_t n4 = n / 4;
@@ -26,7 +30,20 @@ __global__ void __launch_bounds__(OPT_THREADS) sumsq_kernel(int64_t n, const flo
   if (threadIdx.x < 32) {
     float t = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.0f;
     t = warp_sum(t);
-    if (threadIdx.x == 0) atomicAdd(out, t);
+    if (threadIdx.x == 0) part[1 + blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(OPT_THREADS) sumsq_final_kernel(int nparts, float* __restrict__ part) {
+  __shared__ float red[OPT_THREADS / 32];
+  float s = 0.0f;
+  for (int t = threadIdx.x; t < nparts; t += OPT_THREADS) s += part[1 + t];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < OPT_THREADS / 32 ? red[threadIdx.x] : 0.0f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) part[0] = t;
   }
 }
 
@@ -85,7 +102,7 @@ extern "C" int vqa_clip_adam_step(const vqa_clip_adam_params* p, void* stream) {
   VQA_REQUIRE((p->step >= 1 || p->step_dev) && p->beta1 >= 0.0f && p->beta1 < 1.0f && p->beta2 >= 0.0f &&
                   p->beta2 < 1.0f && p->eps >= 0.0f,
               "vqa_clip_adam_step: bad hyper-parameter (step counts from 1)");
-  VQA_REQUIRE(p->max_norm <= 0.0f || p->scratch, "vqa_clip_adam_step: clipping needs the 1-float scratch");
+  VQA_REQUIRE(p->max_norm <= 0.0f || p->scratch, "vqa_clip_adam_step: clipping needs the VQA_CLIP_SCRATCH_FLOATS scratch");
   VQA_REQUIRE(reinterpret_cast<uintptr_t>(p->grads_flat) % 16 == 0, "vqa_clip_adam_step: grads_flat must be 16-byte aligned");
   int64_t biggest = 0;
   SegTable tab = {};
@@ -99,11 +116,13 @@ extern "C" int vqa_clip_adam_step(const vqa_clip_adam_params* p, void* stream) {
   if (p->nsegs == 0 || biggest == 0) return VQA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->max_norm > 0.0f) {
-    cudaMemsetAsync(p->scratch, 0, sizeof(float), st);
     int64_t blocks = cdiv(p->total / 4 + 1, OPT_THREADS);
     if (blocks > 4 * (int64_t)sm_count()) blocks = 4 * (int64_t)sm_count();
+    if (blocks > OPT_MAX_PARTIALS) blocks = OPT_MAX_PARTIALS;
     sumsq_kernel<<<(unsigned)blocks, OPT_THREADS, 0, st>>>(p->total, p->grads_flat, p->scratch);
     VQA_TRY(check_launch("sumsq"));
+    sumsq_final_kernel<<<1, OPT_THREADS, 0, st>>>((int)blocks, p->scratch);
+    VQA_TRY(check_launch("sumsq_final"));
   }
   if (p->step_dev) {
     adam_tick_kernel<<<1, 1, 0, st>>>(p->step_dev, p->lr_dev, p->lr_gamma);

@@ -54,7 +54,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         dev = sink.flat.device
         self.exp_avg = torch.zeros_like(sink.flat)
         self.exp_avg_sq = torch.zeros_like(sink.flat)
-        self.scratch = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.scratch = torch.zeros(1024, device=dev, dtype=torch.float32)      # VQA_CLIP_SCRATCH_FLOATS
         self.step_count = 0
         self.device_clock = bool(device_clock)
         self.lr_gamma = float(lr_gamma) if lr_gamma else 0.0
@@ -102,7 +102,7 @@ class FusedClipAdam(torch.optim.Optimizer):
 
     def grad_norm(self):
         """||g||_2 of the last step (device tensor; only meaningful when clipping is on)."""
-        return self.scratch.sqrt()
+        return self.scratch[:1].sqrt()
 
     # ---- checkpointing (train.py:250-284 saves / restores optimizer.state_dict()) -------------------------------
     def state_dict(self):

@@ -1,4 +1,5 @@
-"""Data-parallel training support: one process per GPU, gradients all-reduced over NCCL.
+"""Data-parallel training support: one process per GPU, gradients all-reduced over NVLink peer memory
+(libvqacore's own kernel, vqa_peer_allreduce_f32) or over NCCL.
 
 Replaces the reference's only multi-GPU mechanism, single-process `nn.DataParallel`
 (train.py:517): every sample is independent through the whole forward, so the batch is
@@ -13,7 +14,17 @@ contiguous buckets; a bucket is all-reduced on a side stream as soon as the back
 enqueued its last producer, so communication overlaps the remaining backward kernels.
 The host logic (layout, bucketing, reduction semantics) also runs on CPU tensors with the
 gloo backend, which is how tests/test_parallel.py covers world_size 2 without GPUs.
+
+Two transports for the one collective:
+  "peer"  the flat buffer is SYMMETRIC memory (torch.distributed._symmetric_memory: the same allocation on every
+          GPU, mapped into every process); vqa_peer_allreduce_f32 reduces a bucket in place with loads / stores over
+          NVLink, uses no shared memory (its CTAs sit next to the persistent GEMMs of the backward instead of taking
+          their SMs) and leaves bit-identical sums on every rank;
+  "nccl"  dist.all_reduce on the communication stream (any backend; the only choice on CPU / gloo).
 """
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -46,13 +57,15 @@ def plan_buckets(sizes_in_order, num_buckets):
 class GradSink:
     """Flat gradient buffer + its per-parameter views (see module docstring)."""
 
-    def __init__(self, params, model_name, num_buckets=4):
+    def __init__(self, params, model_name, num_buckets=4, alloc=None):
         order = [i for grp in COMPLETION_ORDER[model_name] for i in grp]
         assert sorted(order) == list(range(len(params))), "completion order must cover every parameter once"
         self.order = order
         dev = params[0].device
         total = sum(p.numel() for p in params)
-        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        # `alloc(n)` supplies the storage (symmetric memory for the peer transport); it may return more than n elements
+        self.storage = alloc(total) if alloc is not None else torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat = self.storage[:total]
         self.slices = [None] * len(params)
         offsets, off = {}, 0
         for i in order:
@@ -68,6 +81,13 @@ class GradSink:
         for g0, g1 in self.bucket_groups:
             first, last = groups[g0][0], groups[g1 - 1][-1]
             self.bucket_ranges.append((offsets[first][0], offsets[last][1]))
+        # 16-byte vector transport: interior boundaries move DOWN to a multiple of 4 floats (the <= 3 elements that
+        # change sides wait for the later bucket, whose groups complete later), the end moves up into the padding
+        self.vector_ranges = []
+        for k, (lo, hi) in enumerate(self.bucket_ranges):
+            lo4 = lo // 4 * 4
+            hi4 = hi // 4 * 4 if k + 1 < len(self.bucket_ranges) else (hi + 3) // 4 * 4
+            self.vector_ranges.append((lo4, hi4))
         self.accumulate = False
         self.params = list(params)
         self.offsets = [offsets[i] for i in range(len(params))]      # (first, last) element of each parameter's slice
@@ -93,12 +113,26 @@ class DataParallelEngine(GradSink):
         loss = ...; loss.backward(); engine.wait()    # grads now hold the global SUM
     """
 
-    def __init__(self, model, num_buckets=4, process_group=None):
+    def __init__(self, model, num_buckets=4, process_group=None, allreduce="auto"):
+        """allreduce: "peer" (NVLink peer-memory kernel; CUDA, one node, <= 8 ranks), "nccl" (dist.all_reduce), or
+        "auto" = peer when it can be set up, else nccl (VQA_ALLREDUCE overrides "auto")."""
         self.model = model
         self.group = process_group
         params = model.core_parameters()
-        super().__init__(params, model.MODEL, num_buckets)
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        if allreduce == "auto":
+            allreduce = os.environ.get("VQA_ALLREDUCE", "auto")
+        if allreduce not in ("auto", "peer", "nccl"):
+            raise ValueError("allreduce must be 'auto', 'peer' or 'nccl', got %r" % (allreduce,))
+        self.peer = None
+        alloc = None
+        if self.world_size > 1 and params[0].is_cuda and allreduce in ("auto", "peer"):
+            alloc = self._symmetric_alloc(params[0].device, strict=allreduce == "peer")
+        super().__init__(params, model.MODEL, num_buckets, alloc=alloc)
+        if alloc is not None and self._symm is not None:
+            self._rendezvous_peers()
+        self.transport = "peer" if self.peer is not None else ("nccl" if self.world_size > 1 else "none")
         self.is_cuda = self.flat.is_cuda
         self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.is_cuda else None
         self._pending = []
@@ -112,6 +146,80 @@ class DataParallelEngine(GradSink):
             for ev in self.group_events:
                 ev.record()             # creates the handle (torch events are lazy)
         model.grad_sink = self
+
+    # ---- peer transport ---------------------------------------------------------------------------------------
+    def _symmetric_alloc(self, device, strict):
+        """Returns alloc(n) -> zeroed symmetric fp32 storage of >= n elements (padded to 16 bytes), or None when
+        symmetric memory is unavailable (strict: raise instead)."""
+        self._symm = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            if self.world_size > 8:
+                raise RuntimeError("the peer transport handles up to 8 ranks of one node")
+            self._symm = symm
+        except Exception as exc:
+            if strict:
+                raise RuntimeError("allreduce='peer' requested but symmetric memory is unavailable: %s" % exc)
+            return None
+
+        def alloc(n):
+            try:
+                t = self._symm.empty((n + 3) // 4 * 4, dtype=torch.float32, device=device)
+                t.zero_()
+                return t
+            except Exception as exc:
+                if strict:
+                    raise RuntimeError("allreduce='peer': symmetric allocation failed: %s" % exc)
+                self._symm = None
+                return torch.zeros(n, device=device, dtype=torch.float32)
+        return alloc
+
+    def _rendezvous_peers(self):
+        """Exchange the mappings of the gradient and signal buffers (collective); falls back to NCCL on failure."""
+        from . import _lib
+        try:
+            group = self.group if self.group is not None else dist.group.WORLD
+            if hasattr(self._symm, "enable_symm_mem_for_group"):
+                try:
+                    self._symm.enable_symm_mem_for_group(group.group_name)
+                except Exception:
+                    pass
+            nsig = int(_lib.lib().vqa_peer_allreduce_signal_bytes()) // 4
+            self._signals = self._symm.empty(nsig, dtype=torch.int32, device=self.storage.device)
+            self._signals.zero_()
+            hb = self._symm.rendezvous(self.storage, group)
+            hs = self._symm.rendezvous(self._signals, group)
+            ok = torch.tensor([1], device=self.storage.device)
+        except Exception as exc:
+            if os.environ.get("VQA_ALLREDUCE") == "peer":
+                raise
+            import warnings
+            warnings.warn("peer all-reduce unavailable (%s); using NCCL" % exc)
+            ok = torch.tensor([0], device=self.storage.device)
+            hb = hs = None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # every rank or none
+        torch.cuda.synchronize()
+        if int(ok.item()) == 1:
+            self._handles = (hb, hs)
+            self.peer = {"buffers": [int(x) for x in hb.buffer_ptrs], "signals": [int(x) for x in hs.buffer_ptrs]}
+            self.peer_max_ctas = int(os.environ.get("VQA_PEER_CTAS", "0"))
+            self.peer_spin_ms = int(os.environ.get("VQA_PEER_SPIN_MS", "20000"))
+
+    def peer_error(self):
+        """True when a peer all-reduce gave up waiting for another rank (vqa_peer_allreduce_params.spin_limit_ms)."""
+        return self.peer is not None and int(self._signals[-1].item()) != 0
+
+    def _peer_reduce(self, k):
+        from . import _lib
+        lo, hi = self.vector_ranges[k]
+        pr = _lib.PeerAllreduce()
+        pr.world, pr.rank = self.world_size, self.rank
+        for r in range(self.world_size):
+            pr.buffers[r], pr.signals[r] = self.peer["buffers"][r], self.peer["signals"][r]
+        pr.offset, pr.count = lo, hi - lo
+        pr.max_ctas, pr.spin_limit_ms = self.peer_max_ctas, self.peer_spin_ms
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().vqa_peer_allreduce_f32(C.byref(pr), stream), "vqa_peer_allreduce_f32")
 
     def broadcast_parameters(self, src=0):
         """Every rank starts from rank 0's weights (the reference's DataParallel replicates each step)."""
@@ -134,7 +242,10 @@ class DataParallelEngine(GradSink):
             else:
                 self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
-                self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                if self.peer is not None:
+                    self._peer_reduce(k)
+                else:
+                    self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         else:
             self._pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 

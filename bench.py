@@ -348,8 +348,9 @@ def run_ours(args):
             torch.cuda.synchronize()
             overlap = False
             graphed = GraphedStep(model, example, engine, capture_collectives=False)
-        what = ("libvqacore peer-memory all-reduce over NVLink (vqa_peer_allreduce_f32, no shared memory: runs next to "
-                "the backward's GEMMs)" if engine.transport == "peer" else "NCCL all-reduce")
+        what = ("libvqacore peer-memory all-reduce over NVLink (vqa_peer_allreduce_f32%s, no shared memory: runs next to "
+                "the backward's GEMMs)" % (", NVLS in-switch reduction" if engine.nvls else "")
+                if engine.transport == "peer" else "NCCL all-reduce")
         args.allreduce = ("bucketed %s captured inside the step graph, overlapped with the backward" % what if overlap
                           else "bucketed %s after the graph replay" % what) if world > 1 else "none (1 GPU)"
 

@@ -443,6 +443,9 @@ typedef struct {
   int64_t offset, count;     /* in floats, multiples of 4 */
   int max_ctas;              /* 0 = default (128); every rank must pass the same value */
   int spin_limit_ms;
+  void* multicast;           /* optional: the MULTICAST mapping of the same symmetric buffer (NVLS).  When non-NULL the
+                                slice is reduced inside the NVSwitch (multimem.ld_reduce) and broadcast by it
+                                (multimem.st): half the NVLink bytes of the peer loads + stores.  All ranks or none. */
 } vqa_peer_allreduce_params;
 size_t vqa_peer_allreduce_signal_bytes(void);
 int vqa_peer_allreduce_f32(const vqa_peer_allreduce_params* p, void* stream);

@@ -103,7 +103,8 @@ def main():
     dist.all_gather(keys, m.seed_device)
     assert len({int(k.item()) for k in keys}) == world, "ranks drew the same dropout key"
     if rank == 0:
-        print("DP_OK transport %s, worst gradient error %.2e (%s)" % ((transport,) + worst), flush=True)
+        print("DP_OK transport %s%s, worst gradient error %.2e (%s)" % ((transport, " (NVLS)" if eng.nvls else "") + worst),
+              flush=True)
     torch.cuda.synchronize()
     dist.barrier()
     sys.stdout.flush()

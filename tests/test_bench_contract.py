@@ -74,6 +74,9 @@ def test_bucket_plan_properties():
     for _ in range(200):
         sizes = [rng.randint(1, 5000) for _ in range(rng.randint(1, 14))]
         nb = rng.randint(1, 6)
-        cuts = plan_buckets(sizes, nb)
+        tail = rng.randint(0, 3)
+        cuts = plan_buckets(sizes, nb, tail=tail)
         assert 1 <= len(cuts) <= nb and cuts[0][0] == 0 and cuts[-1][1] == len(sizes)
         assert all(a < b for a, b in cuts) and all(cuts[i][1] == cuts[i + 1][0] for i in range(len(cuts) - 1))
+        if tail and nb > 1 and len(sizes) > tail:
+            assert cuts[-1] == (len(sizes) - tail, len(sizes))       # the late groups form the last bucket alone

@@ -44,7 +44,20 @@ __device__ __forceinline__ void st_peer4(float4* p, const float4& v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// NVLS: one instruction on the MULTICAST mapping of the symmetric buffer makes the NVSwitch fetch the 16 bytes from every
+// GPU, add them and return the sum / replicate a store to every GPU — half the NVLink bytes of the peer loads+stores.
+__device__ __forceinline__ float4 mc_ld_reduce4(const float4* p) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st4(float4* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 struct ArArgs {
+  float* mc;                         // multicast mapping of the symmetric buffer (NVLS) or nullptr
   float* buf[AR_MAX_WORLD];          // every rank's buffer, as mapped in this process
   uint32_t* sig[AR_MAX_WORLD];       // every rank's signal buffer
   int world, rank;
@@ -116,6 +129,41 @@ __global__ void __launch_bounds__(AR_THREADS) peer_allreduce_kernel(ArArgs a) {
   ar_barrier(a, AR_END, e);                         // every slice is written on every rank
 }
 
+// NVLS variant: the slice of this rank is reduced in the switch and broadcast by it.
+__global__ void __launch_bounds__(AR_THREADS) peer_allreduce_mc_kernel(ArArgs a) {
+  __shared__ uint32_t epoch_s;
+  if (threadIdx.x == 0) {
+    uint32_t* ep = a.sig[a.rank] + AR_EPOCH + blockIdx.x;
+    epoch_s = *ep + 1u;
+    *ep = epoch_s;
+  }
+  __syncthreads();
+  const uint32_t e = epoch_s;
+  ar_barrier(a, AR_START, e);
+  const int64_t n4 = a.count >> 2;
+  const int64_t per = (n4 + a.world - 1) / a.world;
+  const int64_t lo = a.rank * per, hi = lo + per < n4 ? lo + per : n4;
+  float4* mc = reinterpret_cast<float4*>(a.mc) + (a.offset >> 2);
+  const int64_t stride = (int64_t)gridDim.x * AR_THREADS;
+  constexpr int U = 8;
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += U * stride) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < hi) v[u] = mc_ld_reduce4(mc + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < hi) mc_st4(mc + i, v[u]);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  ar_barrier(a, AR_END, e);
+}
+
 }  // namespace vqa
 
 using namespace vqa;
@@ -137,6 +185,8 @@ extern "C" int vqa_peer_allreduce_f32(const vqa_peer_allreduce_params* p, void* 
     a.sig[r] = reinterpret_cast<uint32_t*>(p->signals[r]);
   }
   a.world = p->world; a.rank = p->rank; a.offset = p->offset; a.count = p->count;
+  a.mc = reinterpret_cast<float*>(p->multicast);
+  VQA_REQUIRE((reinterpret_cast<uintptr_t>(p->multicast) & 15) == 0, "vqa_peer_allreduce_f32: multicast pointer must be 16-byte aligned");
   a.spin_limit = p->spin_limit_ms > 0 ? (long long)p->spin_limit_ms * 2000000ll : (1ll << 62);
   int ctas = p->max_ctas > 0 ? p->max_ctas : 128;
   if (ctas > AR_MAX_CTAS) ctas = AR_MAX_CTAS;
@@ -146,6 +196,10 @@ extern "C" int vqa_peer_allreduce_f32(const vqa_peer_allreduce_params* p, void* 
   // every rank must launch the same grid (CTA c meets CTA c): the grid depends on count and world only
   KProf kp_(stream, "peer_allreduce", "hbm", 4.0 * (double)p->count * 2.0 * (p->world - 1) / p->world);
   cudaStream_t st = (cudaStream_t)stream;
+  if (a.mc) {
+    peer_allreduce_mc_kernel<<<ctas, AR_THREADS, 0, st>>>(a);
+    return check_launch("peer_allreduce_mc");
+  }
   switch (p->world) {
     case 2: peer_allreduce_kernel<2><<<ctas, AR_THREADS, 0, st>>>(a); break;
     case 4: peer_allreduce_kernel<4><<<ctas, AR_THREADS, 0, st>>>(a); break;

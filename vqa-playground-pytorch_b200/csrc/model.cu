@@ -608,12 +608,23 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
   mark(1, ms);
   const cudaEvent_t e_ff = L->record(ms);          // dvf, dqf ready
   Lanes::wait(ss, e_ff);
+  // The four 2400->310 question projections are differentiated as soon as THEIR output gradient exists — linear_q
+  // here (dqf), compress_q_1/2 after the gates, only compress_q (dql) at the very end — so that three quarters of
+  // their 12 MB of weight gradients reach the all-reduce early instead of forming its exposed tail.
+  float* dqp[4] = {w.dq_parts, w.dq_parts + B * Q, w.dq_parts + 2 * B * Q, w.dq_parts + 3 * B * Q};
+  {
+    const float* X[1] = {p->q}; int64_t ldx[1] = {Q}; int widx[1] = {LINEAR_Q}; const float* Y[1] = {w.qf};
+    int64_t ldy[1] = {HP}; const float* dY[1] = {w.dqf}; int64_t lddy[1] = {HP}; uint32_t layer[1] = {L_LINEAR_Q};
+    float* dX[1] = {dqp[3]}; int64_t lddx[1] = {Q};
+    { ProfScope ps_(ss, "linear_q.bwd"); VQA_TRY(lin_bwd(cs, 1, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, bp->dq ? dX : nullptr, bp->dq ? lddx : nullptr, 0, layer)); }
+  }
+  mark(2, ss);
   { ProfScope ps_(ss, "att1.glimpse.bwd"); VQA_TRY(glimpse_bwd(cs, B, w.pooled1, ATT1_G, w.vf, w.dvf, 2 * A, 0, w.dpooled1, L_ATT1_G)); }
-  mark(6, ss);
+  mark(3, ss);
   const cudaEvent_t e_g1 = L->record(ss);          // dpooled1 initialised
   // ---- att2 branch
   { ProfScope ps_(stream, "att2.glimpse.bwd"); VQA_TRY(glimpse_bwd(c, B, w.pooled2, ATT2_G, w.vf, w.dvf, 2 * A, A, w.dpooled2, L_ATT2_G)); }
-  mark(2, ms);
+  mark(4, ms);
   {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
@@ -626,16 +637,16 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     ap.dx = nullptr;             // the pooling's share of dv2 is added by compress_v2's dgrad epilogue below
     { ProfScope ps_(stream, "att2.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
-  mark(3, ms);
+  mark(5, ms);
   { ProfScope ps_(stream, "fusion_vq2.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.v2l, HP, w.ql, HP, VQ2_L1, VQ2_L2, w.f2_H1, w.f2_H2, w.dfuse2, F, w.d_f2_H2, w.dv2l, HP, w.dql, HP, 0, w.vq2_w1p, w.vq2_w2p, b16 ? &x_vq2 : nullptr)); }
-  mark(4, ms);
+  mark(6, ms);
   {  // compress_v2: v2 feeds both compress_v2 and att2's pooling; the dgrad store adds sum_g alpha2 * dpooled2
     const float* X[1] = {p->v2}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V2}; const float* Y[1] = {w.v2l};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dv2l}; int64_t lddy[1] = {HP};
     float* dX[1] = {w.dv2}; int64_t lddx[1] = {D}; uint32_t layer[1] = {L_COMPRESS_V2};
     { ProfScope ps_(stream, "compress_v2.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, nullptr, p->alpha2, w.dpooled2, N, b16 ? &x_cv2 : nullptr)); }
   }
-  mark(5, ms);
+  mark(7, ms);
   // ---- att1 branch: the glimpse linears (side lane) initialise dpooled1, then the compound objects add to it
   Lanes::wait(ms, e_g1);
   {
@@ -656,7 +667,15 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     Lanes::wait(ss, L->record(ms));                // dg1, dg2 ready
     { ProfScope ps_(ss, "gates.bwd"); VQA_TRY(lin_bwd(cs, 2, B, H, D, VQA_ACT_SIGMOID, X, ldx, widx, Y, ldy, dY, lddy, dX, lddx, 0, layer, eqp)); }
   }
-  mark(7, ss);
+  mark(8, ss);
+  {  // compress_q_1 / compress_q_2 (the gates' first layers): dhq1, dhq2 were just written on this lane
+    const float* X[2] = {p->q, p->q}; int64_t ldx[2] = {Q, Q}; int widx[2] = {CQ1, CQ2};
+    const float* Y[2] = {w.hq1, w.hq2}; int64_t ldy[2] = {HP, HP}; const float* dY[2] = {w.dhq1, w.dhq2};
+    int64_t lddy[2] = {HP, HP}; uint32_t layer[2] = {L_CQ1, L_CQ2};
+    float* dX[2] = {dqp[1], dqp[2]}; int64_t lddx[2] = {Q, Q};
+    { ProfScope ps_(ss, "compress_q12.bwd"); VQA_TRY(lin_bwd(cs, 2, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, bp->dq ? dX : nullptr, bp->dq ? lddx : nullptr, 0, layer)); }
+  }
+  mark(9, ss);
   {
     vqa_region_softmax_pool_bwd_params ap = {};
     ap.B = B; ap.N = N; ap.Ff = F; ap.D = D;
@@ -668,27 +687,24 @@ extern "C" int vqa_cor2_bwd(const vqa_model_bwd_params* bp, void* stream) {
     ap.dWc = c.grad(ATT1_CONV); ap.dbc = c.grad(ATT1_CONV + 1); ap.dfuse = w.dfuse1; ap.dx = nullptr;
     { ProfScope ps_(stream, "att1.pool.bwd"); VQA_TRY(vqa_region_softmax_pool_bwd(&ap, stream)); }
   }
-  mark(8, ms);
+  mark(10, ms);
   { ProfScope ps_(stream, "fusion_vq1.bwd"); VQA_TRY(mutan_bwd(c, 2, M, H, H, N, w.vl, HP, w.ql, HP, VQ1_L1, VQ1_L2, w.f1_H1, w.f1_H2, w.dfuse1, F, w.d_f1_H2, w.dvl, HP, w.dql, HP, 1, w.vq1_w1p, w.vq1_w2p, b16 ? &x_vq1 : nullptr)); }
-  mark(9, ms);
+  mark(11, ms);
   Lanes::wait(ss, L->record(ms));                  // dql complete (fusion_vq2 + fusion_vq1)
   {  // compress_v: v is a graph input, no dgrad
     const float* X[1] = {p->v}; int64_t ldx[1] = {D}; int widx[1] = {COMPRESS_V}; const float* Y[1] = {w.vl};
     int64_t ldy[1] = {HP}; const float* dY[1] = {w.dvl}; int64_t lddy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_V};
     { ProfScope ps_(stream, "compress_v.bwd"); VQA_TRY(lin_bwd(c, 1, M, D, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, nullptr, nullptr, 0, layer, nullptr, nullptr, nullptr, 0, b16 ? &x_cv : nullptr)); }
   }
-  mark(10, ms);
-  {  // the four question projections
-    const float* X[4] = {p->q, p->q, p->q, p->q}; int64_t ldx[4] = {Q, Q, Q, Q};
-    int widx[4] = {COMPRESS_Q, CQ1, CQ2, LINEAR_Q}; const float* Y[4] = {w.ql, w.hq1, w.hq2, w.qf};
-    int64_t ldy[4] = {HP, HP, HP, HP}; const float* dY[4] = {w.dql, w.dhq1, w.dhq2, w.dqf}; int64_t lddy[4] = {HP, HP, HP, HP};
-    uint32_t layer[4] = {L_COMPRESS_Q, L_CQ1, L_CQ2, L_LINEAR_Q};
-    float* dX[4] = {w.dq_parts, w.dq_parts + B * Q, w.dq_parts + 2 * B * Q, w.dq_parts + 3 * B * Q};
-    int64_t lddx[4] = {Q, Q, Q, Q};
-    { ProfScope ps_(ss, "q_proj4.bwd"); VQA_TRY(lin_bwd(cs, 4, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, bp->dq ? dX : nullptr, bp->dq ? lddx : nullptr, 0, layer)); }
+  mark(12, ms);
+  {  // compress_q: its output gradient dql is complete only now (fusion_vq2 + fusion_vq1)
+    const float* X[1] = {p->q}; int64_t ldx[1] = {Q}; int widx[1] = {COMPRESS_Q}; const float* Y[1] = {w.ql};
+    int64_t ldy[1] = {HP}; const float* dY[1] = {w.dql}; int64_t lddy[1] = {HP}; uint32_t layer[1] = {L_COMPRESS_Q};
+    float* dX[1] = {dqp[0]}; int64_t lddx[1] = {Q};
+    { ProfScope ps_(ss, "compress_q.bwd"); VQA_TRY(lin_bwd(cs, 1, B, Q, H, VQA_ACT_RELU, X, ldx, widx, Y, ldy, dY, lddy, bp->dq ? dX : nullptr, bp->dq ? lddx : nullptr, 0, layer)); }
     if (bp->dq) VQA_TRY(sum_parts(B * Q, 4, w.dq_parts, bp->dq, ss));
   }
-  mark(11, ss);
+  mark(13, ss);
   Lanes::wait(ms, L->record(ss));                  // join
   return VQA_OK;
 }
@@ -699,10 +715,10 @@ extern "C" int vqa_grad_groups(int model, int* group_of_param, int n_params) {
   if (model == 0) {
     if (n_params != 62) return -1;
     auto set = [&](int a, int b, int g) { for (int i = a; i < b; ++i) group_of_param[i] = g; };
-    set(52, 54, 0); set(44, 52, 1); set(34, 42, 2); set(32, 34, 3); set(24, 32, 4); set(2, 4, 5); set(16, 24, 6);
-    set(56, 58, 7); set(60, 62, 7); set(14, 16, 8); set(6, 14, 9); set(0, 2, 10);
-    set(4, 6, 11); set(54, 56, 11); set(58, 60, 11); set(42, 44, 11);
-    return 12;
+    set(52, 54, 0); set(44, 52, 1); set(42, 44, 2); set(16, 24, 3); set(34, 42, 4); set(32, 34, 5); set(24, 32, 6);
+    set(2, 4, 7); set(56, 58, 8); set(60, 62, 8); set(54, 56, 9); set(58, 60, 9); set(14, 16, 10); set(6, 14, 11);
+    set(0, 2, 12); set(4, 6, 13);
+    return 14;
   }
   if (model == 1) {
     if (n_params != 38) return -1;

@@ -29,19 +29,24 @@ import torch
 import torch.distributed as dist
 
 # state_dict index groups in the order the backward plans (csrc/model.cu) finish them
-_COR2_ORDER = [[52, 53], list(range(44, 52)), list(range(34, 42)), [32, 33], list(range(24, 32)), [2, 3],
-               list(range(16, 24)), [56, 57, 60, 61], [14, 15], list(range(6, 14)), [0, 1],
-               [4, 5, 54, 55, 58, 59, 42, 43]]
+_COR2_ORDER = [[52, 53], list(range(44, 52)), [42, 43], list(range(16, 24)), list(range(34, 42)), [32, 33],
+               list(range(24, 32)), [2, 3], [56, 57, 60, 61], [54, 55, 58, 59], [14, 15], list(range(6, 14)), [0, 1],
+               [4, 5]]
 _ODA_ORDER = [[36, 37], list(range(16, 36)), list(range(6, 14)), [4, 5], [0, 1], [2, 3, 14, 15]]
 COMPLETION_ORDER = {"CoR2": _COR2_ORDER, "ODA": _ODA_ORDER}
 
 
-def plan_buckets(sizes_in_order, num_buckets):
+def plan_buckets(sizes_in_order, num_buckets, tail=0):
     """Cut a sequence of tensor sizes into <= num_buckets contiguous buckets of roughly equal bytes.
-    Returns a list of (first_index, last_index_exclusive)."""
-    total = sum(sizes_in_order)
+    tail > 0: the last `tail` entries form the final bucket on their own (the groups that complete at the very end of
+    the backward: their all-reduce is the part nothing can hide, so it is kept as small as the plan allows) and the
+    rest is cut into <= num_buckets - 1.  Returns a list of (first_index, last_index_exclusive)."""
     if not sizes_in_order:
         return []
+    if tail > 0 and num_buckets > 1 and len(sizes_in_order) > tail:
+        head = plan_buckets(sizes_in_order[:-tail], num_buckets - 1)
+        return head + [(len(sizes_in_order) - tail, len(sizes_in_order))]
+    total = sum(sizes_in_order)
     target = total / max(1, num_buckets)
     buckets, start, acc = [], 0, 0
     for i, s in enumerate(sizes_in_order):
@@ -54,10 +59,13 @@ def plan_buckets(sizes_in_order, num_buckets):
     return buckets
 
 
+TAIL_GROUPS = {"CoR2": 2, "ODA": 1}      # groups whose gradients appear only at the end of the backward plan
+
+
 class GradSink:
     """Flat gradient buffer + its per-parameter views (see module docstring)."""
 
-    def __init__(self, params, model_name, num_buckets=4, alloc=None):
+    def __init__(self, params, model_name, num_buckets=6, alloc=None):
         order = [i for grp in COMPLETION_ORDER[model_name] for i in grp]
         assert sorted(order) == list(range(len(params))), "completion order must cover every parameter once"
         self.order = order
@@ -75,7 +83,7 @@ class GradSink:
             off += n
         # buckets are cut at completion-group boundaries
         group_sizes = [sum(params[i].numel() for i in grp) for grp in COMPLETION_ORDER[model_name]]
-        self.bucket_groups = plan_buckets(group_sizes, num_buckets)
+        self.bucket_groups = plan_buckets(group_sizes, num_buckets, tail=TAIL_GROUPS.get(model_name, 0))
         self.bucket_ranges = []
         groups = COMPLETION_ORDER[model_name]
         for g0, g1 in self.bucket_groups:
@@ -113,7 +121,7 @@ class DataParallelEngine(GradSink):
         loss = ...; loss.backward(); engine.wait()    # grads now hold the global SUM
     """
 
-    def __init__(self, model, num_buckets=4, process_group=None, allreduce="auto"):
+    def __init__(self, model, num_buckets=6, process_group=None, allreduce="auto"):
         """allreduce: "peer" (NVLink peer-memory kernel; CUDA, one node, <= 8 ranks), "nccl" (dist.all_reduce), or
         "auto" = peer when it can be set up, else nccl (VQA_ALLREDUCE overrides "auto")."""
         self.model = model
@@ -133,6 +141,7 @@ class DataParallelEngine(GradSink):
         if alloc is not None and self._symm is not None:
             self._rendezvous_peers()
         self.transport = "peer" if self.peer is not None else ("nccl" if self.world_size > 1 else "none")
+        self.nvls = bool(self.peer and self.peer.get("multicast"))
         self.is_cuda = self.flat.is_cuda
         self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.is_cuda else None
         self._pending = []
@@ -202,6 +211,16 @@ class DataParallelEngine(GradSink):
         if int(ok.item()) == 1:
             self._handles = (hb, hs)
             self.peer = {"buffers": [int(x) for x in hb.buffer_ptrs], "signals": [int(x) for x in hs.buffer_ptrs]}
+            # NVLS: the multicast mapping of the gradient buffer, when the fabric offers one (all ranks or none)
+            mc = 0
+            if os.environ.get("VQA_PEER_MC", "1") != "0":
+                try:
+                    mc = int(hb.multicast_ptr or 0)
+                except Exception:
+                    mc = 0
+            flag = torch.tensor([1 if mc else 0], device=self.storage.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            self.peer["multicast"] = mc if int(flag.item()) == 1 else 0
             self.peer_max_ctas = int(os.environ.get("VQA_PEER_CTAS", "0"))
             self.peer_spin_ms = int(os.environ.get("VQA_PEER_SPIN_MS", "20000"))
 
@@ -218,6 +237,7 @@ class DataParallelEngine(GradSink):
             pr.buffers[r], pr.signals[r] = self.peer["buffers"][r], self.peer["signals"][r]
         pr.offset, pr.count = lo, hi - lo
         pr.max_ctas, pr.spin_limit_ms = self.peer_max_ctas, self.peer_spin_ms
+        pr.multicast = self.peer["multicast"] or None
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(_lib.lib().vqa_peer_allreduce_f32(C.byref(pr), stream), "vqa_peer_allreduce_f32")
 

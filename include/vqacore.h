@@ -441,7 +441,7 @@ typedef struct {
   void* buffers[VQA_AR_MAX_WORLD];
   void* signals[VQA_AR_MAX_WORLD];
   int64_t offset, count;     /* in floats, multiples of 4 */
-  int max_ctas;              /* 0 = default (128); every rank must pass the same value */
+  int max_ctas;              /* 0 = default (160 CTAs of 128 threads); every rank must pass the same value */
   int spin_limit_ms;
   void* multicast;           /* optional: the MULTICAST mapping of the same symmetric buffer (NVLS).  When non-NULL the
                                 slice is reduced inside the NVSwitch (multimem.ld_reduce) and broadcast by it

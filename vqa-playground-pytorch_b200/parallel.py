@@ -65,7 +65,7 @@ TAIL_GROUPS = {"CoR2": 2, "ODA": 1}      # groups whose gradients appear only at
 class GradSink:
     """Flat gradient buffer + its per-parameter views (see module docstring)."""
 
-    def __init__(self, params, model_name, num_buckets=6, alloc=None):
+    def __init__(self, params, model_name, num_buckets=4, alloc=None):
         order = [i for grp in COMPLETION_ORDER[model_name] for i in grp]
         assert sorted(order) == list(range(len(params))), "completion order must cover every parameter once"
         self.order = order
@@ -121,7 +121,7 @@ class DataParallelEngine(GradSink):
         loss = ...; loss.backward(); engine.wait()    # grads now hold the global SUM
     """
 
-    def __init__(self, model, num_buckets=6, process_group=None, allreduce="auto"):
+    def __init__(self, model, num_buckets=4, process_group=None, allreduce="auto"):
         """allreduce: "peer" (NVLink peer-memory kernel; CUDA, one node, <= 8 ranks), "nccl" (dist.all_reduce), or
         "auto" = peer when it can be set up, else nccl (VQA_ALLREDUCE overrides "auto")."""
         self.model = model

@@ -446,6 +446,7 @@ typedef struct {
   void* multicast;           /* optional: the MULTICAST mapping of the same symmetric buffer (NVLS).  When non-NULL the
                                 slice is reduced inside the NVSwitch (multimem.ld_reduce) and broadcast by it
                                 (multimem.st): half the NVLink bytes of the peer loads + stores.  All ranks or none. */
+  int cta_threads;           /* 0 / 128: light CTAs (default); 256: wide CTAs, more loads in flight.  Same on all ranks. */
 } vqa_peer_allreduce_params;
 size_t vqa_peer_allreduce_signal_bytes(void);
 int vqa_peer_allreduce_f32(const vqa_peer_allreduce_params* p, void* stream);

@@ -9,11 +9,8 @@ try:
 except Exception as e: print('FAILED', e, t[:300])
 " "$@"; grep -v "^\*\*\*\|OMP_NUM\|FutureWarning\|enable_symm" gpurun_out/multi_err.log | tail -3 | cut -c1-300; }
 run --transport peer
-VQA_PEER_MC=0 run --transport peer
-run --transport peer --no-overlap
-run --transport nccl
+VQA_PEER_THREADS=256 run --transport peer
+VQA_PEER_THREADS=256 VQA_BUCKETS=6 run --transport peer
 run --transport peer --batch 512
 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('1 GPU batch 256 ->', round(d['value']), 'samples/s', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']))"
-python bench.py --steps 30 --warmup 5 --no-cpu-baseline --batch 512 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('1 GPU batch 512 ->', round(d['value']), 'samples/s', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']))"

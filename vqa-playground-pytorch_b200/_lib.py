@@ -131,7 +131,7 @@ class KldParams(C.Structure):
 
 class PeerAllreduce(C.Structure):
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("buffers", fp * 8), ("signals", fp * 8), ("offset", i64),
-                ("count", i64), ("max_ctas", C.c_int), ("spin_limit_ms", C.c_int), ("multicast", fp)]
+                ("count", i64), ("max_ctas", C.c_int), ("spin_limit_ms", C.c_int), ("multicast", fp), ("cta_threads", C.c_int)]
 
 
 class GruGateFwd(C.Structure):

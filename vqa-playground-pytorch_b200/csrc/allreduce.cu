@@ -19,7 +19,8 @@ namespace vqa {
 
 constexpr int AR_MAX_WORLD = VQA_AR_MAX_WORLD;
 constexpr int AR_MAX_CTAS = VQA_AR_MAX_CTAS;
-constexpr int AR_THREADS = 128;      // small CTAs of <= 48 registers: several fit beside a 320-thread GEMM CTA of 128 registers
+constexpr int AR_THREADS = 128;      // default: small CTAs of <= 48 registers, several fit beside a 320-thread GEMM CTA of 128 registers
+constexpr int AR_THREADS_WIDE = 256; // cta_threads = 256: twice the loads in flight per CTA (faster alone, heavier beside the GEMMs)
 // signal buffer layout (uint32 words): start[c][src], end[c][src], epoch[c], error flag
 constexpr int AR_START = 0;
 constexpr int AR_END = AR_MAX_CTAS * AR_MAX_WORLD;
@@ -79,8 +80,9 @@ __device__ __forceinline__ void ar_barrier(const ArArgs& a, int slot, uint32_t e
   __syncthreads();
 }
 
-template <int W>       // W = world size as a compile-time constant (0: generic)
-__global__ void __launch_bounds__(AR_THREADS, 10) peer_allreduce_kernel(ArArgs a) {
+template <int W, int THREADS>       // W = world size as a compile-time constant (0: generic)
+__global__ void __launch_bounds__(THREADS, THREADS == AR_THREADS ? 10 : 2) peer_allreduce_kernel(ArArgs a) {
+  constexpr int AR_THREADS = THREADS;
   __shared__ uint32_t epoch_s;
   const int world = W > 0 ? W : a.world;
   if (threadIdx.x == 0) {
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(AR_THREADS, 10) peer_allreduce_kernel(ArArgs a
   const int64_t lo = a.rank * per, hi = lo + per < n4 ? lo + per : n4;
   const int64_t base4 = a.offset >> 2;
   const int64_t stride = (int64_t)gridDim.x * AR_THREADS;
-  constexpr int U = W == 2 ? 4 : (W == 4 ? 2 : 1);  // independent elements per thread and iteration: 8 peer loads in flight
+  constexpr int U = (W == 2 ? 4 : (W == 4 ? 2 : 1)) * (THREADS == 128 ? 1 : 2);  // independent elements per thread and iteration
   for (int64_t i0 = lo + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += U * stride) {
     float4 acc[U];
 #pragma unroll
@@ -130,7 +132,9 @@ __global__ void __launch_bounds__(AR_THREADS, 10) peer_allreduce_kernel(ArArgs a
 }
 
 // NVLS variant: the slice of this rank is reduced in the switch and broadcast by it.
-__global__ void __launch_bounds__(AR_THREADS, 10) peer_allreduce_mc_kernel(ArArgs a) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == AR_THREADS ? 10 : 2) peer_allreduce_mc_kernel(ArArgs a) {
+  constexpr int AR_THREADS = THREADS;
   __shared__ uint32_t epoch_s;
   if (threadIdx.x == 0) {
     uint32_t* ep = a.sig[a.rank] + AR_EPOCH + blockIdx.x;
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(AR_THREADS, 10) peer_allreduce_mc_kernel(ArArg
   const int64_t lo = a.rank * per, hi = lo + per < n4 ? lo + per : n4;
   float4* mc = reinterpret_cast<float4*>(a.mc) + (a.offset >> 2);
   const int64_t stride = (int64_t)gridDim.x * AR_THREADS;
-  constexpr int U = 4;
+  constexpr int U = THREADS == 128 ? 4 : 8;
   for (int64_t i0 = lo + (int64_t)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += U * stride) {
     float4 v[U];
 #pragma unroll
@@ -188,23 +192,33 @@ extern "C" int vqa_peer_allreduce_f32(const vqa_peer_allreduce_params* p, void* 
   a.mc = reinterpret_cast<float*>(p->multicast);
   VQA_REQUIRE((reinterpret_cast<uintptr_t>(p->multicast) & 15) == 0, "vqa_peer_allreduce_f32: multicast pointer must be 16-byte aligned");
   a.spin_limit = p->spin_limit_ms > 0 ? (long long)p->spin_limit_ms * 2000000ll : (1ll << 62);
-  int ctas = p->max_ctas > 0 ? p->max_ctas : 160;
+  const bool wide = p->cta_threads == AR_THREADS_WIDE;
+  VQA_REQUIRE(p->cta_threads == 0 || p->cta_threads == AR_THREADS || wide, "vqa_peer_allreduce_f32: cta_threads must be 0, 128 or 256");
+  const int threads = wide ? AR_THREADS_WIDE : AR_THREADS;
+  int ctas = p->max_ctas > 0 ? p->max_ctas : (wide ? 128 : 160);
   if (ctas > AR_MAX_CTAS) ctas = AR_MAX_CTAS;
   const int64_t slice4 = (p->count / 4 + p->world - 1) / p->world;
-  const int64_t want = cdiv(slice4, AR_THREADS * 4);
+  const int64_t want = cdiv(slice4, threads * (wide ? 8 : 4));
   if (want < ctas) ctas = (int)(want < 1 ? 1 : want);
-  // every rank must launch the same grid (CTA c meets CTA c): the grid depends on count and world only
+  // every rank must launch the same grid (CTA c meets CTA c): the grid depends on count, world and the options only
   KProf kp_(stream, "peer_allreduce", "hbm", 4.0 * (double)p->count * 2.0 * (p->world - 1) / p->world);
   cudaStream_t st = (cudaStream_t)stream;
   if (a.mc) {
-    peer_allreduce_mc_kernel<<<ctas, AR_THREADS, 0, st>>>(a);
+    if (wide) peer_allreduce_mc_kernel<AR_THREADS_WIDE><<<ctas, threads, 0, st>>>(a);
+    else peer_allreduce_mc_kernel<AR_THREADS><<<ctas, threads, 0, st>>>(a);
     return check_launch("peer_allreduce_mc");
   }
+#define VQA_AR_LAUNCH(W)                                                                              \
+  do {                                                                                                \
+    if (wide) peer_allreduce_kernel<W, AR_THREADS_WIDE><<<ctas, threads, 0, st>>>(a);                 \
+    else peer_allreduce_kernel<W, AR_THREADS><<<ctas, threads, 0, st>>>(a);                           \
+  } while (0)
   switch (p->world) {
-    case 2: peer_allreduce_kernel<2><<<ctas, AR_THREADS, 0, st>>>(a); break;
-    case 4: peer_allreduce_kernel<4><<<ctas, AR_THREADS, 0, st>>>(a); break;
-    case 8: peer_allreduce_kernel<8><<<ctas, AR_THREADS, 0, st>>>(a); break;
-    default: peer_allreduce_kernel<0><<<ctas, AR_THREADS, 0, st>>>(a); break;
+    case 2: VQA_AR_LAUNCH(2); break;
+    case 4: VQA_AR_LAUNCH(4); break;
+    case 8: VQA_AR_LAUNCH(8); break;
+    default: VQA_AR_LAUNCH(0); break;
   }
+#undef VQA_AR_LAUNCH
   return check_launch("peer_allreduce");
 }

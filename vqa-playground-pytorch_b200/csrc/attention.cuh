@@ -18,6 +18,31 @@ struct FuseGeneric {
     return d.mul(e);
   }
   __device__ __forceinline__ float raw(int64_t b, int64_t i, int64_t c) const { return fuse[(b * N + i) * Ff + c]; }
+  // Row-relative access (the row base is computed once, columns are 32-bit offsets): rowbase = element index of
+  // (b, i, 0); the kernels' inner loops were dominated by 64-bit index arithmetic before.
+  __device__ __forceinline__ void begin_sample(int64_t) {}
+  __device__ __forceinline__ int64_t rowbase(int64_t b, int64_t i) const { return (b * N + i) * Ff; }
+  // value at element index base + off; `col` = its column (only the ODA source needs it)
+  __device__ __forceinline__ float raw_at(int64_t base, int off, int) const { return __ldg(fuse + base + off); }
+  __device__ __forceinline__ float mul_at(int64_t rb, int c) const {
+    const uint64_t e = (uint64_t)(rb + c);
+    if (bits) return ((__ldg(bits + (e >> 3)) >> (e & 7)) & 1u) ? d.scale : 0.0f;
+    return d.mul(e);
+  }
+  // keep flags of the 4 consecutive elements c..c+3 (bit j = element c+j); the multiplier of a kept element is scale()
+  __device__ __forceinline__ uint32_t keep4_at(int64_t rb, int c) const {
+    const uint64_t e = (uint64_t)(rb + c);
+    if (bits) {
+      const uint32_t sh = (uint32_t)(e & 7);
+      uint32_t w = __ldg(bits + (e >> 3));
+      if (sh > 4) w |= (uint32_t)__ldg(bits + (e >> 3) + 1) << 8;      // the 4 bits straddle two bytes
+      return (w >> sh) & 0xFu;
+    }
+    float m[4];
+    d.mul4(e, m);
+    return (m[0] != 0.0f ? 1u : 0u) | (m[1] != 0.0f ? 2u : 0u) | (m[2] != 0.0f ? 4u : 0u) | (m[3] != 0.0f ? 8u : 0u);
+  }
+  __device__ __forceinline__ float scale() const { return d.scale; }
   // multipliers of 4 consecutive elements c..c+3 of row (b,i)
   __device__ __forceinline__ void mul4(int64_t b, int64_t i, int64_t c, float (&m)[4]) const {
     const uint64_t e = (uint64_t)((b * N + i) * Ff + c);
@@ -42,6 +67,15 @@ struct FuseOdaEval {
   __device__ __forceinline__ float raw(int64_t b, int64_t i, int64_t c) const {
     return vl[(b * N + i) * Ff + c] * ql[b * Ff + c];
   }
+  __device__ __forceinline__ int64_t rowbase(int64_t b, int64_t i) const { return (b * N + i) * Ff; }
+  int64_t qoff;                                        // b * Ff of the sample being processed (begin_sample)
+  __device__ __forceinline__ void begin_sample(int64_t b) { qoff = b * Ff; }
+  __device__ __forceinline__ float raw_at(int64_t base, int off, int col) const {
+    return __ldg(vl + base + off) * __ldg(ql + qoff + col);
+  }
+  __device__ __forceinline__ float mul_at(int64_t, int) const { return 1.0f; }
+  __device__ __forceinline__ uint32_t keep4_at(int64_t, int) const { return 0xFu; }
+  __device__ __forceinline__ float scale() const { return 1.0f; }
 };
 
 // softmax over regions of z[N][G] held in shared memory, one warp per glimpse, in place
@@ -71,42 +105,65 @@ __device__ __forceinline__ void softmax_regions_smem(float* z, int N) {
 // elements (one Philox call per quad when the row start is 4-aligned, two otherwise) and issues all of its
 // loads for the row before using them.
 template <class FS>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 4)     // <= 64 registers: 116 left two CTAs per SM and 3.5 waves (ncu r2)
 att_logits_softmax_kernel(FS fs, int64_t N, int64_t Ff, const float* __restrict__ Wc, const float* __restrict__ bc,
                           float* __restrict__ alpha) {
   extern __shared__ float smem[];
   float* w_s = smem;
   float* z_s = smem + G * Ff;
   const int64_t b = blockIdx.x;
-  for (int64_t t = threadIdx.x; t < G * Ff; t += ATT_THREADS) w_s[t] = Wc[t];
+  fs.begin_sample(b);
+  {  // weights -> shared memory, every load of a thread in flight before its first store
+    const int total = (int)(G * Ff);
+    constexpr int WU = 8;
+    float wv[WU];
+#pragma unroll
+    for (int u = 0; u < WU; ++u) {
+      const int t = threadIdx.x + u * ATT_THREADS;
+      wv[u] = t < total ? __ldg(Wc + t) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < WU; ++u) {
+      const int t = threadIdx.x + u * ATT_THREADS;
+      if (t < total) w_s[t] = wv[u];
+    }
+    for (int t = threadIdx.x + WU * ATT_THREADS; t < total; t += ATT_THREADS) w_s[t] = __ldg(Wc + t);
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int QPL = 4;                       // quads per lane per pass: 32 lanes * 4 quads * 4 = 512 elements
   const int S = gridDim.y;
   for (int64_t i = (int64_t)blockIdx.y + (int64_t)warp * S; i < N; i += (int64_t)(ATT_THREADS / 32) * S) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int64_t c0 = 0; c0 < Ff; c0 += 32 * QPL * 4) {
+    const int64_t rb = fs.rowbase(b, i);
+    const int F = (int)Ff;
+    for (int c0 = 0; c0 < F; c0 += 32 * QPL * 4) {
       float f[QPL][4];
+      uint32_t keep[QPL];
 #pragma unroll
       for (int j = 0; j < QPL; ++j) {
-        const int64_t c = c0 + (int64_t)(lane + 32 * j) * 4;
+        const int c = c0 + (lane + 32 * j) * 4;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) f[j][e] = (c + e < Ff) ? fs.raw(b, i, c + e) : 0.0f;
+        for (int e = 0; e < 4; ++e) f[j][e] = (c + e < F) ? fs.raw_at(rb, c + e, c + e) : 0.0f;
       }
 #pragma unroll
+      for (int j = 0; j < QPL; ++j) {      // the mask loads are issued before the first use of anything above
+        const int c = c0 + (lane + 32 * j) * 4;
+        keep[j] = c < F ? fs.keep4_at(rb, c) : 0u;
+      }
+      const float sc = fs.scale();
+#pragma unroll
       for (int j = 0; j < QPL; ++j) {
-        const int64_t c = c0 + (int64_t)(lane + 32 * j) * 4;
-        if (c < Ff) {
-          float mul[4];
-          fs.mul4(b, i, c, mul);
+        const int c = c0 + (lane + 32 * j) * 4;
+        if (c < F) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            if (c + e < Ff) {
-              const float v = f[j][e] * mul[e];
+            if (c + e < F) {
+              const float v = (keep[j] >> e) & 1u ? f[j][e] * sc : 0.0f;
               a0 = fmaf(w_s[c + e], v, a0);
-              a1 = fmaf(w_s[Ff + c + e], v, a1);
-              a2 = fmaf(w_s[2 * Ff + c + e], v, a2);
-              a3 = fmaf(w_s[3 * Ff + c + e], v, a3);
+              a1 = fmaf(w_s[F + c + e], v, a1);
+              a2 = fmaf(w_s[2 * F + c + e], v, a2);
+              a3 = fmaf(w_s[3 * F + c + e], v, a3);
             }
           }
         }
@@ -164,6 +221,7 @@ att_logits_softmax_bwd_kernel(FS fs, int64_t B, int64_t N, int64_t Ff, const flo
     for (int g = 0; g < G; ++g) w[g] = Wc[g * Ff + c];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    fs.begin_sample(b);
     __syncthreads();
     for (int64_t t = threadIdx.x; t < N * G; t += ATT_THREADS) {
       dz_s[t] = dalpha[b * N * G + t];
@@ -192,12 +250,14 @@ att_logits_softmax_bwd_kernel(FS fs, int64_t B, int64_t N, int64_t Ff, const flo
     if (active) {
       float dq = 0.0f;
       constexpr int U = 6;
-      for (int64_t i0 = 0; i0 < N; i0 += U) {
+      const int64_t sb = fs.rowbase(b, 0) + c;          // element (b, 0, c); rows are Ff apart (32-bit offsets below)
+      const int F = (int)Ff, Ni = (int)N;
+      for (int i0 = 0; i0 < Ni; i0 += U) {
         float fr[U], mu[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) fr[u] = (i0 + u < N) ? fs.raw(b, i0 + u, c) : 0.0f;
+        for (int u = 0; u < U; ++u) fr[u] = (i0 + u < Ni) ? fs.raw_at(sb, (i0 + u) * F, (int)c) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < U; ++u) mu[u] = (i0 + u < N) ? fs.mul(b, i0 + u, c) : 0.0f;
+        for (int u = 0; u < U; ++u) mu[u] = (i0 + u < Ni) ? fs.mul_at(sb, (i0 + u) * F) : 0.0f;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int64_t i = i0 + u;

@@ -137,6 +137,7 @@ class DataParallelEngine(GradSink):
         alloc = None
         if self.world_size > 1 and params[0].is_cuda and allreduce in ("auto", "peer"):
             alloc = self._symmetric_alloc(params[0].device, strict=allreduce == "peer")
+        num_buckets = int(os.environ.get("VQA_BUCKETS", num_buckets))
         super().__init__(params, model.MODEL, num_buckets, alloc=alloc)
         if alloc is not None and self._symm is not None:
             self._rendezvous_peers()
@@ -238,6 +239,7 @@ class DataParallelEngine(GradSink):
         pr.offset, pr.count = lo, hi - lo
         pr.max_ctas, pr.spin_limit_ms = self.peer_max_ctas, self.peer_spin_ms
         pr.multicast = self.peer["multicast"] or None
+        pr.cta_threads = int(os.environ.get("VQA_PEER_THREADS", "0"))
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(_lib.lib().vqa_peer_allreduce_f32(C.byref(pr), stream), "vqa_peer_allreduce_f32")
 

@@ -76,7 +76,9 @@ cor_compound_fwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const
 
 // One CTA per sample (deterministic ds reduction).
 constexpr int CMPB_THREADS = 512;
-__global__ void __launch_bounds__(CMPB_THREADS)
+// __launch_bounds__(.., 2): <= 64 registers, two CTAs per SM, so that the 256 samples of the benchmark batch are ONE wave
+// (ncu r2: 126 registers, one CTA per SM, two waves, 37 % of the HBM rate).
+__global__ void __launch_bounds__(CMPB_THREADS, 2)
 cor_compound_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* __restrict__ pooled,
                         const float* __restrict__ alpha, const float* __restrict__ g1, const float* __restrict__ g2,
                         const float* __restrict__ dv2, float* __restrict__ dg1, float* __restrict__ dg2,
@@ -84,40 +86,42 @@ cor_compound_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const
                         const uint8_t* __restrict__ keep_bits, float keep_scale, const float* __restrict__ pool_alpha,
                         const float* __restrict__ pool_dp) {
   __shared__ float red[CMPB_THREADS / 32];
-  extern __shared__ float al2_s[];                  // [N*G] pool_alpha of this sample (fused dv2 finish)
+  extern __shared__ __align__(16) float cmpb_smem[];
+  float* dp2_s = cmpb_smem;                         // [G][D] pool_dp of this sample (kept out of the register budget)
+  float* al2_s = cmpb_smem + (pool_alpha ? G * D : 0);   // [N*G] pool_alpha of this sample (fused dv2 finish)
   const int64_t b = blockIdx.x;
   if (pool_alpha) {
     for (int64_t t = threadIdx.x; t < N * G; t += CMPB_THREADS) al2_s[t] = pool_alpha[b * N * G + t];
+    for (int64_t t = (int64_t)threadIdx.x * 4; t < G * D; t += CMPB_THREADS * 4)
+      *reinterpret_cast<float4*>(dp2_s + t) = __ldg(reinterpret_cast<const float4*>(pool_dp + b * G * D + t));
     __syncthreads();
   }
   float s = 0.0f;
   for (int64_t i = 0; i < N; ++i) s += __ldg(&alpha[(b * N + i) * G]);
   float ds = 0.0f;
-  for (int64_t c = (int64_t)threadIdx.x * 4; c < D; c += CMPB_THREADS * 4) {
+  const int Ni = (int)N, Di = (int)D;                 // 32-bit row / column offsets below (one sample is N*D < 2^31 floats)
+  for (int c = (int)threadIdx.x * 4; c < Di; c += CMPB_THREADS * 4) {
     float4 dbar = make_float4(0.f, 0.f, 0.f, 0.f), xd = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* xb = x + b * N * D + c;
     const float* db = dv2 + b * N * D + c;
-    float4 dp2[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      dp2[g] = pool_alpha ? __ldg(reinterpret_cast<const float4*>(pool_dp + (b * G + g) * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const uint8_t* kb = keep_bits ? keep_bits + ((b * N * D + c) >> 3) : nullptr;      // D % 8 == 0: rows are D/8 bytes apart
     const uint32_t ksh = (uint32_t)(c & 4);
-    constexpr int U = 6;                             // rows in flight per thread: every load of a batch before its first use
-    for (int64_t j0 = 0; j0 < N; j0 += U) {
+    const int Db = Di >> 3;
+    constexpr int U = 3;                             // rows in flight per thread: every load of a batch before its first use
+    for (int j0 = 0; j0 < Ni; j0 += U) {
       float4 xs[U], ds[U];
       uint32_t ns[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const bool in = j0 + u < N;
-        xs[u] = in ? ld_stream4(xb + (j0 + u) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ds[u] = in ? ld_stream4(db + (j0 + u) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ns[u] = (in && kb) ? (uint32_t)__ldg(kb + (j0 + u) * (D >> 3)) >> ksh : 0xFu;
+        const bool in = j0 + u < Ni;
+        xs[u] = in ? ld_stream4(xb + (j0 + u) * Di) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ds[u] = in ? ld_stream4(db + (j0 + u) * Di) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ns[u] = (in && kb) ? (uint32_t)__ldg(kb + (j0 + u) * Db) >> ksh : 0xFu;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-      const int64_t j = j0 + u;
-      if (j >= N) break;
+      const int j = j0 + u;
+      if (j >= Ni) break;
       const float4 xv = xs[u];
       float4 dv = ds[u];
       if (kb) {                                     // the raw GEMM term gets compress_v2's input-dropout mask here
@@ -130,8 +134,9 @@ cor_compound_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const
         const float av[G] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          dv.x = fmaf(av[g], dp2[g].x, dv.x); dv.y = fmaf(av[g], dp2[g].y, dv.y);
-          dv.z = fmaf(av[g], dp2[g].z, dv.z); dv.w = fmaf(av[g], dp2[g].w, dv.w);
+          const float4 dp = *reinterpret_cast<const float4*>(dp2_s + g * Di + c);
+          dv.x = fmaf(av[g], dp.x, dv.x); dv.y = fmaf(av[g], dp.y, dv.y);
+          dv.z = fmaf(av[g], dp.z, dv.z); dv.w = fmaf(av[g], dp.w, dv.w);
         }
       }
       dbar.x += dv.x; dbar.y += dv.y; dbar.z += dv.z; dbar.w += dv.w;
@@ -190,7 +195,13 @@ extern "C" int vqa_cor_compound_bwd(const vqa_cor_compound_bwd_params* p, void* 
   VQA_REQUIRE(!p->dv2_keep_bits || p->D % 8 == 0, "vqa_cor_compound_bwd: dv2_keep_bits needs D %% 8 == 0");
   if (p->B == 0) return VQA_OK;
   KProf kp_(stream, "cor_compound_bwd", "hbm", 8.0 * (double)p->B * p->N * p->D);
-  const size_t smem = p->dv2_pool_alpha ? (size_t)p->N * G * sizeof(float) : 0;
+  const size_t smem = p->dv2_pool_alpha ? (size_t)(p->N * G + G * p->D) * sizeof(float) : 0;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(cor_compound_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("vqa_cor_compound_bwd: cannot reserve %zu bytes of shared memory", smem);
+    return VQA_ECUDA;
+  }
   cor_compound_bwd_kernel<<<(unsigned)p->B, CMPB_THREADS, smem, (cudaStream_t)stream>>>(
       p->N, p->D, p->x, p->pooled, p->alpha, p->g1, p->g2, p->dv2, p->dg1, p->dg2, p->dpooled, p->dalpha0_ext,
       p->dv2_keep_bits, p->dv2_keep_bits ? p->dv2_keep_scale : 1.0f, p->dv2_pool_alpha, p->dv2_pool_dpooled);

@@ -79,14 +79,22 @@ int launch_pool_fwd(int64_t B, int64_t N, int64_t D, const float* x, const float
 // the warp count so that one CTA covers a whole sample when N <= 48 (no nearly-empty tail CTA).
 constexpr int POOL_BWD_RW = 4;
 constexpr int POOL_BWD_MAX_WARPS = 12;
-__global__ void __launch_bounds__(POOL_BWD_MAX_WARPS * 32)
+// The sample's dpooled [G][D] (32 KB at D = 2048) is staged in shared memory once per CTA: holding the 8 float4 of it a
+// lane needs per iteration in registers made the kernel a 128-register one (one 9-warp CTA per SM, two waves at batch
+// 256, 38 % of the HBM rate in ncu r2); from shared memory it is ~70 registers and three CTAs per SM.
+template <bool DX>      // DX = false: only dalpha is produced (x is a graph input, or its pooling gradient is added elsewhere)
+__global__ void __launch_bounds__(POOL_BWD_MAX_WARPS * 32, DX ? 2 : 3)
 pool_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* __restrict__ alpha,
                 const float* __restrict__ dpooled, const float* __restrict__ dalpha0_ext,
                 const float* __restrict__ dalpha_ext, float* __restrict__ dalpha, float* __restrict__ dx,
                 int accumulate_x) {
   constexpr int RW = POOL_BWD_RW;
+  extern __shared__ __align__(16) float dp_s[];       // [G][D]
   const int64_t b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t t = (int64_t)threadIdx.x * 4; t < G * D; t += (int64_t)blockDim.x * 4)
+    *reinterpret_cast<float4*>(dp_s + t) = __ldg(reinterpret_cast<const float4*>(dpooled + b * G * D + t));
+  __syncthreads();
   const int64_t i0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * RW;
   if (i0 >= N) return;
   const int nr = N - i0 < RW ? (int)(N - i0) : RW;
@@ -96,39 +104,41 @@ pool_bwd_kernel(int64_t N, int64_t D, const float* __restrict__ x, const float* 
   for (int r = 0; r < RW; ++r)
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      a[r][g] = r < nr ? alpha[(b * N + i0 + r) * G + g] : 0.0f;
+      a[r][g] = (DX && r < nr) ? alpha[(b * N + i0 + r) * G + g] : 0.0f;
       dot[r][g] = 0.0f;
     }
   const float* xr = x + (b * N + i0) * D;
-  const float* dp = dpooled + b * G * D;
-  constexpr int CU = 2;                              // column chunks in flight per lane
-  for (int64_t c0 = lane * 4; c0 < D; c0 += 128 * CU) {
+  const int Di = (int)D;
+  constexpr int CU = 1;                              // column chunks in flight per lane (registers: 3 CTAs per SM instead)
+  for (int c0 = lane * 4; c0 < Di; c0 += 128 * CU) {
     float4 xv[CU][RW];
-    float4 d[CU][G];
 #pragma unroll
     for (int u = 0; u < CU; ++u) {
-      const int64_t c = c0 + u * 128;
+      const int c = c0 + u * 128;
 #pragma unroll
       for (int r = 0; r < RW; ++r)
-        xv[u][r] = (r < nr && c < D) ? ld_stream4(xr + r * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int g = 0; g < G; ++g)
-        d[u][g] = c < D ? __ldg(reinterpret_cast<const float4*>(dp + g * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[u][r] = (r < nr && c < Di) ? ld_stream4(xr + r * Di + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < CU; ++u) {
-      const int64_t c = c0 + u * 128;
+      const int c = c0 + u * 128;
+      float4 d[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        d[g] = c < Di ? *reinterpret_cast<const float4*>(dp_s + g * Di + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < RW; ++r) {
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const float4 dg = d[u][g], xr4 = xv[u][r];
+          const float4 dg = d[g], xr4 = xv[u][r];
           dot[r][g] = fmaf(xr4.x, dg.x, fmaf(xr4.y, dg.y, fmaf(xr4.z, dg.z, fmaf(xr4.w, dg.w, dot[r][g]))));
-          o.x = fmaf(a[r][g], dg.x, o.x); o.y = fmaf(a[r][g], dg.y, o.y);
-          o.z = fmaf(a[r][g], dg.z, o.z); o.w = fmaf(a[r][g], dg.w, o.w);
+          if (DX) {
+            o.x = fmaf(a[r][g], dg.x, o.x); o.y = fmaf(a[r][g], dg.y, o.y);
+            o.z = fmaf(a[r][g], dg.z, o.z); o.w = fmaf(a[r][g], dg.w, o.w);
+          }
         }
-        if (dx && r < nr && c < D) {
+        if (DX && dx && r < nr && c < Di) {
           float4* dst = reinterpret_cast<float4*>(dx + (b * N + i0 + r) * D + c);
           if (accumulate_x) {
             const float4 old = *dst;
@@ -164,8 +174,15 @@ int launch_pool_bwd(int64_t B, int64_t N, int64_t D, const float* x, const float
   if (warps > POOL_BWD_MAX_WARPS) warps = 8;
   dim3 grid((unsigned)cdiv(N, warps * POOL_BWD_RW), (unsigned)B);
   KProf kp_(st, "pool_bwd", "hbm", 4.0 * ((double)B * N * D * (dx ? 2 : 1) + (double)B * G * D));
-  pool_bwd_kernel<<<grid, (unsigned)(warps * 32), 0, st>>>(N, D, x, alpha, dpooled, dalpha0_ext, dalpha_ext, dalpha, dx,
-                                                           accumulate_x);
+  const size_t smem = (size_t)G * D * sizeof(float);
+  if (smem > 200 * 1024) { set_error("pool_bwd: D=%lld too large for the shared dpooled stage", (long long)D); return VQA_EINVAL; }
+  auto kern = dx ? pool_bwd_kernel<true> : pool_bwd_kernel<false>;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("pool_bwd: cannot reserve %zu bytes of shared memory", smem);
+    return VQA_ECUDA;
+  }
+  kern<<<grid, (unsigned)(warps * 32), smem, st>>>(N, D, x, alpha, dpooled, dalpha0_ext, dalpha_ext, dalpha, dx, accumulate_x);
   return check_launch("pool_bwd");
 }
 

@@ -364,7 +364,8 @@ int vqa_cor_compound_bwd(const vqa_cor_compound_bwd_params* p, void* stream);
  * produced in registers with its keep flag (Philox index ((b*N+i)*N+j)*H+k).  Train mode needs a scratch buffer of
  * vqa_oda_pair_attn_workspace_bytes(B,N,H): the 1-bit-per-element keep cache of the dropped tensor
  * (vqa_dropout_bits layout, drawn ONCE per step) followed by the forward's partial logits.  The forward fills it,
- * the backward reads the keep bits back: pass the SAME buffer to both calls.
+ * the backward reads the keep bits back: pass the SAME buffer to both calls.  Train mode handles N <= 144 regions
+ * (a CTA owns all regions of a feature range; the eval path has no such limit).
  */
 size_t vqa_oda_pair_attn_workspace_bytes(int64_t B, int64_t N, int64_t H);
 typedef struct {

@@ -20,7 +20,7 @@ def test_two_rank_graph_step_matches_one_gpu_global_batch(cuda, transport):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", {"peer": "29731", "peer-p2p": "29735", "nccl": "29733"}[transport], os.path.join(ROOT, "tests", "dp_worker.py")]
     env = dict(os.environ, VQA_ALLREDUCE=transport.split("-")[0], VQA_PEER_SPIN_MS="20000",
-               VQA_PEER_MC="0" if transport == "peer-p2p" else "1")
+               VQA_PEER_MC="0" if transport == "peer-p2p" else "1")      # "peer": force the NVLS path even at 2 ranks
     transport = transport.split("-")[0]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and "DP_OK transport %s" % transport in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])

@@ -213,8 +213,11 @@ class DataParallelEngine(GradSink):
             self._handles = (hb, hs)
             self.peer = {"buffers": [int(x) for x in hb.buffer_ptrs], "signals": [int(x) for x in hs.buffer_ptrs]}
             # NVLS: the multicast mapping of the gradient buffer, when the fabric offers one (all ranks or none)
+            # measured (profiles/r2_experiments.md): the in-switch reduction wins at 8 ranks (half the NVLink bytes) and
+            # loses to plain peer loads/stores at 2 (no traffic advantage): VQA_PEER_MC = auto (>= 4 ranks) | 1 | 0
             mc = 0
-            if os.environ.get("VQA_PEER_MC", "1") != "0":
+            want_mc = os.environ.get("VQA_PEER_MC", "auto")
+            if want_mc == "1" or (want_mc == "auto" and self.world_size >= 4):
                 try:
                     mc = int(hb.multicast_ptr or 0)
                 except Exception:

@@ -107,3 +107,24 @@ def test_completion_order_matches_the_library_groups():
         for g, members in enumerate(COMPLETION_ORDER[name]):
             assert all(tab[i] == g for i in members), (name, g)
     assert L.vqa_grad_groups(0, (C.c_int * 10)(), 10) == -1
+
+
+def test_vector_ranges_tile_the_padded_buffer_in_16_byte_units():
+    """The peer transport moves 16-byte vectors: bucket boundaries move DOWN to a multiple of 4 floats (the <= 3 elements
+    that change sides belong to a parameter that is complete by then and simply travel with the later bucket), the end
+    moves up into the padding; the ranges still tile the buffer, in order."""
+    from vqa_playground_pytorch_b200.parallel import GradSink
+    for name, C in (("CoR2", 2000), ("ODA", 3000)):
+        m = FakeModel(name, C)
+        sink = GradSink(m.core_parameters(), name)
+        total = sink.flat.numel()
+        pos = 0
+        for (lo, hi), (lo4, hi4) in zip(sink.bucket_ranges, sink.vector_ranges):
+            assert lo4 == pos and lo4 % 4 == 0 and hi4 % 4 == 0 and hi4 > lo4
+            assert lo - 3 <= lo4 <= lo and (hi - 3 <= hi4 <= hi or hi == total)
+            pos = hi4
+        assert total <= pos <= total + 3
+        # the late groups (TAIL_GROUPS) are alone in the last bucket
+        from vqa_playground_pytorch_b200.parallel import COMPLETION_ORDER, TAIL_GROUPS
+        g0, g1 = sink.bucket_groups[-1]
+        assert g1 == len(COMPLETION_ORDER[name]) and g1 - g0 == TAIL_GROUPS[name]

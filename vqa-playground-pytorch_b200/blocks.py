@@ -216,12 +216,18 @@ class SkipThoughts(nn.Module):
         self.embedding = nn.Embedding(num_embeddings=len(vocab_list), embedding_dim=620, padding_idx=0)
         self.gru = BayesianGRU(input_size=620, hidden_size=2400, dropout=0.25, return_last=return_last, af=af)
         self.fixed_seed = None
+        self.graph_capture = False      # set by the owning CoreModel while engine.GraphedStep captures / replays it
 
     def forward(self, x, return_hidden=False):
         c = self.gru.gru_cell
         p = float(self.gru.dropout) if self.training else 0.0
         seed = 0
         if p > 0.0:
+            if self.graph_capture:
+                # the sequence-tied masks are drawn from a host-side key: a captured step would replay ONE mask forever
+                raise NotImplementedError("SkipThoughts: train-mode dropout inside a CUDA-graph-captured step is not "
+                                          "supported (the encoder's Philox key is host-resident); run the encoder "
+                                          "eagerly in front of the graphed core, or in eval mode")
             seed = self.fixed_seed if self.fixed_seed is not None else ops.next_seed()
         out = ops.BayesianGruFn.apply(x, self.embedding.weight, c.weight_ir.weight, c.weight_ir.bias, c.weight_ii.weight,
                                       c.weight_ii.bias, c.weight_in.weight, c.weight_in.bias, c.weight_hr.weight,

@@ -42,6 +42,8 @@ class CoreModel(nn.Module):
 
     def _run_core(self, sample):
         v = sample['v']
+        if hasattr(self.seq2vec, "graph_capture"):
+            self.seq2vec.graph_capture = bool(self.use_seed_device)
         q = self.seq2vec(sample['q_idxes'])
         if v.numel() % (self.num_regions * 2048) != 0:
             raise ValueError("sample['v'] with %d elements cannot be viewed as [-1, %d, 2048]" %
